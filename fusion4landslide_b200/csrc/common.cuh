@@ -1,0 +1,158 @@
+// Shared device helpers for libf4l_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/f4l_b200.h"
+
+#define F4L_WARP 32
+#define F4L_FULL 0xffffffffu
+
+// ---- host-side error plumbing -------------------------------------------------------------
+void f4l_set_error(const char* fmt, ...);
+int f4l_check_launch(const char* what);
+
+#define F4L_REQUIRE(cond, msg)                       \
+    do {                                             \
+        if (!(cond)) {                               \
+            f4l_set_error("%s: %s", __func__, msg);  \
+            return F4L_E_ARG;                        \
+        }                                            \
+    } while (0)
+
+static inline int f4l_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- warp reductions ----------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F4L_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F4L_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F4L_FULL, v, o);
+    return v;
+}
+
+// segment bounds: CSR when count == nullptr
+__device__ __forceinline__ void seg_bounds(const int32_t* start, const int32_t* count, int q,
+                                           int& s, int& n) {
+    s = start[q];
+    n = count ? count[q] : (start[q + 1] - s);
+}
+
+// ---- 3x3 SVD, fp64, one-sided Jacobi (Hestenes) ---------------------------------------------
+// H (row-major) = U diag(S) V^T with S descending (torch.svd convention).  U, V row-major.
+// Rank-deficient columns of U are completed to an orthonormal basis.
+__device__ inline void svd3x3(const double H[9], double U[9], double S[3], double V[9]) {
+    double a[3][3];  // a[c][r]: column c
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) a[c][r] = H[r * 3 + c];
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // v[c][r]
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0;
+            const int q = (pq == 0) ? 1 : 2;
+            double alpha = a[p][0] * a[p][0] + a[p][1] * a[p][1] + a[p][2] * a[p][2];
+            double beta = a[q][0] * a[q][0] + a[q][1] * a[q][1] + a[q][2] * a[q][2];
+            double gamma = a[p][0] * a[q][0] + a[p][1] * a[q][1] + a[p][2] * a[q][2];
+            if (gamma == 0.0 || fabs(gamma) <= 1.2e-16 * sqrt(alpha * beta)) continue;
+            rotated = true;
+            double zeta = (beta - alpha) / (2.0 * gamma);
+            double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            double c = 1.0 / sqrt(1.0 + t * t);
+            double s = c * t;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double ap = a[p][r], aq = a[q][r];
+                a[p][r] = c * ap - s * aq;
+                a[q][r] = s * ap + c * aq;
+                double vp = v[p][r], vq = v[q][r];
+                v[p][r] = c * vp - s * vq;
+                v[q][r] = s * vp + c * vq;
+            }
+        }
+        if (!rotated) break;
+    }
+    double sv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sv[c] = sqrt(a[c][0] * a[c][0] + a[c][1] * a[c][1] + a[c][2] * a[c][2]);
+    // sort columns by singular value, descending (3-element network)
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (sv[o0] < sv[o1]) { int tmp = o0; o0 = o1; o1 = tmp; }
+    if (sv[o1] < sv[o2]) { int tmp = o1; o1 = o2; o2 = tmp; }
+    if (sv[o0] < sv[o1]) { int tmp = o0; o0 = o1; o1 = tmp; }
+    const int ord[3] = {o0, o1, o2};
+    double u[3][3];
+    const double tiny = 1e-300;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int k = ord[c];
+        S[c] = sv[k];
+        double inv = sv[k] > tiny ? 1.0 / sv[k] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            u[c][r] = a[k][r] * inv;
+            V[r * 3 + c] = v[k][r];
+        }
+    }
+    // complete U for (numerically) zero singular values
+    const double rel = 1e-14 * S[0];
+    if (!(S[0] > tiny)) {
+        u[0][0] = 1; u[0][1] = 0; u[0][2] = 0;
+        u[1][0] = 0; u[1][1] = 1; u[1][2] = 0;
+        u[2][0] = 0; u[2][1] = 0; u[2][2] = 1;
+    } else {
+        if (!(S[1] > rel)) {
+            // any unit vector orthogonal to u0
+            int m = 0;
+            if (fabs(u[0][1]) < fabs(u[0][m])) m = 1;
+            if (fabs(u[0][2]) < fabs(u[0][m])) m = 2;
+            double e[3] = {0, 0, 0};
+            e[m] = 1.0;
+            double d = u[0][m];
+            double w0 = e[0] - d * u[0][0], w1 = e[1] - d * u[0][1], w2 = e[2] - d * u[0][2];
+            double nrm = rsqrt(w0 * w0 + w1 * w1 + w2 * w2);
+            u[1][0] = w0 * nrm; u[1][1] = w1 * nrm; u[1][2] = w2 * nrm;
+        }
+        if (!(S[2] > rel)) {
+            u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
+            u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
+            u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) U[r * 3 + c] = u[c][r];
+}
+
+__device__ __forceinline__ double det3(const double M[9]) {
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) +
+           M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// R = V diag(1,1,d) U^T.  mode 0: d = sign(det(V U^T)) (weighted_svd.py:114); mode 1: raw det
+// (functions.py:73-77); mode 2: Eigen::umeyama S(2) = -1 iff det(U) det(V) < 0 else +1.
+__device__ inline void rotation_from_svd(const double U[9], const double V[9], int mode, double R[9]) {
+    double dd = det3(U) * det3(V);
+    double d;
+    if (mode == 0) d = (dd > 0.0) ? 1.0 : ((dd < 0.0) ? -1.0 : 0.0);
+    else if (mode == 1) d = dd;
+    else d = (dd < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            R[i * 3 + j] = V[i * 3 + 0] * U[j * 3 + 0] + V[i * 3 + 1] * U[j * 3 + 1] + d * V[i * 3 + 2] * U[j * 3 + 2];
+}

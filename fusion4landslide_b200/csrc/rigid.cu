@@ -1,0 +1,178 @@
+// K-d segmented weighted Kabsch / Procrustes, K-f transform apply, K-c rigidity check and
+// segmented median.  One warp per segment for the reductions: a segment's points are read from
+// HBM exactly once, moments are accumulated in fp64 about a per-segment pivot, the 3x3 SVD runs
+// in fp64 on lane 0.
+#include "common.cuh"
+#include "rigid_device.cuh"
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_segmented_kabsch(const float* __restrict__ src, const float* __restrict__ tgt,
+                   const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
+                   const float* __restrict__ w, const int32_t* __restrict__ seg_start,
+                   const int32_t* __restrict__ seg_count, int Q, double eps, float weight_thresh,
+                   int variant, float* __restrict__ R, float* __restrict__ t,
+                   double* __restrict__ T64, float* __restrict__ res, uint8_t* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    int s0, n;
+    seg_bounds(seg_start, seg_count, q, s0, n);
+    double Rm[9], tv[3];
+    bool bad = warp_fit_segment(src, tgt, src_idx, tgt_idx, w, s0, n, eps, weight_thresh, variant, lane, Rm, tv);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[(size_t)q * 9 + i] = (float)Rm[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t[(size_t)q * 3 + i] = (float)tv[i];
+        if (T64) {
+            double* T = T64 + (size_t)q * 16;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                T[i * 4 + 0] = Rm[i * 3 + 0]; T[i * 4 + 1] = Rm[i * 3 + 1]; T[i * 4 + 2] = Rm[i * 3 + 2];
+                T[i * 4 + 3] = tv[i];
+            }
+            T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+        }
+        if (flag) flag[q] = bad ? 1 : 0;
+    }
+    if (res) {
+        for (int i = lane; i < n; i += 32) {
+            const int k = s0 + i;
+            double sx, sy, sz, tx, ty, tz;
+            load_pt(src, src_idx, k, sx, sy, sz);
+            load_pt(tgt, tgt_idx, k, tx, ty, tz);
+            double rx = Rm[0] * sx + Rm[1] * sy + Rm[2] * sz + tv[0] - tx;
+            double ry = Rm[3] * sx + Rm[4] * sy + Rm[5] * sz + tv[1] - ty;
+            double rz = Rm[6] * sx + Rm[7] * sy + Rm[8] * sz + tv[2] - tz;
+            res[k] = (float)sqrt(rx * rx + ry * ry + rz * rz);
+        }
+    }
+}
+
+extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const int32_t* src_idx,
+                                    const int32_t* tgt_idx, const float* w, const int32_t* seg_start,
+                                    const int32_t* seg_count, int32_t Q, float eps, float weight_thresh,
+                                    int variant, float* R, float* t, double* T64, float* res,
+                                    uint8_t* flag, void* stream) {
+    F4L_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return F4L_OK;
+    F4L_REQUIRE(src && tgt && seg_start && R && t, "null pointer");
+    F4L_REQUIRE(variant == F4L_KABSCH_PROCRUSTES || variant == F4L_KABSCH_F2S3, "unknown variant");
+    const int warps = 4;
+    k_segmented_kabsch<<<f4l_div_up(Q, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q, (double)eps, weight_thresh, variant, R, t,
+        T64, res, flag);
+    return f4l_check_launch("f4l_segmented_kabsch");
+}
+
+// ------------------------------------------------------------------------------------------
+// K-f: one warp per segment, rows [p | R p + t] in f32 (the reference applies T in f32,
+// base.py:3373); fp64 accumulate then round once.
+__global__ void __launch_bounds__(256)
+k_apply_transforms(const float* __restrict__ pts, const int32_t* __restrict__ idx,
+                   const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_count,
+                   const int32_t* __restrict__ out_start, const uint8_t* __restrict__ seg_skip, int Q,
+                   const float* __restrict__ T, int inverse, float* __restrict__ dvf,
+                   float* __restrict__ mag) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    if (seg_skip && seg_skip[q]) return;
+    int s0, n;
+    seg_bounds(seg_start, seg_count, q, s0, n);
+    const int o0 = out_start ? out_start[q] : s0;
+    const float* Tq = T + (size_t)q * 16;
+    double Rm[9], tv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        Rm[i * 3 + 0] = Tq[i * 4 + 0]; Rm[i * 3 + 1] = Tq[i * 4 + 1]; Rm[i * 3 + 2] = Tq[i * 4 + 2];
+        tv[i] = Tq[i * 4 + 3];
+    }
+    for (int i = lane; i < n; i += 32) {
+        double x, y, z;
+        load_pt(pts, idx, s0 + i, x, y, z);
+        float2* row = reinterpret_cast<float2*>(dvf + (size_t)(o0 + i) * 6);
+        float ox, oy, oz;
+        if (!inverse) {
+            ox = (float)(Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0]);
+            oy = (float)(Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1]);
+            oz = (float)(Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2]);
+            row[0] = make_float2((float)x, (float)y);
+            row[1] = make_float2((float)z, ox);
+            row[2] = make_float2(oy, oz);
+        } else {
+            // f32 subtraction first, as base.py:3389-3390 does: R^T (p - t)
+            double dx = (double)((float)x - (float)tv[0]);
+            double dy = (double)((float)y - (float)tv[1]);
+            double dz = (double)((float)z - (float)tv[2]);
+            ox = (float)(Rm[0] * dx + Rm[3] * dy + Rm[6] * dz);
+            oy = (float)(Rm[1] * dx + Rm[4] * dy + Rm[7] * dz);
+            oz = (float)(Rm[2] * dx + Rm[5] * dy + Rm[8] * dz);
+            row[0] = make_float2(ox, oy);
+            row[1] = make_float2(oz, (float)x);
+            row[2] = make_float2((float)y, (float)z);
+        }
+        if (mag) {
+            float ex = ox - (float)x, ey = oy - (float)y, ez = oz - (float)z;
+            mag[o0 + i] = sqrtf(ex * ex + ey * ey + ez * ez);
+        }
+    }
+}
+
+extern "C" int f4l_apply_transforms(const float* pts, const int32_t* idx, const int32_t* seg_start,
+                                    const int32_t* seg_count, const int32_t* out_start,
+                                    const uint8_t* seg_skip, int32_t Q, const float* T, int inverse,
+                                    float* dvf, float* mag, void* stream) {
+    F4L_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return F4L_OK;
+    F4L_REQUIRE(pts && seg_start && T && dvf, "null pointer");
+    const int warps = 8;
+    k_apply_transforms<<<f4l_div_up(Q, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        pts, idx, seg_start, seg_count, out_start, seg_skip, Q, T, inverse, dvf, mag);
+    return f4l_check_launch("f4l_apply_transforms");
+}
+
+// ------------------------------------------------------------------------------------------
+// K-c rigidity check: one CTA per segment, points staged in shared memory (f32), the K(K-1)/2
+// pair terms are spread over the CTA's threads.
+#define RIG_MAX_SMEM_PTS 2048
+__global__ void __launch_bounds__(256)
+k_rigidity(const float* __restrict__ src, const float* __restrict__ tgt,
+           const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
+           const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_count, int Q,
+           float thres, float* __restrict__ ratio_inlier, float* __restrict__ dist_mean) {
+    extern __shared__ float sm[];
+    __shared__ double red_sum[8];
+    __shared__ unsigned long long red_cnt[8];
+    const int q = blockIdx.x;
+    int s0, n;
+    seg_bounds(seg_start, seg_count, q, s0, n);
+    double sum;
+    unsigned long long cnt;
+    block_rigidity(src, tgt, src_idx, tgt_idx, s0, n, thres, sm, red_sum, red_cnt, sum, cnt);
+    if (threadIdx.x == 0) {
+        double num_ele = 0.5 * (double)n * (double)(n - 1);
+        // base.py:3315-3316: count over the full KxK matrix (2*pairs + K diagonal zeros) minus K
+        dist_mean[q] = (float)(sum / num_ele);
+        ratio_inlier[q] = (float)((double)(2ull * cnt) / (num_ele * 2.0));
+    }
+}
+
+extern "C" int f4l_rigidity_check(const float* src, const float* tgt, const int32_t* src_idx,
+                                  const int32_t* tgt_idx, const int32_t* seg_start,
+                                  const int32_t* seg_count, int32_t Q, float thres_dist_diff,
+                                  float* ratio_inlier, float* dist_mean, void* stream) {
+    F4L_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return F4L_OK;
+    F4L_REQUIRE(src && tgt && seg_start && ratio_inlier && dist_mean, "null pointer");
+    size_t smem = (size_t)RIG_MAX_SMEM_PTS * 6 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_rigidity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_rigidity<<<Q, 256, smem, (cudaStream_t)stream>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count, Q,
+                                                      thres_dist_diff, ratio_inlier, dist_mean);
+    return f4l_check_launch("f4l_rigidity_check");
+}

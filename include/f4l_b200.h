@@ -1,0 +1,234 @@
+/*
+ * f4l_b200.h -- C ABI of libf4l_b200.so: the B200 (sm_100a) implementation of the patch-wise 3D
+ * correspondence and rigid-estimation hot path of gseg-ethz/fusion4landslide.
+ *
+ * The reference has no FFI for this path (it is Python calling torch / Open3D / scipy), so each
+ * entry point names the reference Python function or code range it replaces
+ * (paths relative to the reference tree; "base.py" = src/coarse_to_fine_matching_base.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless its name starts with
+ *     `h_`; buffers are caller-owned, inputs are never written, outputs are fully written
+ *   - point arrays are row-major (n,3); f32 unless the name ends in 64
+ *   - segments ("patches") are CSR: ptr[Q+1] int32 offsets into a packed item array.  Where a
+ *     pair (start,count) is taken instead, segment q owns items [start[q], start[q]+count[q])
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises the device, no host-visible scalars are produced unless documented
+ *   - workspaces are caller-provided; f4l_*_workspace_bytes() gives the size (host function)
+ *   - return value: 0 = ok, <0 = error (F4L_E_*); f4l_last_error() gives the message of the
+ *     last failing call on this thread
+ *   - there is NO CPU fallback: every function fails with F4L_E_CUDA if no sm_100 device/kernel
+ *     image is usable
+ */
+#ifndef F4L_B200_H
+#define F4L_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F4L_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define F4L_API __attribute__((visibility("default")))
+#else
+#define F4L_API
+#endif
+
+#define F4L_OK 0
+#define F4L_E_ARG (-1)   /* bad argument (null pointer, negative size, unsupported k / D ...) */
+#define F4L_E_CUDA (-2)  /* CUDA runtime error; message in f4l_last_error() */
+#define F4L_E_WORKSPACE (-3) /* workspace too small */
+
+F4L_API int f4l_abi_version(void);
+F4L_API const char* f4l_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (d) Weighted Kabsch / Procrustes, one fit per segment.                           kernel K-d
+ * Replaces scripts/weighted_svd.py:58-129 weighted_procrustes (variant 0: w/(sum w+eps),
+ * reflection fix sign(det)) and src/functions.py:12-85 kabsch_transformation_estimation
+ * (variant 1: w/(sum w+eps), means divided again by (sum+eps), raw det).
+ *   src,tgt : packed (K,3) pairs, or base arrays gathered through src_idx/tgt_idx (K) when
+ *             those are non-null
+ *   w       : (K) weights or NULL (all ones);  weight_thresh: w < thresh -> 0 (variant 0)
+ *   seg_start,seg_count : (Q) ; seg_count may be NULL -> CSR: count = seg_start[q+1]-seg_start[q]
+ *                         (seg_start then has Q+1 entries)
+ *   R (Q,9), t (Q,3) f32; T64 (Q,16) f64 row-major 4x4 or NULL; res (K) residual
+ *   ||R s + t - tgt|| or NULL; flag (Q) uint8 or NULL: 1 = degenerate (K<1 or non-finite) ->
+ *   identity, mirroring functions.py:62-71.
+ */
+#define F4L_KABSCH_PROCRUSTES 0
+#define F4L_KABSCH_F2S3 1
+F4L_API int f4l_segmented_kabsch(const float* src, const float* tgt, const int32_t* src_idx,
+                         const int32_t* tgt_idx, const float* w, const int32_t* seg_start,
+                         const int32_t* seg_count, int32_t Q, float eps, float weight_thresh,
+                         int variant, float* R, float* t, double* T64, float* res, uint8_t* flag,
+                         void* stream);
+
+/* (d)/apply: rows [p | R p + t] (or [R^T (p - t) | p] when inverse != 0) for every item of
+ * every segment, plus the displacement magnitude.                                   kernel K-f
+ * Replaces src/functions.py:107-124 transform_point_cloud and base.py:3373-3380, 3389-3390,
+ * 3463-3472.  pts (n,3) gathered through idx (items) when idx != NULL.  T (Q,16) f32 row-major.
+ * seg_skip (Q) uint8 or NULL: segments with seg_skip != 0 emit nothing; out_start (Q) gives the
+ * first output row of each segment.  dvf (rows,6), mag (rows) or NULL. */
+F4L_API int f4l_apply_transforms(const float* pts, const int32_t* idx, const int32_t* seg_start,
+                         const int32_t* seg_count, const int32_t* out_start,
+                         const uint8_t* seg_skip, int32_t Q, const float* T, int inverse,
+                         float* dvf, float* mag, void* stream);
+
+/* (c) rigidity / isometry check of each segment's correspondences.                  kernel K-c
+ * Replaces base.py:3308-3317: ratio_inlier = (#(|dS-dT| <= thres) - K)/(K(K-1)),
+ * dist_mean = sum triu(|dS-dT|,1)/(K(K-1)/2).  Outputs (Q) f32 each. */
+F4L_API int f4l_rigidity_check(const float* src, const float* tgt, const int32_t* src_idx,
+                       const int32_t* tgt_idx, const int32_t* seg_start,
+                       const int32_t* seg_count, int32_t Q, float thres_dist_diff,
+                       float* ratio_inlier, float* dist_mean, void* stream);
+
+/* (c) lower median (torch.median semantics) of each segment of x.  med (Q) f32.
+ * Replaces torch.median at src/models/outlier_classifier.py:80,91. */
+F4L_API int f4l_segmented_median(const float* x, const int32_t* seg_start, const int32_t* seg_count,
+                         int32_t Q, float* med, void* stream);
+
+/* (c)+(d) F2S3 pruning tail per supervoxel: Kabsch(w) -> residuals -> res < coeff*median ->
+ * (>=5 inliers and median < 0.5) -> refit with 0/1 weights.
+ * Replaces src/models/outlier_classifier.py:71-105 (everything after the network forward).
+ * corr (K,6) rows [src|tgt] f32, scores (K).  Outputs R (Q,9), t (Q,3), robust (Q) uint8,
+ * res (K) residuals of the final fit or NULL, median (Q) or NULL. */
+F4L_API int f4l_f2s3_prune_tail(const float* corr, const float* scores, const int32_t* seg_start,
+                        const int32_t* seg_count, int32_t Q, float coeff, float* R, float* t,
+                        uint8_t* robust, float* res, float* median, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) exact xyz k-nearest neighbours on a uniform grid.                             kernel K-a
+ * Replaces sklearn NearestNeighbors(kd_tree) at base.py:2727-2736, src/f2s3.py:492-501,
+ * src/functions.py:139-142 and scipy cKDTree.query at base.py:1038-1042.
+ *   q (N,3), r (M,3); k in [1,8]; max_radius <= 0 -> unbounded.
+ *   idx (N,k) int32 (-1 = none within radius), d2 (N,k) f32 squared distances, ascending;
+ *   exact ties are broken towards the lower reference index.
+ *   Set r == q (same pointer) for a self query (the point itself is neighbour 0).
+ * cell <= 0 lets the library choose the cell size from the bounding box and M. */
+F4L_API size_t f4l_knn_grid_workspace_bytes(int32_t N, int32_t M);
+F4L_API int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M, int32_t k,
+                 float max_radius, float cell, int32_t* idx, float* d2, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* k-th smallest (0-based) of x (n) f32, written to out[0] (device).  With k2 >= 0 also the k2-th
+ * to out[1] (np.median of an even count averages the two middle elements: base.py:2732). */
+F4L_API size_t f4l_select_kth_workspace_bytes(int32_t n);
+F4L_API int f4l_select_kth(const float* x, int32_t n, int32_t stride, int32_t offset, int32_t k,
+                   int32_t k2, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* (a) segmented 1-NN: for every query item of segment q, the nearest reference item of the SAME
+ * segment pair, optionally after applying T[q] to the query, kept iff d2 < thr[q]^2.
+ * Replaces base.py:48-97 refine_dvfs_with_threshold (Open3D KDTreeFlann per point).
+ *   nn (items) int32 = position in the reference segment's item list (or -1), d2 (items). */
+F4L_API int f4l_segmented_nn(const float* qpts, const int32_t* qidx, const int32_t* q_start,
+                     const int32_t* q_count, const float* rpts, const int32_t* ridx,
+                     const int32_t* r_start, const int32_t* r_count, int32_t Q, const float* T,
+                     const float* thr, int32_t* nn, float* d2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (e) per-patch point-to-point ICP, the kNN <-> Kabsch iterate loop in one persistent kernel.
+ * Replaces utils/o3d_tools.py:12-71 icp_registration -> Open3D registration_icp
+ * (TransformationEstimationPointToPoint(False), ICPConvergenceCriteria(1e-6,1e-6,30)).
+ *   source segment q = src items, target segment q = tgt items (gathered through *_idx if given);
+ *   T0 (Q,16) f64 row-major initial transforms (NULL = identity); fp64 arithmetic throughout.
+ *   Outputs: T (Q,16) f64, fitness (Q) f64, rmse (Q) f64, iters (Q) int32,
+ *   corr (src items) int32 = matched target item position or -1 (final correspondence set), or NULL.
+ *   seg_skip (Q) or NULL: skipped segments get T = T0, fitness = rmse = 0, iters = 0. */
+F4L_API int f4l_patch_icp(const float* src, const int32_t* src_idx, const int32_t* s_start,
+                  const int32_t* s_count, const float* tgt, const int32_t* tgt_idx,
+                  const int32_t* t_start, const int32_t* t_count, const uint8_t* seg_skip,
+                  int32_t Q, const double* T0, double max_corr_dist, int32_t max_iter,
+                  double rel_fitness, double rel_rmse, double* T, double* fitness, double* rmse,
+                  int32_t* iters, int32_t* corr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The fused fine-matching stage for one tile (all patch pairs in one launch sequence).
+ * Replaces base.py:3236-3457 fine_matching_with_different_types:
+ *   F2 select correspondences of each pair, F3 rigidity check, D2 Procrustes, E1 ICP on the
+ *   matched points, D5 apply to all src patch points (+ inverse for tgt2src), A4 assign_then_nn.
+ * See f4l_fine_params and the buffer list below. */
+typedef struct f4l_fine_params {
+    int32_t mode;                 /* 0 only_3d, 1 only_2d, 2 fusion (3D rows then 2D rows) */
+    int32_t remove_low_quality;   /* method.remove_low_quality_patch_matches */
+    int32_t num_min_quality;      /* method.num_min_matches_for_quality_check */
+    float thres_dist_diff;        /* method.thres_dist_diff */
+    float thres_inlier_ratio;     /* method.thres_inlier_ratio */
+    int32_t num_min_fine_match;   /* method.num_min_fine_match */
+    int32_t icp_refine;           /* method.icp_refine */
+    int32_t assign_type;          /* 0 assign_all_src, 1 assign_then_nn */
+    int32_t output_tgt2src;       /* method.output_tgt2src */
+    double icp_threshold;         /* parameter_setting.icp_threshold */
+    double median_max_resolution; /* para.median_max_resolution (base.py:2751) */
+    int32_t icp_max_iter;         /* 30 */
+} f4l_fine_params;
+
+typedef struct f4l_fine_buffers {
+    /* inputs */
+    const float* src_pts;  int32_t n_src;      /* (n_src,3) */
+    const float* tgt_pts;  int32_t n_tgt;      /* (n_tgt,3) */
+    const int64_t* corr3d;                      /* (n_src,2) or NULL; col1 = tgt index or -1 */
+    const int64_t* corr2d;                      /* (n_src,2) or NULL */
+    const int32_t* sp_idx;  const int32_t* sp_ptr;   /* src patch point lists, CSR over pairs (Q+1) */
+    const int32_t* tp_idx;  const int32_t* tp_ptr;   /* tgt patch point lists, CSR over pairs (Q+1) */
+    const int32_t* tgt_patch_of_point;          /* (n_tgt) id of the tgt patch owning each point, -1 none */
+    const int32_t* pair_tgt_patch;              /* (Q) tgt patch id of each pair */
+    int32_t Q;
+    /* outputs (caller-allocated upper bounds) */
+    float* T;              /* (Q,16) f32 row-major, identity when not fitted */
+    double* T64;           /* (Q,16) */
+    int8_t* status;        /* (Q) 0 fitted, 1 rejected by quality check, 2 too few matches */
+    int32_t* K;            /* (Q) matched correspondences per pair */
+    double* fitness; double* rmse; int32_t* iters;   /* (Q) */
+    float* ratio_inlier; float* dist_mean;           /* (Q) */
+    float* dense;          /* (sum n_s, 6) rows [p | T p] of fitted pairs, pair order */
+    float* sparse;         /* (2*sum n_s, 6) */
+    float* tgt2src;        /* (sum n_t, 6) or NULL */
+    int32_t* counts;       /* (4): dense rows, sparse rows, tgt2src rows, fitted pairs */
+} f4l_fine_buffers;
+
+F4L_API size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t n_tgt_items, int32_t Q,
+                                         int32_t mode);
+F4L_API int f4l_fine_matching(const f4l_fine_params* h_params, const f4l_fine_buffers* h_buffers,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) exact descriptor-space nearest neighbour, D in {32, 64}, on tensor cores.      kernel K-b
+ * Replaces torch.cdist + min at base.py:2783-2815 (global_matches_from_3d exact branches),
+ * the hnswlib query at src/f2s3.py:273-281 (exact instead of approximate) and, with
+ * both_dirs + the xyz gate, the coarse mutual matching at base.py:2966-2995.
+ *   a (N,D), b (M,D) f32.  a_xyz/b_xyz (.,3) + max_mag > 0: pairs with ||xyz_a - xyz_b|| > max_mag
+ *   are excluded (base.py:2969).  row_idx (N) int32 argmin over b (-1 = all excluded),
+ *   row_d2 (N) f32 squared L2; col_idx (M)/col_d2 (M) likewise when both_dirs (else NULL).
+ *   Ties (and everything within the re-rank margin) are resolved in exact fp32 arithmetic
+ *   towards the lower index (torch.min semantics). */
+F4L_API size_t f4l_desc_nn_workspace_bytes(int32_t N, int32_t M, int32_t D, int both_dirs);
+F4L_API int f4l_desc_nn(const float* a, int32_t N, const float* b, int32_t M, int32_t D,
+                const float* a_xyz, const float* b_xyz, float max_mag, int both_dirs,
+                int32_t* row_idx, float* row_d2, int32_t* col_idx, float* col_d2,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* (b)+(c) scatter of global 3D matches: base.py:2872-2889.  corres (n_raw,2) int64. */
+F4L_API int f4l_scatter_global_matches(const int32_t* labels, const float* src_sub, const float* tgt_sub,
+                               int32_t n_sub, const int64_t* voxel2pts_src,
+                               const int64_t* voxel2pts_tgt, float max_magnitude,
+                               int64_t* corres, int32_t n_raw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Piecewise "ICP" cells (Open3D octree leaves at depth `depth`), fp64.               kernel K-g
+ * Replaces src/piecewise_icp.py:89-132 (octree build + traversal + per-cell centroid).
+ *   pts64 (n,3) f64 (the 8 bounding-box corners already appended), origin[3], size: octree cube.
+ *   code (n) int64 leaf code (base-8 digits x+2y+4z, root first) or -1 if out of bounds.
+ * The cell table is produced by f4l_cells_build. */
+F4L_API int f4l_cell_codes(const double* pts64, int32_t n, const double* h_origin, double size,
+                   int32_t depth, int64_t* code, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F4L_B200_H */

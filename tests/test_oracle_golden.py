@@ -1,0 +1,100 @@
+"""CPU: pins the oracle (oracle/*.py, fp64 restatements) to the golden vectors produced by the
+UNMODIFIED reference functions (oracle/make_golden.py).  Tolerances are the fp32 rounding of the
+reference itself (it computes in fp32, the oracle in fp64)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import desc_nn, knn, rigid
+
+
+def _cases(z, suffix="_src"):
+    return sorted(k[:-len(suffix)] for k in z.files if k.endswith(suffix))
+
+
+def _act_err(Ra, ta, Rb, tb, pts):
+    """max_p || (Ra p + ta) - (Rb p + tb) ||  -- transforms compared by their action."""
+    pa = pts.astype(np.float64) @ np.asarray(Ra, np.float64).T + np.asarray(ta, np.float64)
+    pb = pts.astype(np.float64) @ np.asarray(Rb, np.float64).T + np.asarray(tb, np.float64)
+    return np.linalg.norm(pa - pb, axis=1).max()
+
+
+def test_procrustes_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rigid_procrustes.npz"))
+    for key in _cases(z):
+        s, t, w = z[key + "_src"], z[key + "_tgt"], z[key + "_w"]
+        w = None if w.size == 0 else w
+        R, tr = rigid.weighted_procrustes(s, t, w, 0.0, eps=1e-6)
+        # fp32 reference: ~1e-6 relative on R entries, a few f32 ulps of |p| (<= 60 m) in action
+        assert _act_err(R, tr, z[key + "_R"], z[key + "_t"], s) < 5e-5, key
+        assert abs(np.linalg.det(R) - 1) < 1e-9, key
+
+
+def test_kabsch_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rigid_kabsch.npz"))
+    for key in _cases(z):
+        s, t, w = z[key + "_src"], z[key + "_tgt"], z[key + "_w"]
+        w = None if w.size == 0 else w
+        R, tr, res, flag = rigid.kabsch(s, t, w)
+        assert not flag
+        assert _act_err(R, tr, z[key + "_R"], z[key + "_t"], s) < 5e-5, key
+        np.testing.assert_allclose(res, z[key + "_res"], atol=5e-5)
+        np.testing.assert_allclose(rigid.transform_point_cloud(s, R, tr), z[key + "_x1t"], atol=5e-5)
+
+
+def test_filter_tail_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "f2s3_filter.npz"))
+    assert "All keys matched" in str(z["load_report"][0]) or "missing_keys=[]" in str(z["load_report"][0])
+    n_robust = 0
+    for key in _cases(z, "_corr"):
+        corr, scores = z[key + "_corr"], z[key + "_scores"]
+        coeff = 2.5 if key.endswith("c25") else 1.0
+        o = rigid.filter_input_tail(corr[:, :3], corr[:, 3:], scores, coeff)
+        assert o["robust_estimate"] == bool(z[key + "_robust"][0]), key
+        n_robust += o["robust_estimate"]
+        assert _act_err(o["rot_est"], o["trans_est"], z[key + "_R"], z[key + "_t"], corr[:, :3]) < 1e-4, key
+    assert n_robust > 0
+
+
+def test_knn_matches_sklearn_calls(golden_dir):
+    z = np.load(os.path.join(golden_dir, "knn_sklearn.npz"))
+    a, b = z["a"], z["b"]
+    idx, d2 = knn.knn_exact(a, a, 2)
+    ties = knn.tie_rows(a, a, 2)
+    same = (idx == z["self_i_a"]).all(1)
+    assert (same | ties).all()
+    np.testing.assert_allclose(np.sqrt(d2), z["self_d_a"], rtol=1e-5, atol=1e-7)
+    assert abs(knn.median_resolution(a, b) - z["median_resolution"][0]) < 1e-7
+    np.testing.assert_allclose(knn.compute_c2c(a, b), z["c2c"], rtol=1e-9, atol=1e-12)
+    i1, _ = knn.knn_exact(a, b, 1)
+    t1 = knn.tie_rows(a, b, 1)
+    assert ((i1[:, 0] == z["c2c_idx"][:, 0]) | t1).all()
+
+
+def test_desc_nn_matches_cdist_min(golden_dir):
+    z = np.load(os.path.join(golden_dir, "desc_cdist.npz"))
+    for D in (32, 64):
+        a, b = z["D%d_a" % D], z["D%d_b" % D]
+        idx, d2, d2b = desc_nn.desc_nn(a, b, return_second=True)
+        tie = (d2b - d2) <= desc_nn.EPS_DESC_ABS
+        ref = z["D%d_labels" % D]
+        # the reference's fp32 GEMM-formulation cdist can flip near-ties: those rows are exempt
+        assert ((idx == ref) | tie).all()
+        assert (idx != ref).sum() <= tie.sum()
+        ok = idx == ref
+        np.testing.assert_allclose(np.sqrt(d2[ok]), z["D%d_dist" % D][ok], atol=2e-3)
+    m, j = desc_nn.coarse_matching_3d(z["coarse_cs"], z["coarse_fs"], z["coarse_ct"], z["coarse_ft"],
+                                      float(z["coarse_max_mag"][0]), "nn_mutual")
+    mask_ref = z["coarse_mutual"] & z["coarse_in_mag"]
+    np.testing.assert_array_equal(m, np.nonzero(mask_ref)[0])
+    np.testing.assert_array_equal(j, z["coarse_j"][mask_ref])
+
+
+def test_rigidity_matches_cdist_expression(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rigidity_cdist.npz"))
+    for ci in range(5):
+        r, m = rigid.rigidity_check(z["r%d_src" % ci], z["r%d_tgt" % ci], 0.5)
+        # torch.cdist switches to the fp32 GEMM formulation above 25 rows: noise ~1e-3 at |p|~40 m
+        assert abs(m - z["r%d_mean" % ci][0]) < 5e-3, ci
+        assert abs(r - z["r%d_ratio" % ci][0]) < 5e-3, ci

@@ -1,0 +1,147 @@
+"""GPU parity: K-d segmented Kabsch / Procrustes, K-f transform apply, K-c rigidity check,
+called through the C ABI, against the fp64 oracle and the reference's golden outputs.
+Tolerance (north_star): transforms compared by their action on the patch points, <= 1e-5 m."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rigid
+from tests.test_oracle_golden import _act_err, _cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _pack(cases, dev):
+    src = np.concatenate([c[0] for c in cases]).astype(np.float32)
+    tgt = np.concatenate([c[1] for c in cases]).astype(np.float32)
+    has_w = any(c[2] is not None for c in cases)
+    w = np.concatenate([np.ones(len(c[0]), np.float32) if c[2] is None else c[2] for c in cases]) if has_w else None
+    ptr = np.zeros(len(cases) + 1, np.int32)
+    ptr[1:] = np.cumsum([len(c[0]) for c in cases])
+    T = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+    return T(src), T(tgt), T(w), T(ptr)
+
+
+@pytest.mark.parametrize("variant,gold", [(0, "rigid_procrustes.npz"), (1, "rigid_kabsch.npz")])
+def test_kabsch_golden(cuda, golden_dir, variant, gold):
+    from fusion4landslide_b200 import ops
+    z = np.load(os.path.join(golden_dir, gold))
+    keys = _cases(z)
+    cases = [(z[k + "_src"], z[k + "_tgt"], None if z[k + "_w"].size == 0 else z[k + "_w"]) for k in keys]
+    src, tgt, w, ptr = _pack(cases, cuda)
+    eps = 1e-6 if variant == 0 else 1e-7
+    R, t, flag, res = ops.segmented_kabsch(src, tgt, ptr, w=w, eps=eps, variant=variant, want_res=True)
+    torch.cuda.synchronize()
+    R, t, res = R.cpu().numpy(), t.cpu().numpy(), res.cpu().numpy()
+    assert flag.sum().item() == 0
+    p = ptr.cpu().numpy()
+    for i, k in enumerate(keys):
+        s, tg, wk = cases[i]
+        if variant == 0:
+            Ro, to = rigid.weighted_procrustes(s, tg, wk, 0.0, eps)
+        else:
+            Ro, to, reso, _ = rigid.kabsch(s, tg, wk)
+            np.testing.assert_allclose(res[p[i]:p[i + 1]], reso, atol=TOL)
+        assert _act_err(R[i], t[i], Ro, to, s) < TOL, ("oracle", k)
+        # and against what the reference itself returned (fp32 torch)
+        assert _act_err(R[i], t[i], z[k + "_R"], z[k + "_t"], s) < TOL, ("reference", k)
+
+
+def test_kabsch_many_patches_and_gather(cuda):
+    """Ragged batch (sizes 1..3000, 2000 patches) at tile-scale coordinates, packed and gathered."""
+    from fusion4landslide_b200 import ops
+    rng = np.random.default_rng(5)
+    Q = 2000
+    sizes = rng.integers(3, 400, size=Q)
+    sizes[:5] = [3, 1000, 3000, 32, 33]
+    cases = []
+    from oracle.make_golden import _patch
+    for n in sizes:
+        s, t = _patch(rng, int(n), rng.uniform(0, 100, size=3))
+        cases.append((s, t, rng.random(int(n)).astype(np.float32)))
+    src, tgt, w, ptr = _pack(cases, cuda)
+    R, t, flag, T64 = ops.segmented_kabsch(src, tgt, ptr, w=w, eps=1e-6, variant=0, want_T64=True)
+    # gathered form: shuffle the base arrays, address through index lists
+    K = src.shape[0]
+    perm = torch.randperm(K, device=cuda)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(K, device=cuda)
+    R2, t2, _ = ops.segmented_kabsch(src[perm].contiguous(), tgt[perm].contiguous(), ptr, w=w, eps=1e-6,
+                                     variant=0, src_idx=inv.int(), tgt_idx=inv.int())
+    torch.cuda.synchronize()
+    assert torch.equal(R, R2) and torch.equal(t, t2)
+    R, t, T64 = R.cpu().numpy(), t.cpu().numpy(), T64.cpu().numpy()
+    worst = 0.0
+    for i in range(Q):
+        s, tg, wk = cases[i]
+        Ro, to = rigid.weighted_procrustes(s, tg, wk, 0.0, 1e-6)
+        worst = max(worst, _act_err(R[i], t[i], Ro, to, s))
+        assert abs(np.linalg.det(T64[i, :3, :3]) - 1) < 1e-9
+    assert worst < TOL, worst
+
+
+def test_kabsch_degenerate_segments(cuda):
+    from fusion4landslide_b200 import ops
+    src = torch.randn(10, 3, device=cuda)
+    ptr = torch.tensor([0, 0, 10], dtype=torch.int32, device=cuda)   # first segment empty
+    R, t, flag = ops.segmented_kabsch(src, src.clone(), ptr)
+    assert flag.tolist() == [1, 0]
+    assert torch.allclose(R[0], torch.eye(3, device=cuda)) and torch.all(t[0] == 0)
+    assert torch.allclose(R[1], torch.eye(3, device=cuda), atol=1e-6)
+    # Q = 0 is a no-op
+    ops.segmented_kabsch(src, src, torch.zeros(1, dtype=torch.int32, device=cuda))
+
+
+def test_apply_transforms(cuda):
+    from fusion4landslide_b200 import ops
+    rng = np.random.default_rng(6)
+    Q = 300
+    sizes = rng.integers(1, 700, size=Q)
+    ptr = np.zeros(Q + 1, np.int32)
+    ptr[1:] = np.cumsum(sizes)
+    pts = rng.uniform(0, 60, size=(ptr[-1], 3)).astype(np.float32)
+    from oracle.make_golden import _rand_rigid
+    T = np.tile(np.eye(4, dtype=np.float32), (Q, 1, 1))
+    for q in range(Q):
+        R, t = _rand_rigid(rng)
+        T[q, :3, :3], T[q, :3, 3] = R, t
+    d_pts, d_ptr, d_T = (torch.from_numpy(x).to(cuda) for x in (pts, ptr, T))
+    dvf, mag = ops.apply_transforms(d_pts, d_ptr, d_T)
+    back, _ = ops.apply_transforms(d_pts, d_ptr, d_T, inverse=True)
+    torch.cuda.synchronize()
+    dvf, mag, back = dvf.cpu().numpy(), mag.cpu().numpy(), back.cpu().numpy()
+    for q in range(Q):
+        sl = slice(ptr[q], ptr[q + 1])
+        ref = rigid.transform_point_cloud(pts[sl], T[q, :3, :3], T[q, :3, 3])
+        np.testing.assert_array_equal(dvf[sl, :3], pts[sl])
+        assert np.abs(dvf[sl, 3:] - ref).max() < TOL
+        refb = (pts[sl].astype(np.float64) - T[q, :3, 3]) @ T[q, :3, :3].astype(np.float64)
+        assert np.abs(back[sl, :3] - refb).max() < TOL
+        np.testing.assert_array_equal(back[sl, 3:], pts[sl])
+    np.testing.assert_allclose(mag, np.linalg.norm(dvf[:, 3:] - dvf[:, :3], axis=1), atol=1e-6)
+
+
+def test_rigidity_golden_and_oracle(cuda, golden_dir):
+    from fusion4landslide_b200 import ops
+    z = np.load(os.path.join(golden_dir, "rigidity_cdist.npz"))
+    cases = [(z["r%d_src" % i], z["r%d_tgt" % i], None) for i in range(5)]
+    rng = np.random.default_rng(7)
+    from oracle.make_golden import _patch
+    for n in (2, 3, 700, 2500):          # 2500 > the shared-memory staging capacity
+        s, t = _patch(rng, n, rng.uniform(0, 50, size=3), outliers=0.2)
+        cases.append((s, t, None))
+    src, tgt, _, ptr = _pack(cases, cuda)
+    ratio, dmean = ops.rigidity_check(src, tgt, ptr, 0.5)
+    torch.cuda.synchronize()
+    ratio, dmean = ratio.cpu().numpy(), dmean.cpu().numpy()
+    for i, (s, t, _) in enumerate(cases):
+        r, m = rigid.rigidity_check(s, t, 0.5)
+        assert abs(dmean[i] - m) < 2e-5 * max(1.0, m), i
+        # a pair whose |dS-dT| sits within fp32 rounding of the threshold may flip: allow 2 pairs
+        assert abs(ratio[i] - r) <= 2.0 / max(len(s) * (len(s) - 1) / 2, 1) + 1e-6, i
+        if i < 5:  # the reference's own (GEMM-formulation, noisier) numbers
+            assert abs(dmean[i] - z["r%d_mean" % i][0]) < 5e-3
+            assert abs(ratio[i] - z["r%d_ratio" % i][0]) < 5e-3
