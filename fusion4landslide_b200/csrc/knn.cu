@@ -1,0 +1,340 @@
+// K-a: exact xyz k-nearest neighbours on a uniform grid, and a radix select for medians.
+//
+// Layout in HBM: reference points are binned into a dense grid (x fastest) and rewritten as
+// float4 {x,y,z,bits(original index)} in cell order, so every candidate load is one aligned
+// 16-byte read and the 3 cells of a grid row that a query visits are ONE contiguous range.
+// Queries are processed in the same cell order (self query: the sorted array itself; otherwise
+// the queries are binned on the same grid), so the threads of a warp visit the same rows and the
+// candidates are served from L1.  Each point crosses HBM O(1) times: bin pass (12 B read + 16 B
+// write), search (16 B read) and the k results (8k B written).
+//
+// Exactness: rings of cells are searched until the k-th best distance is strictly below the
+// distance to the border of the searched block (or the radius is covered); ties in squared
+// distance are broken towards the lower original index, independent of the in-cell order.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+struct GridParams {
+    float minx, miny, minz;
+    float inv_cell, cell;
+    int nx, ny, nz;
+    int ncells;
+    int pad;
+};
+
+// ---- bounding box ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void k_bbox_init(unsigned* bb) {
+    if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ p, int n, unsigned* bb) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = __ldg(p + (size_t)i * 3 + a);
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(F4L_FULL, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(F4L_FULL, mx[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(bb + a, f2ord(mn[a]));
+            atomicMax(bb + 3 + a, f2ord(mx[a]));
+        }
+    }
+}
+
+// one thread: choose the cell size (surface-like data: ~2x the mean spacing on the largest face
+// of the box) and clamp the table to max_cells.
+__global__ void k_grid_params(const unsigned* bb, int m, float cell_in, int max_cells, GridParams* gp) {
+    float mn[3], ex[3];
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = ord2f(bb[a]);
+        ex[a] = fmaxf(ord2f(bb[3 + a]) - mn[a], 0.f);
+    }
+    float face = fmaxf(ex[0] * ex[1], fmaxf(ex[0] * ex[2], ex[1] * ex[2]));
+    float c = cell_in > 0.f ? cell_in : 2.0f * sqrtf(face / fmaxf((float)m, 1.f));
+    float longest = fmaxf(ex[0], fmaxf(ex[1], ex[2]));
+    if (!(c > 0.f)) c = fmaxf(longest, 1e-3f);
+    c = fmaxf(c, longest * 1e-4f);   // never more than 10^4 cells per axis
+    int nx, ny, nz;
+    for (int it = 0; it < 64; ++it) {
+        nx = (int)floorf(ex[0] / c) + 1;
+        ny = (int)floorf(ex[1] / c) + 1;
+        nz = (int)floorf(ex[2] / c) + 1;
+        if ((long long)nx * ny * nz <= (long long)max_cells) break;
+        c *= 1.2599211f;
+    }
+    gp->minx = mn[0]; gp->miny = mn[1]; gp->minz = mn[2];
+    gp->cell = c; gp->inv_cell = 1.0f / c;
+    gp->nx = nx; gp->ny = ny; gp->nz = nz;
+    gp->ncells = nx * ny * nz;
+}
+
+__device__ __forceinline__ void cell_of(const GridParams& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = min(max((int)floorf((x - g.minx) * g.inv_cell), 0), g.nx - 1);
+    cy = min(max((int)floorf((y - g.miny) * g.inv_cell), 0), g.ny - 1);
+    cz = min(max((int)floorf((z - g.minz) * g.inv_cell), 0), g.nz - 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_count(const float* __restrict__ p, int n, const GridParams* __restrict__ gp, int* __restrict__ cid,
+            int* __restrict__ cell_count) {
+    const GridParams g = *gp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float x = __ldg(p + (size_t)i * 3), y = __ldg(p + (size_t)i * 3 + 1), z = __ldg(p + (size_t)i * 3 + 2);
+        int cx, cy, cz;
+        cell_of(g, x, y, z, cx, cy, cz);
+        int c = (cz * g.ny + cy) * g.nx + cx;
+        cid[i] = c;
+        atomicAdd(cell_count + c, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_scatter(const float* __restrict__ p, int n, const int* __restrict__ cid,
+              const int* __restrict__ cell_start, int* __restrict__ cell_fill, float4* __restrict__ sorted) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int c = cid[i];
+        int pos = cell_start[c] + atomicAdd(cell_fill + c, 1);
+        sorted[pos] = make_float4(__ldg(p + (size_t)i * 3), __ldg(p + (size_t)i * 3 + 1),
+                                  __ldg(p + (size_t)i * 3 + 2), __int_as_float(i));
+    }
+}
+
+// variant that advances the (scanned) table itself: table[c] walks from the cell's start to its end
+__global__ void __launch_bounds__(256)
+k_bin_scatter_advance(const float* __restrict__ p, int n, const int* __restrict__ cid,
+                      int* __restrict__ table, float4* __restrict__ sorted) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int pos = atomicAdd(table + cid[i], 1);
+        sorted[pos] = make_float4(__ldg(p + (size_t)i * 3), __ldg(p + (size_t)i * 3 + 1),
+                                  __ldg(p + (size_t)i * 3 + 2), __int_as_float(i));
+    }
+}
+
+// ---- search --------------------------------------------------------------------------------
+template <int K>
+struct TopK {
+    float d[K];
+    int i[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int a = 0; a < K; ++a) { d[a] = INFINITY; i[a] = -1; }
+    }
+    __device__ __forceinline__ void push(float dd, int ii) {
+        // lexicographic (d, idx) ordering -> deterministic under any visiting order
+        if (dd > d[K - 1] || (dd == d[K - 1] && (ii > i[K - 1] && i[K - 1] >= 0))) return;
+        d[K - 1] = dd;
+        i[K - 1] = ii;
+#pragma unroll
+        for (int a = K - 1; a > 0; --a) {
+            bool sw = d[a] < d[a - 1] || (d[a] == d[a - 1] && i[a] < i[a - 1]);
+            if (sw) {
+                float td = d[a]; d[a] = d[a - 1]; d[a - 1] = td;
+                int ti = i[a]; i[a] = i[a - 1]; i[a - 1] = ti;
+            }
+        }
+    }
+};
+
+template <int K>
+__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, int b, int e, float qx,
+                                           float qy, float qz, TopK<K>& tk) {
+    for (int j = b; j < e; ++j) {
+        float4 c = __ldg(sorted + j);
+        float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+        float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        tk.push(dd, __float_as_int(c.w));
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __restrict__ sorted,
+              const int* __restrict__ cell_start, const GridParams* __restrict__ gp, int k, float max_r2,
+              int* __restrict__ out_idx, float* __restrict__ out_d2) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const GridParams g = *gp;
+    const float4 q = __ldg(queries_sorted + t);
+    const int qi = __float_as_int(q.w);
+    int cx, cy, cz;
+    cell_of(g, q.x, q.y, q.z, cx, cy, cz);
+    TopK<K> tk;
+    tk.init();
+    const int maxR = max(g.nx, max(g.ny, g.nz));
+    for (int R = 0; R <= maxR; ++R) {
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+        const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
+        for (int z = z0; z <= z1; ++z) {
+            const bool zshell = (z == cz - R) || (z == cz + R);
+            for (int y = y0; y <= y1; ++y) {
+                const bool shell = zshell || (y == cy - R) || (y == cy + R);
+                const int row = (z * g.ny + y) * g.nx;
+                if (shell || R == 0) {
+                    scan_range<K>(sorted, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1), q.x, q.y, q.z, tk);
+                } else {
+                    if (cx - R >= 0)
+                        scan_range<K>(sorted, __ldg(cell_start + row + cx - R), __ldg(cell_start + row + cx - R + 1), q.x, q.y, q.z, tk);
+                    if (cx + R <= g.nx - 1)
+                        scan_range<K>(sorted, __ldg(cell_start + row + cx + R), __ldg(cell_start + row + cx + R + 1), q.x, q.y, q.z, tk);
+                }
+            }
+        }
+        // distance from the query to the border of the searched block (infinite where the block
+        // reaches the grid border: no reference point lies outside the grid's bounding box)
+        float margin = INFINITY;
+        if (cx - R > 0) margin = fminf(margin, q.x - (g.minx + (float)(cx - R) * g.cell));
+        if (cx + R < g.nx - 1) margin = fminf(margin, (g.minx + (float)(cx + R + 1) * g.cell) - q.x);
+        if (cy - R > 0) margin = fminf(margin, q.y - (g.miny + (float)(cy - R) * g.cell));
+        if (cy + R < g.ny - 1) margin = fminf(margin, (g.miny + (float)(cy + R + 1) * g.cell) - q.y);
+        if (cz - R > 0) margin = fminf(margin, q.z - (g.minz + (float)(cz - R) * g.cell));
+        if (cz + R < g.nz - 1) margin = fminf(margin, (g.minz + (float)(cz + R + 1) * g.cell) - q.z);
+        if (margin == INFINITY) break;
+        // conservative (cell borders are computed in f32): shrink the margin by a few ulps
+        margin = fmaxf(margin - 4e-7f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + g.cell), 0.f);
+        const float m2 = margin * margin;
+        const float kth = tk.d[K - 1 < k - 1 ? K - 1 : k - 1];
+        if (kth < m2 || m2 >= max_r2) break;
+    }
+    for (int a = 0; a < k; ++a) {
+        float dd = a < K ? tk.d[a] : INFINITY;
+        int ii = a < K ? tk.i[a] : -1;
+        if (!(dd < max_r2)) { dd = INFINITY; ii = -1; }
+        out_idx[(size_t)qi * k + a] = ii;
+        out_d2[(size_t)qi * k + a] = dd;
+    }
+}
+
+__global__ void k_fill_none(int n, int k, int* idx, float* d2) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n * k) { idx[t] = -1; d2[t] = INFINITY; }
+}
+
+// ---- workspace layout ------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int knn_max_cells(int M) {
+    long long c = 8LL * (long long)M + 4096;
+    if (c > (1LL << 27)) c = 1LL << 27;
+    return (int)c;
+}
+
+struct KnnWs {
+    GridParams* gp;
+    unsigned* bb;
+    int* cell_count;   // max_cells+1 (counts, then exclusive scan in cell_start)
+    int* cell_start;   // max_cells+1
+    int* cid;          // max(N,M)
+    float4* sorted_r;  // M
+    float4* sorted_q;  // N
+    void* cub_tmp;
+    size_t cub_bytes;
+    size_t total;
+};
+
+static KnnWs knn_layout(void* base, int N, int M) {
+    KnnWs w;
+    const int mc = knn_max_cells(M);
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t bytes) { char* p = b + off; off += align_up(bytes); return (void*)p; };
+    w.gp = (GridParams*)take(sizeof(GridParams));
+    w.bb = (unsigned*)take(6 * sizeof(unsigned));
+    w.cell_count = (int*)take((size_t)(mc + 1) * 4);
+    w.cell_start = (int*)take((size_t)(mc + 1) * 4);
+    w.cid = (int*)take((size_t)(N > M ? N : M) * 4);
+    w.sorted_r = (float4*)take((size_t)M * 16);
+    w.sorted_q = (float4*)take((size_t)N * 16);
+    size_t cb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cb, (int*)nullptr, (int*)nullptr, mc + 1);
+    w.cub_bytes = cb;
+    w.cub_tmp = take(cb);
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t f4l_knn_grid_workspace_bytes(int32_t N, int32_t M) {
+    if (N < 0) N = 0;
+    if (M < 0) M = 0;
+    return knn_layout(nullptr, N, M).total;
+}
+
+static int bin_points(const float* p, int n, const KnnWs& w, int mc, float4* sorted, cudaStream_t st) {
+    cudaMemsetAsync(w.cell_count, 0, (size_t)(mc + 1) * 4, st);
+    const int blocks = min(f4l_div_up(n, 256), 148 * 8);
+    k_bin_count<<<blocks, 256, 0, st>>>(p, n, w.gp, w.cid, w.cell_count);
+    size_t cb = w.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.cell_count, w.cell_start, mc + 1, st);
+    cudaMemsetAsync(w.cell_count, 0, (size_t)(mc + 1) * 4, st);
+    k_bin_scatter<<<blocks, 256, 0, st>>>(p, n, w.cid, w.cell_start, w.cell_count, sorted);
+    return f4l_check_launch("f4l_knn_grid/bin");
+}
+
+extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
+                            float cell, int32_t* idx, float* d2, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    F4L_REQUIRE(N >= 0 && M >= 0, "negative size");
+    F4L_REQUIRE(k >= 1 && k <= 8, "k must be in [1,8]");
+    if (N == 0) return F4L_OK;
+    F4L_REQUIRE(q && idx && d2, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        k_fill_none<<<f4l_div_up((long long)N * k, 256), 256, 0, st>>>(N, k, idx, d2);
+        return f4l_check_launch("f4l_knn_grid/fill");
+    }
+    F4L_REQUIRE(r && workspace, "null pointer");
+    KnnWs w = knn_layout(workspace, N, M);
+    if (workspace_bytes < w.total) {
+        f4l_set_error("f4l_knn_grid: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        return F4L_E_WORKSPACE;
+    }
+    const int mc = knn_max_cells(M);
+    k_bbox_init<<<1, 32, 0, st>>>(w.bb);
+    k_bbox<<<min(f4l_div_up(M, 256), 148 * 4), 256, 0, st>>>(r, M, w.bb);
+    k_grid_params<<<1, 1, 0, st>>>(w.bb, M, cell, mc, w.gp);
+    int rc = bin_points(r, M, w, mc, w.sorted_r, st);
+    if (rc) return rc;
+    // keep the reference table: the query binning below needs its own counters
+    const float4* qs = w.sorted_r;
+    int* ref_start = w.cell_start;
+    if (q != r || N != M) {
+        // bin the queries on the same grid (queries outside the box clamp to border cells); their
+        // table is scanned in place in cell_count, cell_start stays the reference table
+        cudaMemsetAsync(w.cell_count, 0, (size_t)(mc + 1) * 4, st);
+        const int blocks = min(f4l_div_up(N, 256), 148 * 8);
+        k_bin_count<<<blocks, 256, 0, st>>>(q, N, w.gp, w.cid, w.cell_count);
+        size_t cb = w.cub_bytes;
+        cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.cell_count, w.cell_count, mc + 1, st);  // in place
+        k_bin_scatter_advance<<<blocks, 256, 0, st>>>(q, N, w.cid, w.cell_count, w.sorted_q);
+        qs = w.sorted_q;
+    }
+    const float max_r2 = max_radius > 0.f ? max_radius * max_radius : INFINITY;
+    const int blocks = f4l_div_up(N, 128);
+    if (k == 1) k_grid_search<1><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
+    else if (k == 2) k_grid_search<2><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
+    else if (k <= 4) k_grid_search<4><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
+    else k_grid_search<8><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
+    return f4l_check_launch("f4l_knn_grid/search");
+}

@@ -34,7 +34,8 @@ def umeyama_noscale(src, dst):
     ms = src.mean(0)
     md = dst.mean(0)
     sigma = (dst - md).T @ (src - ms) / n
-    U, _, Vt = np.linalg.svd(sigma)
+    U, sv, Vt = np.linalg.svd(sigma)
+    umeyama_noscale.last_sv = sv
     S = np.ones(3)
     if np.linalg.det(U) * np.linalg.det(Vt) < 0:
         S[2] = -1.0
@@ -63,14 +64,20 @@ def icp_point_to_point(source, target, init=None, max_dist=0.1, max_iter=30,
     T = np.eye(4) if init is None else np.asarray(init, dtype=np.float64).copy()
     if src.shape[0] == 0 or tgt.shape[0] == 0:
         return dict(transformation=T, fitness=0.0, inlier_rmse=0.0,
-                    correspondence_set=np.zeros((0, 2), np.int64), iters=0)
+                    correspondence_set=np.zeros((0, 2), np.int64), iters=0, min_ncorr=0, min_sv_ratio=0.0)
     tree = cKDTree(tgt)
     P = src @ T[:3, :3].T + T[:3, 3]
     ok, j, fit, rmse = _match(P, tree, tgt.shape[0], max_dist)
     it = 0
+    # bookkeeping for the tests: the rigid fit is not unique when fewer than 3 pairs (or a
+    # rank-deficient covariance) enter it -- those patches are exempt from path comparison
+    min_ncorr, min_sv_ratio = int(ok.sum()), 1.0
     for it in range(1, max_iter + 1):
+        min_ncorr = min(min_ncorr, int(ok.sum()))
         if ok.any():
             U = umeyama_noscale(P[ok], tgt[j[ok]])
+            sv = umeyama_noscale.last_sv
+            min_sv_ratio = min(min_sv_ratio, sv[1] / sv[0] if sv[0] > 0 else 0.0)
         else:
             U = np.eye(4)
         T = U @ T
@@ -80,4 +87,5 @@ def icp_point_to_point(source, target, init=None, max_dist=0.1, max_iter=30,
         if abs(pfit - fit) < rel_fitness and abs(prmse - rmse) < rel_rmse:
             break
     corr = np.stack([np.nonzero(ok)[0], j[ok]], axis=1).astype(np.int64)
-    return dict(transformation=T, fitness=fit, inlier_rmse=rmse, correspondence_set=corr, iters=it)
+    return dict(transformation=T, fitness=fit, inlier_rmse=rmse, correspondence_set=corr, iters=it,
+                min_ncorr=min_ncorr, min_sv_ratio=min_sv_ratio)

@@ -14,7 +14,7 @@ third-party trees is implementation-defined, so near-ties are flagged, not compa
 import numpy as np
 from scipy.spatial import cKDTree
 
-EPS_XYZ_REL = 1e-6   # documented tie: |d2_a - d2_b| <= EPS_XYZ_REL * d2_best (+ tiny absolute)
+EPS_XYZ_REL = 1e-6   # documented tie: |d2_a - d2_b| <= EPS_XYZ_REL * max(d2_a, d2_b) (+ 1e-12 absolute)
 
 
 def knn_exact(q, r, k, workers=-1):
@@ -46,7 +46,7 @@ def tie_rows(q, r, k, workers=-1):
     if kk < 2:
         return np.zeros(q.shape[0], bool)
     gap = np.diff(d2, axis=1)
-    tol = EPS_XYZ_REL * d2[:, :1] + 1e-12
+    tol = EPS_XYZ_REL * d2[:, 1:] + 1e-12      # relative to the larger distance of each adjacent pair
     return (gap <= tol).any(axis=1)
 
 

@@ -47,7 +47,10 @@ def test_kabsch_golden(cuda, golden_dir, variant, gold):
             np.testing.assert_allclose(res[p[i]:p[i + 1]], reso, atol=TOL)
         assert _act_err(R[i], t[i], Ro, to, s) < TOL, ("oracle", k)
         # and against what the reference itself returned (fp32 torch)
-        assert _act_err(R[i], t[i], z[k + "_R"], z[k + "_t"], s) < TOL, ("reference", k)
+        # the reference computes in fp32 at absolute coordinates: its own rounding noise is a few
+        # f32 ulps of |p| (measured <= 1.6e-5 m at |p| ~ 35 m), on top of the 1e-5 m budget
+        tol_ref = TOL + 4 * np.finfo(np.float32).eps * np.abs(s).max()
+        assert _act_err(R[i], t[i], z[k + "_R"], z[k + "_t"], s) < tol_ref, ("reference", k)
 
 
 def test_kabsch_many_patches_and_gather(cuda):
