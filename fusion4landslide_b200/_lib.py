@@ -37,6 +37,7 @@ class FineBuffers(ctypes.Structure):
         ("corr3d", c_void_p), ("corr2d", c_void_p),
         ("sp_idx", c_void_p), ("sp_ptr", c_void_p), ("tp_idx", c_void_p), ("tp_ptr", c_void_p),
         ("tgt_patch_of_point", c_void_p), ("pair_tgt_patch", c_void_p), ("Q", c_i32),
+        ("n_src_items", c_i32), ("n_tgt_items", c_i32), ("d_median_resolution", c_void_p),
         ("T", c_void_p), ("T64", c_void_p), ("status", c_void_p), ("K", c_void_p),
         ("fitness", c_void_p), ("rmse", c_void_p), ("iters", c_void_p),
         ("ratio_inlier", c_void_p), ("dist_mean", c_void_p),
@@ -59,6 +60,8 @@ SIGNATURES = {
     "f4l_knn_grid": (c_int, [P, c_i32, P, c_i32, c_i32, c_f32, c_f32, P, P, P, c_size, P]),
     "f4l_select_kth_workspace_bytes": (c_size, [c_i32]),
     "f4l_select_kth": (c_int, [P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P, c_size, P]),
+    "f4l_median_resolution_workspace_bytes": (c_size, [c_i32, c_i32]),
+    "f4l_median_resolution": (c_int, [P, c_i32, P, c_i32, P, P, c_size, P]),
     "f4l_segmented_nn": (c_int, [P, P, P, P, P, P, P, P, c_i32, P, P, P, P, P]),
     "f4l_patch_icp": (c_int, [P, P, P, P, P, P, P, P, P, c_i32, P, c_f64, c_i32, c_f64, c_f64,
                               P, P, P, P, P, P]),

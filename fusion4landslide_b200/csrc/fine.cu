@@ -1,0 +1,465 @@
+// The fused fine-matching stage for one tile: every patch pair of the tile in six launches.
+// Replaces src/coarse_to_fine_matching_base.py:3236-3457.
+//
+//   k_select_corr   F2  warp per pair: ordered compaction of the pair's correspondences
+//   k_patch_fit     F3 + D2 + E1  CTA per pair: rigidity check, Procrustes, on-chip ICP loop
+//   k_row_offsets   scan of the per-pair output row counts (dense, tgt2src)
+//   k_apply_assign  D5 + A4  CTA per pair: dense DVF rows, inverse rows, 1-NN assignment
+//   k_sparse_offsets, k_emit_sparse   ordered compaction of the kept sparse rows (twice, q4)
+//
+// No host round trip happens between the stages: per-pair decisions (quality reject, too few
+// matches) are status bytes consumed by the later kernels, row counts are device scalars.
+#include "icp_device.cuh"
+
+#define FINE_MODE_3D 0
+#define FINE_MODE_2D 1
+#define FINE_MODE_FUSION 2
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_compact_rows(const int64_t* __restrict__ corr, const int32_t* __restrict__ sp_idx,
+                                                 int s0, int ns, const int32_t* __restrict__ tgt_patch_of_point,
+                                                 int want_patch, int n_tgt, int lane, int32_t* __restrict__ cs,
+                                                 int32_t* __restrict__ ct, int base) {
+    // rows of corr[sp_idx[s0..s0+ns)] whose target belongs to the pair's target patch
+    // (torch.isin at base.py:3260 == label test because target patches are disjoint)
+    int written = base;
+    for (int i0 = 0; i0 < ns; i0 += 32) {
+        const int i = i0 + lane;
+        int p = -1;
+        long long t = -1;
+        bool ok = false;
+        if (i < ns) {
+            p = sp_idx[s0 + i];
+            t = corr[2 * (size_t)p + 1];
+            ok = t >= 0 && t < n_tgt && tgt_patch_of_point[t] == want_patch;
+        }
+        const unsigned m = __ballot_sync(F4L_FULL, ok);
+        if (ok) {
+            const int pos = written + __popc(m & ((1u << lane) - 1u));
+            cs[pos] = p;
+            ct[pos] = (int)t;
+        }
+        written += __popc(m);
+    }
+    return written;
+}
+
+__global__ void __launch_bounds__(128)
+k_select_corr(const int64_t* __restrict__ corr3d, const int64_t* __restrict__ corr2d,
+              const int32_t* __restrict__ sp_idx, const int32_t* __restrict__ sp_ptr,
+              const int32_t* __restrict__ tgt_patch_of_point, const int32_t* __restrict__ pair_tgt_patch,
+              int n_tgt, int Q, int mode, int32_t* __restrict__ cs, int32_t* __restrict__ ct,
+              int32_t* __restrict__ kstart, int32_t* __restrict__ K) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    const int s0 = sp_ptr[q], ns = sp_ptr[q + 1] - s0;
+    const int slot = (mode == FINE_MODE_FUSION ? 2 : 1) * s0;
+    const int want = pair_tgt_patch[q];
+    int w = slot;
+    if (mode != FINE_MODE_2D) w = warp_compact_rows(corr3d, sp_idx, s0, ns, tgt_patch_of_point, want, n_tgt, lane, cs, ct, w);
+    if (mode != FINE_MODE_3D) w = warp_compact_rows(corr2d, sp_idx, s0, ns, tgt_patch_of_point, want, n_tgt, lane, cs, ct, w);
+    if (lane == 0) {
+        kstart[q] = slot;
+        K[q] = w - slot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct FitShared {
+    IcpShared icp;
+    double red_sum[ICP_WARPS];
+    unsigned long long red_cnt[ICP_WARPS];
+    double Tsvd[16];
+    int decision;
+};
+
+__global__ void __launch_bounds__(ICP_THREADS)
+k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
+            const int32_t* __restrict__ cs, const int32_t* __restrict__ ct,
+            const int32_t* __restrict__ kstart, const int32_t* __restrict__ K, int Q, f4l_fine_params prm,
+            float* __restrict__ T32, double* __restrict__ T64, int8_t* __restrict__ status,
+            double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
+            float* __restrict__ ratio_inlier, float* __restrict__ dist_mean) {
+    extern __shared__ float dyn[];
+    __shared__ FitShared sh;
+    const int tid = threadIdx.x;
+    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+        __syncthreads();
+        const int k0 = kstart[q], k = K[q];
+        int st = 0;
+        float ratio = 0.f, dmean = 0.f;
+        if (prm.remove_low_quality && k >= prm.num_min_quality) {
+            double sum;
+            unsigned long long cnt;
+            block_rigidity<2048>(src_pts, tgt_pts, cs, ct, k0, k, prm.thres_dist_diff, dyn, sh.red_sum, sh.red_cnt, sum, cnt);
+            if (tid == 0) {
+                const double ne = 0.5 * (double)k * (double)(k - 1);
+                const float dm = (float)(sum / ne);
+                const float ra = (float)((double)(2ull * cnt) / (ne * 2.0));
+                ratio_inlier[q] = ra;
+                dist_mean[q] = dm;
+                sh.decision = (ra <= prm.thres_inlier_ratio || dm >= prm.thres_dist_diff) ? 1 : 0;   // base.py:3320
+            }
+            __syncthreads();
+            st = sh.decision;
+        } else if (tid == 0) {
+            ratio_inlier[q] = ratio;
+            dist_mean[q] = dmean;
+        }
+        if (st == 0 && k < prm.num_min_fine_match) st = 2;                                          // base.py:3338
+        double* T64q = T64 + (size_t)q * 16;
+        if (st != 0) {
+            if (tid < 16) {
+                const double v = (tid % 5 == 0) ? 1.0 : 0.0;
+                T64q[tid] = v;
+                T32[(size_t)q * 16 + tid] = (float)v;
+            }
+            if (tid == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
+            continue;
+        }
+        // D2: Procrustes on the matched pairs (weights None, eps 1e-6: weighted_svd.py:134-142)
+        if (tid < 32) {
+            double R[9], t[3];
+            warp_fit_segment(src_pts, tgt_pts, cs, ct, nullptr, k0, k, 1e-6, 0.f, 0, tid, R, t);
+            if (tid == 0) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    sh.Tsvd[r * 4 + 0] = R[r * 3 + 0]; sh.Tsvd[r * 4 + 1] = R[r * 3 + 1];
+                    sh.Tsvd[r * 4 + 2] = R[r * 3 + 2]; sh.Tsvd[r * 4 + 3] = t[r];
+                }
+                sh.Tsvd[12] = 0; sh.Tsvd[13] = 0; sh.Tsvd[14] = 0; sh.Tsvd[15] = 1;
+            }
+        }
+        __syncthreads();
+        IcpResult r;
+        r.fitness = 0; r.rmse = 0; r.iters = 0;
+        if (prm.icp_refine) {
+            // E1: ICP between the MATCHED points (base.py:3353-3358), init = T_svd
+            r = block_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, sh.Tsvd, prm.icp_threshold, prm.icp_max_iter,
+                          1e-6, 1e-6, T64q, nullptr, dyn, sh.icp);
+        } else if (tid < 16) {
+            T64q[tid] = sh.Tsvd[tid];
+        }
+        __syncthreads();
+        if (tid < 16) T32[(size_t)q * 16 + tid] = (float)T64q[tid];                                   // base.py:3366
+        if (tid == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// single-CTA exclusive scans over the pairs (Q is 10^3..10^4)
+__global__ void __launch_bounds__(1024)
+k_row_offsets(const int8_t* __restrict__ status, const int32_t* __restrict__ sp_ptr,
+              const int32_t* __restrict__ tp_ptr, int Q, int emit, int32_t* __restrict__ dense_off,
+              int32_t* __restrict__ t2s_off, int32_t* __restrict__ counts) {
+    __shared__ int wsum[2][32];
+    __shared__ int carry[3];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 3) carry[tid] = 0;
+    __syncthreads();
+    for (int base = 0; base < Q; base += 1024) {
+        const int q = base + tid;
+        int a = 0, b = 0, f = 0;
+        if (q < Q && status[q] == 0) {
+            f = 1;
+            if (emit) { a = sp_ptr[q + 1] - sp_ptr[q]; b = tp_ptr[q + 1] - tp_ptr[q]; }
+        }
+        int ia = a, ib = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int va = __shfl_up_sync(F4L_FULL, ia, o), vb = __shfl_up_sync(F4L_FULL, ib, o);
+            if (lane >= o) { ia += va; ib += vb; }
+        }
+        if (lane == 31) { wsum[0][wid] = ia; wsum[1][wid] = ib; }
+        const int fc = __syncthreads_count(f);
+        if (wid == 0) {
+            int sa = wsum[0][lane], sb = wsum[1][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int va = __shfl_up_sync(F4L_FULL, sa, o), vb = __shfl_up_sync(F4L_FULL, sb, o);
+                if (lane >= o) { sa += va; sb += vb; }
+            }
+            wsum[0][lane] = sa; wsum[1][lane] = sb;
+        }
+        __syncthreads();
+        const int pa = (wid ? wsum[0][wid - 1] : 0) + carry[0];
+        const int pb = (wid ? wsum[1][wid - 1] : 0) + carry[1];
+        if (q < Q) { dense_off[q] = pa + ia - a; t2s_off[q] = pb + ib - b; }
+        __syncthreads();
+        if (tid == 0) { carry[0] += wsum[0][31]; carry[1] += wsum[1][31]; carry[2] += fc; }
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = carry[0]; counts[2] = carry[1]; counts[3] = carry[2]; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_sparse_offsets(const int32_t* __restrict__ sparse_cnt, int Q, int32_t* __restrict__ sparse_off,
+                 int32_t* __restrict__ counts) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < Q; base += 1024) {
+        const int q = base + tid;
+        const int a = q < Q ? sparse_cnt[q] : 0;
+        int ia = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int va = __shfl_up_sync(F4L_FULL, ia, o);
+            if (lane >= o) ia += va;
+        }
+        if (lane == 31) wsum[wid] = ia;
+        __syncthreads();
+        if (wid == 0) {
+            int sa = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int va = __shfl_up_sync(F4L_FULL, sa, o);
+                if (lane >= o) sa += va;
+            }
+            wsum[lane] = sa;
+        }
+        __syncthreads();
+        if (q < Q) sparse_off[q] = (wid ? wsum[wid - 1] : 0) + carry + ia - a;
+        __syncthreads();
+        if (tid == 0) carry += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) counts[1] = carry;
+}
+
+// ------------------------------------------------------------------------------------------
+#define AA_THREADS 256
+#define AA_SMEM_PTS 8192
+
+__global__ void __launch_bounds__(AA_THREADS)
+k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
+               const int32_t* __restrict__ sp_idx, const int32_t* __restrict__ sp_ptr,
+               const int32_t* __restrict__ tp_idx, const int32_t* __restrict__ tp_ptr,
+               const int32_t* __restrict__ cs, const int32_t* __restrict__ kstart, const int32_t* __restrict__ K,
+               const int8_t* __restrict__ status, const float* __restrict__ T32, const double* __restrict__ rmse,
+               const int32_t* __restrict__ dense_off, const int32_t* __restrict__ t2s_off, int Q,
+               f4l_fine_params prm, const float* __restrict__ d_median_res, float* __restrict__ dense,
+               float* __restrict__ tgt2src, int32_t* __restrict__ nn, int32_t* __restrict__ sparse_cnt) {
+    extern __shared__ float sref[];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
+    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+        __syncthreads();
+        if (status[q] != 0 || !prm.icp_refine) {
+            if (tid == 0) sparse_cnt[q] = 0;
+            continue;
+        }
+        const int s0 = sp_ptr[q], ns = sp_ptr[q + 1] - s0;
+        const int t0 = tp_ptr[q], nt = tp_ptr[q + 1] - t0;
+        const float* Tq = T32 + (size_t)q * 16;
+        double R[9], tv[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            R[i * 3] = Tq[i * 4]; R[i * 3 + 1] = Tq[i * 4 + 1]; R[i * 3 + 2] = Tq[i * 4 + 2];
+            tv[i] = Tq[i * 4 + 3];
+        }
+        const bool assign_nn = prm.assign_type == 1;
+        const bool staged = nt <= AA_SMEM_PTS;
+        if (tid == 0) s_cnt = 0;
+        if ((assign_nn && staged) || prm.output_tgt2src) {
+            for (int j = tid; j < nt; j += AA_THREADS) {
+                float x, y, z;
+                load_ptf(tgt_pts, tp_idx, t0 + j, x, y, z);
+                if (assign_nn && staged) { sref[3 * j] = x; sref[3 * j + 1] = y; sref[3 * j + 2] = z; }
+                if (prm.output_tgt2src) {
+                    // base.py:3389-3390: R^T (q - t), the subtraction in f32
+                    const double dx = (double)(x - Tq[3]), dy = (double)(y - Tq[7]), dz = (double)(z - Tq[11]);
+                    float2* row = reinterpret_cast<float2*>(tgt2src + (size_t)(t2s_off[q] + j) * 6);
+                    row[0] = make_float2((float)(R[0] * dx + R[3] * dy + R[6] * dz), (float)(R[1] * dx + R[4] * dy + R[7] * dz));
+                    row[1] = make_float2((float)(R[2] * dx + R[5] * dy + R[8] * dz), x);
+                    row[2] = make_float2(y, z);
+                }
+            }
+        }
+        __syncthreads();
+        // adaptive threshold, base.py:3420-3423
+        double thr = rmse[q] * 2.0;
+        const double mres = d_median_res ? (double)d_median_res[0] : prm.median_max_resolution;
+        if (isnan(thr) || isinf(thr)) thr = mres;
+        thr = fmax(thr, mres);
+        const double thr2 = thr * thr;
+        int kept = 0;
+        for (int i = tid; i < ns; i += AA_THREADS) {
+            double x, y, z;
+            load_pt(src_pts, sp_idx, s0 + i, x, y, z);
+            const float mx = (float)(R[0] * x + R[1] * y + R[2] * z + tv[0]);
+            const float my = (float)(R[3] * x + R[4] * y + R[5] * z + tv[1]);
+            const float mz = (float)(R[6] * x + R[7] * y + R[8] * z + tv[2]);
+            float2* row = reinterpret_cast<float2*>(dense + (size_t)(dense_off[q] + i) * 6);
+            row[0] = make_float2((float)x, (float)y);
+            row[1] = make_float2((float)z, mx);
+            row[2] = make_float2(my, mz);
+            if (assign_nn) {
+                double best = INFINITY;
+                int bj = -1;
+                for (int j = 0; j < nt; ++j) {
+                    float gx, gy, gz;
+                    if (staged) { gx = sref[3 * j]; gy = sref[3 * j + 1]; gz = sref[3 * j + 2]; }
+                    else load_ptf(tgt_pts, tp_idx, t0 + j, gx, gy, gz);
+                    const double dx = (double)mx - (double)gx, dy = (double)my - (double)gy, dz = (double)mz - (double)gz;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < best) { best = d2; bj = j; }
+                }
+                const bool ok = best < thr2;
+                nn[s0 + i] = ok ? bj : -1;
+                kept += ok ? 1 : 0;
+            }
+        }
+        if (assign_nn) {
+            kept = warp_sum(kept);
+            if ((tid & 31) == 0 && kept) atomicAdd(&s_cnt, kept);
+            __syncthreads();
+            if (tid == 0) sparse_cnt[q] = 2 * s_cnt;          // appended twice (q4)
+        } else if (tid == 0) {
+            sparse_cnt[q] = K[q];                              // assign_all_src: the matched points
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_emit_sparse(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
+              const int32_t* __restrict__ sp_idx, const int32_t* __restrict__ sp_ptr,
+              const int32_t* __restrict__ tp_idx, const int32_t* __restrict__ tp_ptr,
+              const int32_t* __restrict__ cs, const int32_t* __restrict__ kstart, const int32_t* __restrict__ K,
+              const int8_t* __restrict__ status, const float* __restrict__ T32, const int32_t* __restrict__ nn,
+              const int32_t* __restrict__ sparse_cnt, const int32_t* __restrict__ sparse_off, int Q,
+              f4l_fine_params prm, float* __restrict__ sparse) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q || status[q] != 0 || !prm.icp_refine) return;
+    const int total = sparse_cnt[q];
+    if (total == 0) return;
+    const int o0 = sparse_off[q];
+    if (prm.assign_type == 1) {
+        const int s0 = sp_ptr[q], ns = sp_ptr[q + 1] - s0, t0 = tp_ptr[q];
+        const int half = total >> 1;
+        int written = 0;
+        for (int i0 = 0; i0 < ns; i0 += 32) {
+            const int i = i0 + lane;
+            const int j = i < ns ? nn[s0 + i] : -1;
+            const unsigned m = __ballot_sync(F4L_FULL, j >= 0);
+            if (j >= 0) {
+                const int r = written + __popc(m & ((1u << lane) - 1u));
+                float x, y, z, gx, gy, gz;
+                load_ptf(src_pts, sp_idx, s0 + i, x, y, z);
+                load_ptf(tgt_pts, tp_idx, t0 + j, gx, gy, gz);
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+                    float2* row = reinterpret_cast<float2*>(sparse + (size_t)(o0 + rep * half + r) * 6);
+                    row[0] = make_float2(x, y);
+                    row[1] = make_float2(z, gx);
+                    row[2] = make_float2(gy, gz);
+                }
+            }
+            written += __popc(m);
+        }
+    } else {
+        // assign_all_src: [A | T A] over the matched source points (base.py:3381-3384, 3412-3413)
+        const float* Tq = T32 + (size_t)q * 16;
+        const int k0 = kstart[q], k = K[q];
+        for (int i = lane; i < k; i += 32) {
+            double x, y, z;
+            load_pt(src_pts, cs, k0 + i, x, y, z);
+            float2* row = reinterpret_cast<float2*>(sparse + (size_t)(o0 + i) * 6);
+            row[0] = make_float2((float)x, (float)y);
+            row[1] = make_float2((float)z, (float)((double)Tq[0] * x + (double)Tq[1] * y + (double)Tq[2] * z + (double)Tq[3]));
+            row[2] = make_float2((float)((double)Tq[4] * x + (double)Tq[5] * y + (double)Tq[6] * z + (double)Tq[7]),
+                                 (float)((double)Tq[8] * x + (double)Tq[9] * y + (double)Tq[10] * z + (double)Tq[11]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+struct FineWs {
+    int32_t *cs, *ct, *kstart, *dense_off, *t2s_off, *nn, *sparse_cnt, *sparse_off;
+    size_t total;
+};
+
+static FineWs fine_layout(void* base, int n_src_items, int Q, int mode) {
+    FineWs w;
+    char* b = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = b + off; off += al(bytes); return (int32_t*)p; };
+    const size_t cap = (size_t)(mode == FINE_MODE_FUSION ? 2 : 1) * n_src_items;
+    w.cs = take(cap * 4);
+    w.ct = take(cap * 4);
+    w.kstart = take((size_t)Q * 4);
+    w.dense_off = take((size_t)Q * 4);
+    w.t2s_off = take((size_t)Q * 4);
+    w.nn = take((size_t)n_src_items * 4);
+    w.sparse_cnt = take((size_t)Q * 4);
+    w.sparse_off = take((size_t)Q * 4);
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t n_tgt_items, int32_t Q, int32_t mode) {
+    (void)n_tgt_items;
+    return fine_layout(nullptr, n_src_items < 0 ? 0 : n_src_items, Q < 0 ? 0 : Q, mode).total;
+}
+
+extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buffers* bf, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    F4L_REQUIRE(prm && bf, "null params");
+    const int Q = bf->Q;
+    const int n_src_items = bf->n_src_items;
+    F4L_REQUIRE(Q >= 0 && n_src_items >= 0, "negative size");
+    F4L_REQUIRE(prm->mode >= 0 && prm->mode <= 2, "unknown mode");
+    F4L_REQUIRE(bf->counts, "counts is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Q == 0) {
+        cudaMemsetAsync(bf->counts, 0, 4 * sizeof(int32_t), st);
+        return F4L_OK;
+    }
+    F4L_REQUIRE(bf->src_pts && bf->tgt_pts && bf->sp_idx && bf->sp_ptr && bf->tp_idx && bf->tp_ptr &&
+                    bf->tgt_patch_of_point && bf->pair_tgt_patch, "null input");
+    F4L_REQUIRE(prm->mode == FINE_MODE_2D || bf->corr3d, "corr3d is null");
+    F4L_REQUIRE(prm->mode == FINE_MODE_3D || bf->corr2d, "corr2d is null");
+    F4L_REQUIRE(bf->T && bf->T64 && bf->status && bf->K && bf->fitness && bf->rmse && bf->iters &&
+                    bf->ratio_inlier && bf->dist_mean && bf->dense && bf->sparse, "null output");
+    F4L_REQUIRE(!prm->output_tgt2src || bf->tgt2src, "tgt2src is null");
+    F4L_REQUIRE(!prm->icp_refine || prm->icp_threshold > 0.0, "icp_threshold must be > 0");
+    FineWs w = fine_layout(workspace, n_src_items, Q, prm->mode);
+    if (!workspace || workspace_bytes < w.total) {
+        f4l_set_error("f4l_fine_matching: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        return F4L_E_WORKSPACE;
+    }
+    static bool attr_set = false;
+    const size_t smem_fit = (size_t)ICP_SMEM_PTS * 3 * sizeof(float);
+    const size_t smem_aa = (size_t)AA_SMEM_PTS * 3 * sizeof(float);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_patch_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
+        cudaFuncSetAttribute(k_apply_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_aa);
+        attr_set = true;
+    }
+    k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
+                                                   bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
+                                                   prm->mode, w.cs, w.ct, w.kstart, bf->K);
+    const int grid_fit = Q < 148 * 16 ? Q : 148 * 16;
+    k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
+                                                        *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
+                                                        bf->iters, bf->ratio_inlier, bf->dist_mean);
+    k_row_offsets<<<1, 1024, 0, st>>>(bf->status, bf->sp_ptr, bf->tp_ptr, Q, prm->icp_refine ? 1 : 0, w.dense_off,
+                                      w.t2s_off, bf->counts);
+    const int grid_aa = Q < 148 * 8 ? Q : 148 * 8;
+    k_apply_assign<<<grid_aa, AA_THREADS, smem_aa, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
+                                                        bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T,
+                                                        bf->rmse, w.dense_off, w.t2s_off, Q, *prm,
+                                                        bf->d_median_resolution, bf->dense, bf->tgt2src, w.nn,
+                                                        w.sparse_cnt);
+    k_sparse_offsets<<<1, 1024, 0, st>>>(w.sparse_cnt, Q, w.sparse_off, bf->counts);
+    k_emit_sparse<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
+                                                   bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T, w.nn,
+                                                   w.sparse_cnt, w.sparse_off, Q, *prm, bf->sparse);
+    return f4l_check_launch("f4l_fine_matching");
+}

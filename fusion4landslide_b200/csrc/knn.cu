@@ -338,3 +338,137 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
     else k_grid_search<8><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
     return f4l_check_launch("f4l_knn_grid/search");
 }
+
+// ---- radix select (k-th smallest) -------------------------------------------------------------
+// Three passes of 11/11/10 bits over the order-preserving integer image of the floats; two ranks
+// are resolved in the same passes (np.median of an even count needs both middle elements).
+struct SelState {
+    unsigned prefix[2];
+    unsigned mask[2];
+    int k[2];
+};
+
+__global__ void k_sel_init(SelState* st, int* hist, int k, int k2) {
+    if (threadIdx.x == 0) {
+        st->prefix[0] = st->prefix[1] = 0u;
+        st->mask[0] = st->mask[1] = 0u;
+        st->k[0] = k;
+        st->k[1] = k2 >= 0 ? k2 : k;
+    }
+    for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_sel_hist(const float* __restrict__ x, int n, int stride, int offset, const SelState* __restrict__ st,
+           int shift, int bits, int* __restrict__ hist) {
+    __shared__ int sh[2][2048];
+    for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned p0 = st->prefix[0], m0 = st->mask[0], p1 = st->prefix[1], m1 = st->mask[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned u = f2ord(__ldg(x + (size_t)i * stride + offset));
+        unsigned b = (u >> shift) & ((1u << bits) - 1u);
+        if ((u & m0) == p0) atomicAdd(&sh[0][b], 1);
+        if ((u & m1) == p1) atomicAdd(&sh[1][b], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) {
+        int v = (&sh[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
+__global__ void k_sel_pick(SelState* st, int* hist, int shift, int bits) {
+    // two warps, one per rank; sequential scan over <= 2048 bins by lane 0 (tiny)
+    const int r = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && r < 2) {
+        int k = st->k[r], cum = 0, nb = 1 << bits, b = 0;
+        for (b = 0; b < nb; ++b) {
+            int h = hist[r * 2048 + b];
+            if (k < cum + h) break;
+            cum += h;
+        }
+        if (b == nb) b = nb - 1;
+        st->prefix[r] |= (unsigned)b << shift;
+        st->mask[r] |= (unsigned)(nb - 1) << shift;
+        st->k[r] = k - cum;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0;
+}
+
+__global__ void k_sel_out(const SelState* st, float* out, int two) {
+    out[0] = ord2f(st->prefix[0]);
+    if (two) out[1] = ord2f(st->prefix[1]);
+}
+
+extern "C" size_t f4l_select_kth_workspace_bytes(int32_t n) {
+    (void)n;
+    return align_up(sizeof(SelState)) + align_up(2 * 2048 * sizeof(int));
+}
+
+extern "C" int f4l_select_kth(const float* x, int32_t n, int32_t stride, int32_t offset, int32_t k, int32_t k2,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    F4L_REQUIRE(x && out && workspace, "null pointer");
+    F4L_REQUIRE(n >= 1 && stride >= 1 && offset >= 0 && k >= 0 && k < n && k2 < n, "bad rank / size");
+    if (workspace_bytes < f4l_select_kth_workspace_bytes(n)) {
+        f4l_set_error("f4l_select_kth: workspace too small");
+        return F4L_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SelState* s = (SelState*)workspace;
+    int* hist = (int*)((char*)workspace + align_up(sizeof(SelState)));
+    k_sel_init<<<1, 256, 0, st>>>(s, hist, k, k2);
+    const int blocks = min(f4l_div_up(n, 256 * 8), 148 * 4);
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+        k_sel_hist<<<blocks, 256, 0, st>>>(x, n, stride, offset, s, shifts[p], bits[p], hist);
+        k_sel_pick<<<1, 256, 0, st>>>(s, hist, shifts[p], bits[p]);
+    }
+    k_sel_out<<<1, 1, 0, st>>>(s, out, k2 >= 0);
+    return f4l_check_launch("f4l_select_kth");
+}
+
+// ---- A1: median point-cloud resolution ------------------------------------------------------------
+// max over the two epochs of the median distance to the nearest other point
+// (base.py:2716-2754, src/f2s3.py:481-508).  out[0] = resolution (device scalar).
+__global__ void k_medres_finish(const float* sel, float* out, int accumulate) {
+    // sel[0], sel[1]: the two middle squared distances (equal ranks when the count is odd)
+    double m = 0.5 * (sqrt((double)sel[0]) + sqrt((double)sel[1]));
+    float v = (float)m;
+    out[0] = accumulate ? fmaxf(out[0], v) : v;
+}
+
+extern "C" size_t f4l_median_resolution_workspace_bytes(int32_t n_src, int32_t n_tgt) {
+    int n = n_src > n_tgt ? n_src : n_tgt;
+    return f4l_knn_grid_workspace_bytes(n, n) + align_up((size_t)n * 2 * 4) * 2 + f4l_select_kth_workspace_bytes(n) + 256;
+}
+
+extern "C" int f4l_median_resolution(const float* src, int32_t n_src, const float* tgt, int32_t n_tgt, float* out,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    F4L_REQUIRE(src && tgt && out && workspace, "null pointer");
+    F4L_REQUIRE(n_src >= 2 && n_tgt >= 2, "need at least 2 points per epoch");
+    if (workspace_bytes < f4l_median_resolution_workspace_bytes(n_src, n_tgt)) {
+        f4l_set_error("f4l_median_resolution: workspace too small");
+        return F4L_E_WORKSPACE;
+    }
+    const int n = n_src > n_tgt ? n_src : n_tgt;
+    char* b = (char*)workspace;
+    size_t off = 0;
+    void* knn_ws = b + off; size_t knn_bytes = f4l_knn_grid_workspace_bytes(n, n); off += align_up(knn_bytes);
+    int32_t* idx = (int32_t*)(b + off); off += align_up((size_t)n * 2 * 4);
+    float* d2 = (float*)(b + off); off += align_up((size_t)n * 2 * 4);
+    void* sel_ws = b + off; size_t sel_bytes = f4l_select_kth_workspace_bytes(n); off += align_up(sel_bytes);
+    float* sel = (float*)(b + off);
+    for (int e = 0; e < 2; ++e) {
+        const float* p = e ? tgt : src;
+        const int m = e ? n_tgt : n_src;
+        int rc = f4l_knn_grid(p, m, p, m, 2, 0.f, 0.f, idx, d2, knn_ws, knn_bytes, stream);
+        if (rc) return rc;
+        // np.median: mean of elements (m-1)/2 and m/2 of the sorted 2nd-neighbour distances
+        rc = f4l_select_kth(d2, m, 2, 1, (m - 1) / 2, m / 2, sel, sel_ws, sel_bytes, stream);
+        if (rc) return rc;
+        k_medres_finish<<<1, 1, 0, (cudaStream_t)stream>>>(sel, out, e);
+    }
+    return f4l_check_launch("f4l_median_resolution");
+}

@@ -132,3 +132,91 @@ def segmented_nn(qpts, rpts, q_start, r_start, q_count=None, r_count=None, qidx=
         ptr(T, F32, True), ptr(thr, F32, True), ptr(nn), ptr(d2, F32, True),
         stream_ptr(qpts.device)), "f4l_segmented_nn")
     return nn, d2
+
+
+def median_resolution(src, tgt, out=None):
+    """A1.  Device scalar (1,) f32: max over epochs of the median nearest-other-point distance."""
+    if out is None:
+        out = _empty((1,), F32, src)
+    nbytes = lib().f4l_median_resolution_workspace_bytes(src.shape[0], tgt.shape[0])
+    ws = _workspace(nbytes, src.device)
+    check(lib().f4l_median_resolution(ptr(src, F32), src.shape[0], ptr(tgt, F32), tgt.shape[0], ptr(out, F32),
+                                      ptr(ws), ws.numel(), stream_ptr(src.device)), "f4l_median_resolution")
+    return out
+
+
+def select_kth(x, k, k2=-1, stride=1, offset=0):
+    n = x.numel() // stride
+    out = _empty((2,), F32, x)
+    ws = _workspace(lib().f4l_select_kth_workspace_bytes(n), x.device)
+    check(lib().f4l_select_kth(ptr(x, F32), n, stride, offset, k, k2, ptr(out), ptr(ws), ws.numel(),
+                               stream_ptr(x.device)), "f4l_select_kth")
+    return out
+
+
+class FineResult:
+    """Outputs of the fused fine-matching stage (device tensors; row counts in `counts`)."""
+    __slots__ = ("T", "T64", "status", "K", "fitness", "rmse", "iters", "ratio_inlier", "dist_mean",
+                 "dense", "sparse", "tgt2src", "counts")
+
+    def rows(self):
+        """Host sync: slice the row buffers to their true lengths (dense, sparse, tgt2src)."""
+        c = self.counts.tolist()
+        return (self.dense[:c[0]], self.sparse[:c[1]],
+                self.tgt2src[:c[2]] if self.tgt2src is not None else None)
+
+
+_MODES = {"only_3d": 0, "only_2d": 1, "fusion": 2}
+_ASSIGN = {"assign_all_src": 0, "assign_then_nn": 1}
+
+
+def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_point, pair_tgt_patch,
+                  corr3d=None, corr2d=None, mode="only_3d", remove_low_quality_patch_matches=True,
+                  num_min_matches_for_quality_check=10, thres_dist_diff=0.5, thres_inlier_ratio=0.15,
+                  num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
+                  output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
+                  d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None):
+    """Fused fine-matching stage of one tile (f4l_fine_matching).  n_*_items = sp_ptr[-1], tp_ptr[-1]
+    (pass them to avoid a device->host read)."""
+    dev = src_pts.device
+    Q = sp_ptr.numel() - 1
+    if n_src_items is None:
+        n_src_items = int(sp_ptr[-1].item()) if Q > 0 else 0
+    if n_tgt_items is None:
+        n_tgt_items = int(tp_ptr[-1].item()) if Q > 0 else 0
+    r = out
+    if r is None:
+        r = FineResult()
+        r.T = torch.empty((Q, 4, 4), dtype=F32, device=dev)
+        r.T64 = torch.empty((Q, 4, 4), dtype=F64, device=dev)
+        r.status = torch.empty((Q,), dtype=torch.int8, device=dev)
+        r.K = torch.empty((Q,), dtype=I32, device=dev)
+        r.fitness = torch.empty((Q,), dtype=F64, device=dev)
+        r.rmse = torch.empty((Q,), dtype=F64, device=dev)
+        r.iters = torch.empty((Q,), dtype=I32, device=dev)
+        r.ratio_inlier = torch.empty((Q,), dtype=F32, device=dev)
+        r.dist_mean = torch.empty((Q,), dtype=F32, device=dev)
+        r.dense = torch.empty((n_src_items, 6), dtype=F32, device=dev)
+        r.sparse = torch.empty((2 * n_src_items, 6), dtype=F32, device=dev)
+        r.tgt2src = torch.empty((n_tgt_items, 6), dtype=F32, device=dev) if output_tgt2src else None
+        r.counts = torch.empty((4,), dtype=I32, device=dev)
+    prm = _lib.FineParams(_MODES[mode], int(remove_low_quality_patch_matches), int(num_min_matches_for_quality_check),
+                          float(thres_dist_diff), float(thres_inlier_ratio), int(num_min_fine_match), int(icp_refine),
+                          _ASSIGN[assign_type], int(output_tgt2src), float(icp_threshold),
+                          float(median_max_resolution), int(icp_max_iter))
+    I64 = torch.int64
+    bf = _lib.FineBuffers(
+        ptr(src_pts, F32), src_pts.shape[0], ptr(tgt_pts, F32), tgt_pts.shape[0],
+        ptr(corr3d, I64, True), ptr(corr2d, I64, True),
+        ptr(sp_idx, I32), ptr(sp_ptr, I32), ptr(tp_idx, I32), ptr(tp_ptr, I32),
+        ptr(tgt_patch_of_point, I32), ptr(pair_tgt_patch, I32), Q, n_src_items, n_tgt_items,
+        ptr(d_median_resolution, F32, True),
+        ptr(r.T), ptr(r.T64), ptr(r.status), ptr(r.K), ptr(r.fitness), ptr(r.rmse), ptr(r.iters),
+        ptr(r.ratio_inlier), ptr(r.dist_mean), ptr(r.dense), ptr(r.sparse),
+        ptr(r.tgt2src, F32, True), ptr(r.counts))
+    nbytes = lib().f4l_fine_matching_workspace_bytes(n_src_items, n_tgt_items, Q, _MODES[mode])
+    ws = _workspace(nbytes, dev)
+    import ctypes
+    check(lib().f4l_fine_matching(ctypes.byref(prm), ctypes.byref(bf), ptr(ws), ws.numel(), stream_ptr(dev)),
+          "f4l_fine_matching")
+    return r

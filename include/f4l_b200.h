@@ -122,6 +122,13 @@ F4L_API int f4l_select_kth(const float* x, int32_t n, int32_t stride, int32_t of
                    int32_t k2, float* out, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* (a) A1: median point-cloud resolution = max over the two epochs of the median distance to the
+ * nearest OTHER point (k=2 self query).  Replaces base.py:2716-2754 and src/f2s3.py:481-508
+ * (_compute_median_resolution).  out[0] (device f32). */
+F4L_API size_t f4l_median_resolution_workspace_bytes(int32_t n_src, int32_t n_tgt);
+F4L_API int f4l_median_resolution(const float* src, int32_t n_src, const float* tgt, int32_t n_tgt,
+                          float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* (a) segmented 1-NN: for every query item of segment q, the nearest reference item of the SAME
  * segment pair, optionally after applying T[q] to the query, kept iff d2 < thr[q]^2.
  * Replaces base.py:48-97 refine_dvfs_with_threshold (Open3D KDTreeFlann per point).
@@ -179,6 +186,10 @@ typedef struct f4l_fine_buffers {
     const int32_t* tgt_patch_of_point;          /* (n_tgt) id of the tgt patch owning each point, -1 none */
     const int32_t* pair_tgt_patch;              /* (Q) tgt patch id of each pair */
     int32_t Q;
+    int32_t n_src_items;                        /* sp_ptr[Q] (host copy, sizes the workspace) */
+    int32_t n_tgt_items;                        /* tp_ptr[Q] */
+    const float* d_median_resolution;           /* device scalar overriding params.median_max_resolution
+                                                   (output of f4l_median_resolution), or NULL */
     /* outputs (caller-allocated upper bounds) */
     float* T;              /* (Q,16) f32 row-major, identity when not fitted */
     double* T64;           /* (Q,16) */

@@ -83,3 +83,26 @@ def test_knn_edge_cases(cuda):
     line[:, 0] = rng.uniform(0, 10, 2000)
     i, dd = ops.knn_grid(torch.from_numpy(line).to(cuda), torch.from_numpy(line).to(cuda), 2)
     _check(line, line, 2, i, dd)
+
+
+def test_select_kth_and_median_resolution(cuda, golden_dir):
+    from fusion4landslide_b200 import ops
+    rng = np.random.default_rng(13)
+    for n in (1, 2, 3, 1000, 65_537, 300_000):
+        x = (rng.random(n) ** 2).astype(np.float32)
+        if n > 10:
+            x[rng.integers(0, n, 5)] = x[0]          # duplicates
+        xs = np.sort(x)
+        for k in sorted({0, (n - 1) // 2, n // 2, n - 1}):
+            k2 = min(k + 1, n - 1)
+            out = ops.select_kth(torch.from_numpy(x).to(cuda), k, k2).cpu().numpy()
+            assert out[0] == xs[k] and out[1] == xs[k2], (n, k)
+    # strided column of an (N,2) array, as the median-resolution path uses it
+    y = rng.random((5000, 2)).astype(np.float32)
+    out = ops.select_kth(torch.from_numpy(y).to(cuda), 2499, 2500, stride=2, offset=1).cpu().numpy()
+    ys = np.sort(y[:, 1])
+    assert out[0] == ys[2499] and out[1] == ys[2500]
+    # A1 against the reference's sklearn call pattern (golden)
+    z = np.load(os.path.join(golden_dir, "knn_sklearn.npz"))
+    med = ops.median_resolution(torch.from_numpy(z["a"]).to(cuda), torch.from_numpy(z["b"]).to(cuda)).item()
+    assert abs(med - z["median_resolution"][0]) < 1e-6 * z["median_resolution"][0] + 1e-8

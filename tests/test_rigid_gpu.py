@@ -50,6 +50,10 @@ def test_kabsch_golden(cuda, golden_dir, variant, gold):
         # the reference computes in fp32 at absolute coordinates: its own rounding noise is a few
         # f32 ulps of |p| (measured <= 1.6e-5 m at |p| ~ 35 m), on top of the 1e-5 m budget
         tol_ref = TOL + 4 * np.finfo(np.float32).eps * np.abs(s).max()
+        if variant == 1:
+            # functions.py:57-60 forms the covariance through a dense NxN f32 matmul; for N >= 1000 its
+            # accumulated rounding reaches 5e-5 m (same bound as tests/test_oracle_golden.py)
+            tol_ref = 5e-5
         assert _act_err(R[i], t[i], z[k + "_R"], z[k + "_t"], s) < tol_ref, ("reference", k)
 
 
