@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Headline benchmark: displacement-field points/sec of the patch-wise hot path.
+
+Workload (BASELINE.json configs[4], "C5"): a 50 M-point epoch pair as 64 synthetic tiles of
+781 250 points per epoch, ~256-point patches, point correspondences resident as (N,2) int64 --
+the shape fusion4landslide processes tile by tile.  One step = one pass of the hot path over all
+tiles: A1 median resolution (k=2 self-kNN of both epochs) and the fused fine-matching stage
+(F2 select, F3 rigidity, D2 Procrustes, E1 per-patch ICP, D5 apply -> dense DVF, A4 1-NN assign ->
+sparse DVF).  Tiles are independent: with N GPUs they are dealt round-robin (equal tiles, LPT is a
+no-op) and the per-patch transforms and the dense DVF are all-gathered over NCCL at the end of the
+step ("strong" scaling: the 50 M-point job is fixed).
+
+    python bench.py --gpus N --steps K --warmup W          (torchrun for N > 1)
+    python bench.py --impl reference ...                   the CPU arm (oracle port, all host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "displacement_field_points_per_sec"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tiles", type=int, default=64)
+    ap.add_argument("--tile-pts", type=int, default=781_250)
+    ap.add_argument("--patch-pts", type=int, default=256)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="patch pairs in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("C5: %d tiles x %d pts/epoch (%.1fM-point epoch pair), ~%d-pt patches, fusion4landslide fine-matching "
+            "path (A1 median-resolution kNN + F2/F3/D2/E1/D5/A4) per tile" %
+            (a.tiles, a.tile_pts, a.tiles * a.tile_pts / 1e6, a.patch_pts))
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                power.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic bytes per launch of each kernel, given the tile quantities (DESIGN.md "Kernels")
+def algorithmic_bytes(name, q):
+    N, M, P = q["n_src"], q["n_tgt"], q["pairs"]
+    ns, nt, K = q["src_items"], q["tgt_items"], q["matched"]
+    table = {
+        # sorted float4 refs once + sorted float4 queries once + k=2 (idx i32 + d2 f32) out; per epoch call
+        "k_grid_search": 16 * N + 16 * N + 8 * 2 * N,
+        "k_bin_count": 12 * N + 4 * N,
+        "k_bin_scatter": 12 * N + 4 * N + 16 * N,
+        # corr col1 (8 B) + labels (4 B) + point index (4 B) per src patch item, 8 B per selected pair
+        "k_select_corr": 16 * ns + 8 * K,
+        # matched pairs: 8 B indices + 24 B coordinates, outputs 64+128+... per pair
+        "k_patch_fit": 32 * K + 240 * P,
+        # src patch points 12+4, tgt patch points 12+4, dense rows 24, nn 4
+        "k_apply_assign": 16 * ns + 16 * nt + 24 * ns + 4 * ns + 64 * P,
+        "k_emit_sparse": 8 * ns + 2 * 24 * q["sparse_half"] + 24 * q["sparse_half"],
+    }
+    return table.get(name)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch.distributed as dist
+    from fusion4landslide_b200 import _lib, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    cfg = pipeline.FineConfig()
+
+    my_tiles = list(range(rank, a.tiles, world))           # equal tiles: round-robin == LPT
+    tiles, host_tiles = [], []
+    for t in my_tiles:
+        d = synth.make_tile(a.tile_pts, seed=a.seed * 100003 + t, device=dev, patch_pts=a.patch_pts,
+                            origin=(0.0, 0.0))
+        tiles.append(pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"]))
+        del d
+    torch.cuda.synchronize()
+
+    # per-rank output arena: every tile writes its dense rows / transforms into its slice, the
+    # arena is what the all-gather ships
+    cap_rows = sum(t.n_src_items for t in tiles)
+    cap_pairs = sum(t.n_pairs for t in tiles)
+    if world > 1:
+        caps = torch.tensor([cap_rows, cap_pairs], device=dev, dtype=torch.int64)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX)
+        cap_rows, cap_pairs = int(caps[0]), int(caps[1])
+    dense_arena = torch.empty((cap_rows, 6), dtype=torch.float32, device=dev)
+    T_arena = torch.empty((cap_pairs, 4, 4), dtype=torch.float32, device=dev)
+    n_tiles_max = (a.tiles + world - 1) // world
+    counts_arena = torch.zeros((n_tiles_max, 4), dtype=torch.int32, device=dev)
+    outs, meds = [], torch.empty((max(len(tiles), 1),), dtype=torch.float32, device=dev)
+    ro = po = 0
+    from fusion4landslide_b200.ops import FineResult
+    for i, t in enumerate(tiles):
+        r = FineResult()
+        Q = t.n_pairs
+        r.T = T_arena[po:po + Q]
+        r.T64 = torch.empty((Q, 4, 4), dtype=torch.float64, device=dev)
+        r.status = torch.empty((Q,), dtype=torch.int8, device=dev)
+        r.K = torch.empty((Q,), dtype=torch.int32, device=dev)
+        r.fitness = torch.empty((Q,), dtype=torch.float64, device=dev)
+        r.rmse = torch.empty((Q,), dtype=torch.float64, device=dev)
+        r.iters = torch.empty((Q,), dtype=torch.int32, device=dev)
+        r.ratio_inlier = torch.empty((Q,), dtype=torch.float32, device=dev)
+        r.dist_mean = torch.empty((Q,), dtype=torch.float32, device=dev)
+        r.dense = dense_arena[ro:ro + t.n_src_items]
+        r.sparse = torch.empty((2 * t.n_src_items, 6), dtype=torch.float32, device=dev)
+        r.tgt2src = None
+        r.counts = counts_arena[i]
+        outs.append(r)
+        ro += t.n_src_items
+        po += Q
+    if world > 1:
+        gathered_dense = torch.empty((world * cap_rows, 6), dtype=torch.float32, device=dev)
+        gathered_T = torch.empty((world * cap_pairs, 4, 4), dtype=torch.float32, device=dev)
+        gathered_counts = torch.empty((world * n_tiles_max * 4,), dtype=torch.int32, device=dev)
+
+    def step():
+        for i, t in enumerate(tiles):
+            pipeline.displacement_field(t, cfg, out=outs[i], med_out=meds[i:i + 1])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered_T, T_arena)
+            dist.all_gather_into_tensor(gathered_dense, dense_arena)
+            dist.all_gather_into_tensor(gathered_counts, counts_arena.reshape(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    L.f4l_launch_count_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.f4l_launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms[0]) / a.steps
+
+    # units processed: source points that received a displacement vector (dense DVF rows), all ranks
+    rows = counts_arena[:, 0].sum().to(torch.int64).reshape(1)
+    stat = torch.stack([rows[0], torch.tensor(sum(t.src.shape[0] for t in tiles), device=dev),
+                        torch.tensor(launches, device=dev)]).to(torch.int64)
+    if world > 1:
+        dist.all_reduce(stat)
+    dvf_points, src_points, launches_all = int(stat[0]), int(stat[1]), int(stat[2])
+    value = dvf_points / (ms_step * 1e-3)
+
+    # ---- e2e: same step through the host-buffer API (H2D inputs + D2H results inside the timing) ----
+    e2e = None
+    if not a.no_e2e:
+        host_tiles = [pipeline.HostTile(t) for t in tiles]
+        host_out = {}
+        for ht in host_tiles[:2]:
+            pipeline.displacement_field_host(ht, cfg, dev, host_out)       # warm the pinned result buffers
+        barrier()
+        n_e2e = max(1, min(a.steps, 3))
+        t0 = time.perf_counter()
+        e0.record()
+        h2d = d2h = 0
+        rows_e2e = 0
+        for _ in range(n_e2e):
+            for ht in host_tiles:
+                res, bi, bo = pipeline.displacement_field_host(ht, cfg, dev, host_out)
+                h2d += bi
+                d2h += bo
+                rows_e2e += res["dense"].shape[0]
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1) / n_e2e
+        te = torch.tensor([ms_e2e, float(rows_e2e) / n_e2e, float(h2d) / n_e2e, float(d2h) / n_e2e], device=dev,
+                          dtype=torch.float64)
+        if world > 1:
+            mx = te[:1].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = te[1:].clone()
+            dist.all_reduce(sm)
+            te = torch.cat([mx, sm])
+        e2e = {"value": float(te[1]) / (float(te[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(te[0]),
+               "steps": n_e2e, "h2d_bytes_per_step": int(te[2]), "d2h_bytes_per_step": int(te[3]),
+               "note": "pinned host inputs -> device, path, dense+sparse DVF/transforms -> pinned host; serial per tile"}
+        del host_tiles, host_out
+
+    # ---- roofline leg: the same step with in-stream per-kernel CUDA events -----------------------
+    roofline, kernel_table = None, None
+    if rank == 0:
+        L.f4l_profile_reset()
+        L.f4l_profile_enable(1)
+        for _ in range(max(1, min(a.steps, 3))):
+            for i, t in enumerate(tiles):
+                pipeline.displacement_field(t, cfg, out=outs[i], med_out=meds[i:i + 1])
+        torch.cuda.synchronize()
+        L.f4l_profile_enable(0)
+        tab = _lib.profile_table()
+        tot = sum(v[0] for v in tab.values()) or 1.0
+        kernel_table = {k: {"ms_avg": v[0] / v[1], "launches": v[1], "share": v[0] / tot}
+                        for k, v in sorted(tab.items(), key=lambda kv: -kv[1][0])}
+        top = next(iter(kernel_table))
+        t0_ = tiles[0]
+        c = counts_arena[0].tolist()
+        q = dict(n_src=t0_.src.shape[0], n_tgt=t0_.tgt.shape[0], pairs=t0_.n_pairs, src_items=t0_.n_src_items,
+                 tgt_items=t0_.n_tgt_items, matched=int(outs[0].K.sum()), sparse_half=c[1] // 2)
+        peak, peak_src = load_peaks()
+        ab = algorithmic_bytes(top, q)
+        ach = ab / (kernel_table[top]["ms_avg"] * 1e-3) / 1e9 if ab else None
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": (ach / peak) if ach else None, "traffic": None,
+                    "algorithmic_bytes_per_launch": ab, "ms_per_launch": kernel_table[top]["ms_avg"],
+                    "share_of_step": kernel_table[top]["share"], "peak_source": peak_src,
+                    "note": "kernel durations from in-stream CUDA events in a separate profiled pass of the same step"}
+        # also report the two kernels the north star names (kNN search, Kabsch/ICP reduction)
+        for name in ("k_grid_search", "k_patch_fit", "k_apply_assign"):
+            if name in kernel_table:
+                b = algorithmic_bytes(name, q)
+                kernel_table[name]["hbm_frac"] = b / (kernel_table[name]["ms_avg"] * 1e-3) / 1e9 / peak
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        cpu = cpu_arm_sample(a, tiles[0], cfg, target_seconds=15.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 i/o, f64 accumulation", "data": "synthetic",
+            "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts,
+                       "src_points_per_step": src_points, "dvf_points_per_step": dvf_points,
+                       "parallelism": "tile-sharded x%d, all-gather of transforms + dense DVF" % world,
+                       "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
+                             (sum(t.nbytes() for t in tiles) * world / 1e9),
+                       "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type},
+            "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline,
+            "kernels": kernel_table, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_arm_sample(a, tile, cfg, target_seconds=15.0, workers=None, pairs=None):
+    """Time the oracle port on a bounded sample of tile 0 (host copy).  Returns the cpu_baseline dict."""
+    from oracle import cpu_path
+    src = tile.src.cpu().numpy()
+    tgt = tile.tgt.cpu().numpy()
+    corr = tile.corr3d.cpu().numpy()
+    sp_ptr, sp_idx = tile.sp_ptr.cpu().numpy(), tile.sp_idx.cpu().numpy().astype("int64")
+    tp_ptr, tp_idx = tile.tp_ptr.cpu().numpy(), tile.tp_idx.cpu().numpy().astype("int64")
+    Q = tile.n_pairs
+    spt_src = [sp_idx[sp_ptr[q]:sp_ptr[q + 1]] for q in range(Q)]
+    spt_tgt = [tp_idx[tp_ptr[q]:tp_ptr[q + 1]] for q in range(Q)]
+    workers = workers or os.cpu_count() or 1
+    if pairs is None:
+        pairs = a.cpu_sample_pairs or min(Q, max(64, int(target_seconds * workers * 150)))   # ~6 ms per pair per core
+    kw = dict(mode=cfg.mode, remove_low_quality_patch_matches=cfg.remove_low_quality_patch_matches,
+              num_min_matches_for_quality_check=cfg.num_min_matches_for_quality_check,
+              thres_dist_diff=cfg.thres_dist_diff, thres_inlier_ratio=cfg.thres_inlier_ratio,
+              num_min_fine_match=cfg.num_min_fine_match, icp_refine=cfg.icp_refine, assign_type=cfg.assign_type,
+              output_tgt2src=cfg.output_tgt2src, icp_threshold=cfg.icp_threshold, icp_max_iter=cfg.icp_max_iter)
+    r = cpu_path.run_tile(src, tgt, corr, spt_src, spt_tgt, workers=workers, max_pairs=pairs, **kw)
+    # the median-resolution kNN covers the whole tile, the fine matching only the sampled pairs:
+    # scale the kNN time by the sampled fraction so both legs describe the same points
+    frac = r["src_points"] / max(1, src.shape[0])
+    secs = r["seconds_fine"] + r["seconds_median"] * frac
+    return {"value": r["dense_rows"] / secs, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": "%d of %d patch pairs of tile 0 (%d src points; %.1f s fine matching + %.1f s x %.3f median-"
+                      "resolution kNN); oracle/cpu_path.py: numpy + scipy cKDTree restatement of base.py:3254-3438, "
+                      "patch pairs spread over %d forked workers" %
+                      (r["pairs"], Q, r["src_points"], r["seconds_fine"], r["seconds_median"], frac, workers),
+            "seconds": secs}
+
+
+def run_reference(a):
+    """--impl reference: the CPU arm alone, on this box's host cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from fusion4landslide_b200 import pipeline, synth
+    cfg = pipeline.FineConfig()
+    d = synth.make_tile(a.tile_pts, seed=a.seed * 100003, device="cpu", patch_pts=a.patch_pts)
+    tile = pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"])
+    workers = os.cpu_count() or 1
+    per_step = a.cpu_sample_pairs or max(32, min(tile.n_pairs, int(8.0 * workers * 150)))
+    vals, secs = [], []
+    for s in range(a.warmup + a.steps):
+        r = cpu_arm_sample(a, tile, cfg, workers=workers, pairs=per_step)
+        if s >= a.warmup:
+            vals.append(r["value"])
+            secs.append(r["seconds"])
+        if s == 0 and r["seconds"] > 40:        # keep the whole run within a few minutes
+            per_step = max(32, int(per_step * 20 / r["seconds"]))
+    v = sum(vals) / len(vals)
+    ms = 1e3 * sum(secs) / len(secs)
+    r["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 (numpy/scipy), f32 i/o", "data": "synthetic",
+            "config": {"workload": workload_name(a), "step": "bounded sample: %d patch pairs of one tile per step" % per_step},
+            "cpu_baseline": r,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

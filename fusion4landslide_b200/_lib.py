@@ -51,6 +51,12 @@ P = c_void_p
 SIGNATURES = {
     "f4l_abi_version": (c_int, []),
     "f4l_last_error": (ctypes.c_char_p, []),
+    "f4l_launch_count": (ctypes.c_longlong, []),
+    "f4l_launch_count_reset": (None, []),
+    "f4l_profile_enable": (None, [c_int]),
+    "f4l_profile_collect": (c_int, []),
+    "f4l_profile_get": (c_int, [c_int, ctypes.c_char_p, c_int, ctypes.POINTER(c_f64), ctypes.POINTER(ctypes.c_longlong)]),
+    "f4l_profile_reset": (None, []),
     "f4l_segmented_kabsch": (c_int, [P, P, P, P, P, P, P, c_i32, c_f32, c_f32, c_int, P, P, P, P, P, P]),
     "f4l_apply_transforms": (c_int, [P, P, P, P, P, P, c_i32, P, c_int, P, P, P]),
     "f4l_rigidity_check": (c_int, [P, P, P, P, P, P, c_i32, c_f32, P, P, P]),
@@ -117,3 +123,17 @@ def ptr(t, dtype=None, allow_none=False):
 
 def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def profile_table():
+    """Collect the in-stream kernel timings: {kernel name: (total ms, launches)}."""
+    L = lib()
+    n = L.f4l_profile_collect()
+    out = {}
+    buf = ctypes.create_string_buffer(128)
+    ms = c_f64()
+    cnt = ctypes.c_longlong()
+    for i in range(n):
+        if L.f4l_profile_get(i, buf, 128, ctypes.byref(ms), ctypes.byref(cnt)) == 0:
+            out[buf.value.decode()] = (ms.value, cnt.value)
+    return out

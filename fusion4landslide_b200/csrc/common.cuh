@@ -12,6 +12,12 @@
 // ---- host-side error plumbing -------------------------------------------------------------
 void f4l_set_error(const char* fmt, ...);
 int f4l_check_launch(const char* what);
+void f4l_count_launches(int n);   // bookkeeping for f4l_launch_count()
+// Timeline mark on `st` before a kernel launch: counts the launch and, when profiling is enabled
+// (f4l_profile_enable), records a CUDA event; the time between two consecutive marks of a stream
+// is attributed to the kernel named by the first.  name == nullptr closes the current interval.
+void f4l_mark(const char* name, cudaStream_t st);
+int f4l_finish(const char* what, void* stream);   // closing mark + launch error check
 
 #define F4L_REQUIRE(cond, msg)                       \
     do {                                             \
@@ -38,6 +44,47 @@ __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F4L_FULL, v, o);
     return v;
+}
+
+// order-preserving map float <-> uint32 (radix select, atomic min/max on floats)
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Block-wide k-th smallest (0-based rank) of vals[0..n) by 4 passes of an 8-bit radix select.
+// hist: 256 unsigned in shared memory, state: 2 unsigned in shared memory.  All threads return it.
+__device__ inline float block_select_kth(const float* vals, int n, int rank, unsigned* hist, unsigned* state) {
+    if (threadIdx.x == 0) { state[0] = 0u; state[1] = (unsigned)rank; }
+    unsigned mask = 0u;
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        const unsigned prefix = state[0];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned u = f2ord(vals[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned r = state[1], cum = 0u;
+            int b = 0;
+            for (b = 0; b < 256; ++b) {
+                if (r < cum + hist[b]) break;
+                cum += hist[b];
+            }
+            if (b == 256) b = 255;
+            state[0] = prefix | ((unsigned)b << shift);
+            state[1] = r - cum;
+        }
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    return ord2f(state[0]);
 }
 
 // segment bounds: CSR when count == nullptr

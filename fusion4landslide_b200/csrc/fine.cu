@@ -442,24 +442,30 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
         cudaFuncSetAttribute(k_apply_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_aa);
         attr_set = true;
     }
+    f4l_mark("k_select_corr", st);
     k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
                                                    bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
                                                    prm->mode, w.cs, w.ct, w.kstart, bf->K);
     const int grid_fit = Q < 148 * 16 ? Q : 148 * 16;
+    f4l_mark("k_patch_fit", st);
     k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
                                                         *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
                                                         bf->iters, bf->ratio_inlier, bf->dist_mean);
+    f4l_mark("k_row_offsets", st);
     k_row_offsets<<<1, 1024, 0, st>>>(bf->status, bf->sp_ptr, bf->tp_ptr, Q, prm->icp_refine ? 1 : 0, w.dense_off,
                                       w.t2s_off, bf->counts);
     const int grid_aa = Q < 148 * 8 ? Q : 148 * 8;
+    f4l_mark("k_apply_assign", st);
     k_apply_assign<<<grid_aa, AA_THREADS, smem_aa, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
                                                         bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T,
                                                         bf->rmse, w.dense_off, w.t2s_off, Q, *prm,
                                                         bf->d_median_resolution, bf->dense, bf->tgt2src, w.nn,
                                                         w.sparse_cnt);
+    f4l_mark("k_sparse_offsets", st);
     k_sparse_offsets<<<1, 1024, 0, st>>>(w.sparse_cnt, Q, w.sparse_off, bf->counts);
+    f4l_mark("k_emit_sparse", st);
     k_emit_sparse<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
                                                    bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T, w.nn,
                                                    w.sparse_cnt, w.sparse_off, Q, *prm, bf->sparse);
-    return f4l_check_launch("f4l_fine_matching");
+    return f4l_finish("f4l_fine_matching", stream);
 }

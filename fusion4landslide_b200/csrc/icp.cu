@@ -52,10 +52,11 @@ extern "C" int f4l_patch_icp(const float* src, const int32_t* src_idx, const int
         attr_set = true;
     }
     const int grid = Q < 148 * 16 ? Q : 148 * 16;
+    f4l_mark("k_patch_icp", (cudaStream_t)stream);
     k_patch_icp<<<grid, ICP_THREADS, smem, (cudaStream_t)stream>>>(
         src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
         rel_fitness, rel_rmse, T, fitness, rmse, iters, corr);
-    return f4l_check_launch("f4l_patch_icp");
+    return f4l_finish("f4l_patch_icp", stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -135,7 +136,8 @@ extern "C" int f4l_segmented_nn(const float* qpts, const int32_t* qidx, const in
         attr_set = true;
     }
     const int grid = Q < 148 * 8 ? Q : 148 * 8;
+    f4l_mark("k_segmented_nn", (cudaStream_t)stream);
     k_segmented_nn<<<grid, SNN_THREADS, smem, (cudaStream_t)stream>>>(qpts, qidx, q_start, q_count, rpts, ridx,
                                                                      r_start, r_count, Q, T, thr, nn, d2);
-    return f4l_check_launch("f4l_segmented_nn");
+    return f4l_finish("f4l_segmented_nn", stream);
 }

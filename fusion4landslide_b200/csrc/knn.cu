@@ -24,14 +24,6 @@ struct GridParams {
 };
 
 // ---- bounding box ------------------------------------------------------------------------
-__device__ __forceinline__ unsigned f2ord(float f) {
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
 __global__ void k_bbox_init(unsigned* bb) {
     if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
     else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
@@ -282,12 +274,17 @@ extern "C" size_t f4l_knn_grid_workspace_bytes(int32_t N, int32_t M) {
 }
 
 static int bin_points(const float* p, int n, const KnnWs& w, int mc, float4* sorted, cudaStream_t st) {
+    f4l_mark("#memset_cells", st);
     cudaMemsetAsync(w.cell_count, 0, (size_t)(mc + 1) * 4, st);
     const int blocks = min(f4l_div_up(n, 256), 148 * 8);
+    f4l_mark("k_bin_count", st);
     k_bin_count<<<blocks, 256, 0, st>>>(p, n, w.gp, w.cid, w.cell_count);
     size_t cb = w.cub_bytes;
+    f4l_count_launches(1); f4l_mark("cub_exclusive_scan", st);   // cub: init + scan kernels
     cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.cell_count, w.cell_start, mc + 1, st);
+    f4l_mark("#memset_cells", st);
     cudaMemsetAsync(w.cell_count, 0, (size_t)(mc + 1) * 4, st);
+    f4l_mark("k_bin_scatter", st);
     k_bin_scatter<<<blocks, 256, 0, st>>>(p, n, w.cid, w.cell_start, w.cell_count, sorted);
     return f4l_check_launch("f4l_knn_grid/bin");
 }
@@ -301,8 +298,9 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
     F4L_REQUIRE(q && idx && d2, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 0) {
+        f4l_mark("k_fill_none", st);
         k_fill_none<<<f4l_div_up((long long)N * k, 256), 256, 0, st>>>(N, k, idx, d2);
-        return f4l_check_launch("f4l_knn_grid/fill");
+        return f4l_finish("f4l_knn_grid/fill", stream);
     }
     F4L_REQUIRE(r && workspace, "null pointer");
     KnnWs w = knn_layout(workspace, N, M);
@@ -311,8 +309,11 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
         return F4L_E_WORKSPACE;
     }
     const int mc = knn_max_cells(M);
+    f4l_mark("k_bbox_init", st);
     k_bbox_init<<<1, 32, 0, st>>>(w.bb);
+    f4l_mark("k_bbox", st);
     k_bbox<<<min(f4l_div_up(M, 256), 148 * 4), 256, 0, st>>>(r, M, w.bb);
+    f4l_mark("k_grid_params", st);
     k_grid_params<<<1, 1, 0, st>>>(w.bb, M, cell, mc, w.gp);
     int rc = bin_points(r, M, w, mc, w.sorted_r, st);
     if (rc) return rc;
@@ -322,21 +323,26 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
     if (q != r || N != M) {
         // bin the queries on the same grid (queries outside the box clamp to border cells); their
         // table is scanned in place in cell_count, cell_start stays the reference table
+        f4l_mark("#memset_cells", st);
         cudaMemsetAsync(w.cell_count, 0, (size_t)(mc + 1) * 4, st);
         const int blocks = min(f4l_div_up(N, 256), 148 * 8);
+        f4l_mark("k_bin_count", st);
         k_bin_count<<<blocks, 256, 0, st>>>(q, N, w.gp, w.cid, w.cell_count);
         size_t cb = w.cub_bytes;
+        f4l_count_launches(1); f4l_mark("cub_exclusive_scan", st);
         cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.cell_count, w.cell_count, mc + 1, st);  // in place
+        f4l_mark("k_bin_scatter_advance", st);
         k_bin_scatter_advance<<<blocks, 256, 0, st>>>(q, N, w.cid, w.cell_count, w.sorted_q);
         qs = w.sorted_q;
     }
     const float max_r2 = max_radius > 0.f ? max_radius * max_radius : INFINITY;
     const int blocks = f4l_div_up(N, 128);
+    f4l_mark("k_grid_search", st);
     if (k == 1) k_grid_search<1><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
     else if (k == 2) k_grid_search<2><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
     else if (k <= 4) k_grid_search<4><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
     else k_grid_search<8><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
-    return f4l_check_launch("f4l_knn_grid/search");
+    return f4l_finish("f4l_knn_grid/search", stream);
 }
 
 // ---- radix select (k-th smallest) -------------------------------------------------------------
@@ -378,18 +384,38 @@ k_sel_hist(const float* __restrict__ x, int n, int stride, int offset, const Sel
     }
 }
 
-__global__ void k_sel_pick(SelState* st, int* hist, int shift, int bits) {
-    // two warps, one per rank; sequential scan over <= 2048 bins by lane 0 (tiny)
-    const int r = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0 && r < 2) {
-        int k = st->k[r], cum = 0, nb = 1 << bits, b = 0;
-        for (b = 0; b < nb; ++b) {
-            int h = hist[r * 2048 + b];
-            if (k < cum + h) break;
-            cum += h;
+__global__ void __launch_bounds__(512) k_sel_pick(SelState* st, int* hist, int shift, int bits) {
+    // 512 threads: threads [0,256) resolve rank 0, [256,512) rank 1; each owns 8 consecutive bins
+    __shared__ int part[2][256];
+    const int r = threadIdx.x >> 8, t = threadIdx.x & 255;
+    const int nb = 1 << bits;
+    int local[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int b = t * 8 + i;
+        local[i] = b < nb ? hist[r * 2048 + b] : 0;
+        sum += local[i];
+    }
+    part[r][t] = sum;
+    __syncthreads();
+    // exclusive prefix of the 256 partial sums (Hillis-Steele in shared memory)
+    for (int o = 1; o < 256; o <<= 1) {
+        const int v = t >= o ? part[r][t - o] : 0;
+        __syncthreads();
+        part[r][t] += v;
+        __syncthreads();
+    }
+    const int k = st->k[r];
+    const int before = part[r][t] - sum;     // elements in bins before this thread's first bin
+    __syncthreads();
+    if (k >= before && k < before + sum) {
+        int cum = before, b = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (k >= cum + local[i]) { cum += local[i]; b = i + 1; }
+            else break;
         }
-        if (b == nb) b = nb - 1;
-        st->prefix[r] |= (unsigned)b << shift;
+        st->prefix[r] |= (unsigned)(t * 8 + b) << shift;
         st->mask[r] |= (unsigned)(nb - 1) << shift;
         st->k[r] = k - cum;
     }
@@ -418,15 +444,19 @@ extern "C" int f4l_select_kth(const float* x, int32_t n, int32_t stride, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     SelState* s = (SelState*)workspace;
     int* hist = (int*)((char*)workspace + align_up(sizeof(SelState)));
+    f4l_mark("k_sel_init", st);
     k_sel_init<<<1, 256, 0, st>>>(s, hist, k, k2);
     const int blocks = min(f4l_div_up(n, 256 * 8), 148 * 4);
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
     for (int p = 0; p < 3; ++p) {
+        f4l_mark("k_sel_hist", st);
         k_sel_hist<<<blocks, 256, 0, st>>>(x, n, stride, offset, s, shifts[p], bits[p], hist);
-        k_sel_pick<<<1, 256, 0, st>>>(s, hist, shifts[p], bits[p]);
+        f4l_mark("k_sel_pick", st);
+        k_sel_pick<<<1, 512, 0, st>>>(s, hist, shifts[p], bits[p]);
     }
+    f4l_mark("k_sel_out", st);
     k_sel_out<<<1, 1, 0, st>>>(s, out, k2 >= 0);
-    return f4l_check_launch("f4l_select_kth");
+    return f4l_finish("f4l_select_kth", stream);
 }
 
 // ---- A1: median point-cloud resolution ------------------------------------------------------------
@@ -468,7 +498,8 @@ extern "C" int f4l_median_resolution(const float* src, int32_t n_src, const floa
         // np.median: mean of elements (m-1)/2 and m/2 of the sorted 2nd-neighbour distances
         rc = f4l_select_kth(d2, m, 2, 1, (m - 1) / 2, m / 2, sel, sel_ws, sel_bytes, stream);
         if (rc) return rc;
+        f4l_mark("k_medres_finish", (cudaStream_t)stream);
         k_medres_finish<<<1, 1, 0, (cudaStream_t)stream>>>(sel, out, e);
     }
-    return f4l_check_launch("f4l_median_resolution");
+    return f4l_finish("f4l_median_resolution", stream);
 }

@@ -60,10 +60,11 @@ extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const in
     F4L_REQUIRE(src && tgt && seg_start && R && t, "null pointer");
     F4L_REQUIRE(variant == F4L_KABSCH_PROCRUSTES || variant == F4L_KABSCH_F2S3, "unknown variant");
     const int warps = 4;
+    f4l_mark("k_segmented_kabsch", (cudaStream_t)stream);
     k_segmented_kabsch<<<f4l_div_up(Q, warps), warps * 32, 0, (cudaStream_t)stream>>>(
         src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q, (double)eps, weight_thresh, variant, R, t,
         T64, res, flag);
-    return f4l_check_launch("f4l_segmented_kabsch");
+    return f4l_finish("f4l_segmented_kabsch", stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -128,9 +129,10 @@ extern "C" int f4l_apply_transforms(const float* pts, const int32_t* idx, const 
     if (Q == 0) return F4L_OK;
     F4L_REQUIRE(pts && seg_start && T && dvf, "null pointer");
     const int warps = 8;
+    f4l_mark("k_apply_transforms", (cudaStream_t)stream);
     k_apply_transforms<<<f4l_div_up(Q, warps), warps * 32, 0, (cudaStream_t)stream>>>(
         pts, idx, seg_start, seg_count, out_start, seg_skip, Q, T, inverse, dvf, mag);
-    return f4l_check_launch("f4l_apply_transforms");
+    return f4l_finish("f4l_apply_transforms", stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -172,7 +174,133 @@ extern "C" int f4l_rigidity_check(const float* src, const float* tgt, const int3
         cudaFuncSetAttribute(k_rigidity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
+    f4l_mark("k_rigidity", (cudaStream_t)stream);
     k_rigidity<<<Q, 256, smem, (cudaStream_t)stream>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count, Q,
                                                       thres_dist_diff, ratio_inlier, dist_mean);
-    return f4l_check_launch("f4l_rigidity_check");
+    return f4l_finish("f4l_rigidity_check", stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Segmented lower median (torch.median semantics): one CTA per segment.
+__global__ void __launch_bounds__(256)
+k_segmented_median(const float* __restrict__ x, const int32_t* __restrict__ seg_start,
+                   const int32_t* __restrict__ seg_count, int Q, float* __restrict__ med) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned state[2];
+    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+        int s0, n;
+        seg_bounds(seg_start, seg_count, q, s0, n);
+        __syncthreads();
+        if (n <= 0) {
+            if (threadIdx.x == 0) med[q] = nanf("");
+            continue;
+        }
+        const float m = block_select_kth(x + s0, n, (n - 1) / 2, hist, state);
+        if (threadIdx.x == 0) med[q] = m;
+    }
+}
+
+extern "C" int f4l_segmented_median(const float* x, const int32_t* seg_start, const int32_t* seg_count, int32_t Q,
+                                    float* med, void* stream) {
+    F4L_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return F4L_OK;
+    F4L_REQUIRE(x && seg_start && med, "null pointer");
+    f4l_mark("k_segmented_median", (cudaStream_t)stream);
+    k_segmented_median<<<Q < 148 * 8 ? Q : 148 * 8, 256, 0, (cudaStream_t)stream>>>(x, seg_start, seg_count, Q, med);
+    return f4l_finish("f4l_segmented_median", stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// F2S3 pruning tail per supervoxel (src/models/outlier_classifier.py:71-105): one CTA per
+// segment.  corr rows are [src | tgt] (stride 6).  res is both output and scratch.
+__device__ __forceinline__ void load_row6(const float* __restrict__ corr, int k, double s[3], double t[3]) {
+    const float2* r = reinterpret_cast<const float2*>(corr + (size_t)k * 6);
+    const float2 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+    s[0] = a.x; s[1] = a.y; s[2] = b.x; t[0] = b.y; t[1] = c.x; t[2] = c.y;
+}
+
+__global__ void __launch_bounds__(128)
+k_f2s3_prune_tail(const float* __restrict__ corr, const float* __restrict__ scores,
+                  const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_count, int Q,
+                  float coeff, float* __restrict__ R, float* __restrict__ t, uint8_t* __restrict__ robust,
+                  float* __restrict__ res, float* __restrict__ median) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned state[2];
+    __shared__ double sR[9], st[3];
+    __shared__ int s_inl;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+        int s0, n;
+        seg_bounds(seg_start, seg_count, q, s0, n);
+        __syncthreads();
+        bool is_robust = false;
+        float med = nanf("");
+        for (int round = 0; round < 2; ++round) {
+            // weighted Kabsch (variant 1: functions.py:36-80); round 0: network scores, round 1: 0/1 inliers
+            if (tid < 32) {
+                double ps[3] = {0, 0, 0}, pt[3] = {0, 0, 0};
+                if (n > 0) load_row6(corr, s0, ps, pt);
+                Moments M;
+                moments_zero(M);
+                const float thr = coeff * med;
+                for (int i = lane; i < n; i += 32) {
+                    double s[3], g[3];
+                    load_row6(corr, s0 + i, s, g);
+                    double w = round == 0 ? (double)__ldg(scores + s0 + i) : ((res[s0 + i] < thr) ? 1.0 : 0.0);
+                    moments_add(M, w, s[0] - ps[0], s[1] - ps[1], s[2] - ps[2], g[0] - pt[0], g[1] - pt[1], g[2] - pt[2]);
+                }
+                moments_warp_reduce(M);
+                double Rm[9], tv[3];
+                if (n > 0) fit_from_moments(M, ps, pt, 1e-7, 1, Rm, tv);
+                else { Rm[0] = 1; Rm[1] = 0; Rm[2] = 0; Rm[3] = 0; Rm[4] = 1; Rm[5] = 0; Rm[6] = 0; Rm[7] = 0; Rm[8] = 1; tv[0] = tv[1] = tv[2] = 0; }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) sR[i] = Rm[i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) st[i] = tv[i];
+                }
+            }
+            __syncthreads();
+            // residuals of this fit (functions.py:100-104)
+            for (int i = tid; i < n; i += blockDim.x) {
+                double s[3], g[3];
+                load_row6(corr, s0 + i, s, g);
+                const double rx = sR[0] * s[0] + sR[1] * s[1] + sR[2] * s[2] + st[0] - g[0];
+                const double ry = sR[3] * s[0] + sR[4] * s[1] + sR[5] * s[2] + st[1] - g[1];
+                const double rz = sR[6] * s[0] + sR[7] * s[1] + sR[8] * s[2] + st[2] - g[2];
+                res[s0 + i] = (float)sqrt(rx * rx + ry * ry + rz * rz);
+            }
+            __syncthreads();
+            if (round == 1 || n <= 0) break;
+            med = block_select_kth(res + s0, n, (n - 1) / 2, hist, state);          // :80 torch.median
+            if (tid == 0) s_inl = 0;
+            __syncthreads();
+            int c = 0;
+            const float thr = coeff * med;
+            for (int i = tid; i < n; i += blockDim.x) c += (res[s0 + i] < thr) ? 1 : 0;
+            c = warp_sum(c);
+            if (lane == 0 && c) atomicAdd(&s_inl, c);
+            __syncthreads();
+            is_robust = s_inl >= 5 && med < 0.5f;                                     // :91
+            if (!is_robust) break;
+        }
+        if (tid < 9) R[(size_t)q * 9 + tid] = (float)sR[tid];
+        if (tid < 3) t[(size_t)q * 3 + tid] = (float)st[tid];
+        if (tid == 0) {
+            robust[q] = is_robust ? 1 : 0;
+            if (median) median[q] = med;
+        }
+    }
+}
+
+extern "C" int f4l_f2s3_prune_tail(const float* corr, const float* scores, const int32_t* seg_start,
+                                   const int32_t* seg_count, int32_t Q, float coeff, float* R, float* t,
+                                   uint8_t* robust, float* res, float* median, void* stream) {
+    F4L_REQUIRE(Q >= 0, "Q < 0");
+    if (Q == 0) return F4L_OK;
+    F4L_REQUIRE(corr && scores && seg_start && R && t && robust && res, "null pointer (res is required: it is scratch too)");
+    f4l_mark("k_f2s3_prune_tail", (cudaStream_t)stream);
+    k_f2s3_prune_tail<<<Q < 148 * 16 ? Q : 148 * 16, 128, 0, (cudaStream_t)stream>>>(corr, scores, seg_start, seg_count, Q,
+                                                                                  coeff, R, t, robust, res, median);
+    return f4l_finish("f4l_f2s3_prune_tail", stream);
 }

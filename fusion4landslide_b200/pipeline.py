@@ -1,0 +1,130 @@
+"""Tile-level public API of the hot path: device-resident inputs -> device-resident DVF.
+
+`prepare_tile` is the step immediately BEFORE the path (labels -> CSR, the reference's
+`prepare_pts2spt_dict`, base.py:1301-1351) and is not timed as part of it; `displacement_field`
+is the path: A1 median resolution (k=2 self-kNN on both epochs) + the fused fine-matching stage.
+`displacement_field_host` is the same call for a caller that holds HOST buffers (pinned):
+host->device copies of the inputs and device->host copies of the results are part of the call.
+"""
+import torch
+
+from . import ops, synth
+
+
+class FineConfig:
+    """The hot-path keys of configs/landslide/fusion_3d_brienz.yaml (method.* / parameter_setting.*)."""
+
+    def __init__(self, mode="only_3d", remove_low_quality_patch_matches=True,
+                 num_min_matches_for_quality_check=10, thres_dist_diff=0.5, thres_inlier_ratio=0.15,
+                 num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
+                 output_tgt2src=False, icp_threshold=0.1, icp_max_iter=30,
+                 num_min_matches_for_small_patch=10):
+        self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
+
+    def fine_kwargs(self):
+        d = dict(self.__dict__)
+        d.pop("num_min_matches_for_small_patch")
+        return d
+
+
+class TileInputs:
+    """Per-tile device tensors the path consumes (SURVEY 9.1 names in comments)."""
+    __slots__ = ("src", "tgt", "corr3d", "corr2d", "sp_idx", "sp_ptr", "tp_idx", "tp_ptr",
+                 "tgt_patch_of_point", "pair_tgt_patch", "n_src_items", "n_tgt_items", "n_pairs")
+
+    def tensors(self):
+        return [(k, getattr(self, k)) for k in self.__slots__ if torch.is_tensor(getattr(self, k))]
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for _, t in self.tensors())
+
+
+def prepare_tile(src, tgt, label_src, label_tgt, corr3d, corr2d=None, min_pts=10, pairs=None):
+    """labels -> CSR patch lists + matched patch pairs.  `pairs` = (src patch pos, tgt patch pos) from the
+    coarse matching; default: patches carrying the same label (synthetic ground truth pairing)."""
+    lab_s, ptr_s, idx_s = synth.patches_from_labels(label_src, min_pts)      # idx_spt2pts_src
+    lab_t, ptr_t, idx_t = synth.patches_from_labels(label_tgt, min_pts)      # idx_spt2pts_tgt
+    m, j = pairs if pairs is not None else synth.pair_patches(lab_s, lab_t)
+    dev = src.device
+
+    def gather_csr(ptr, idx, sel):
+        cnt = (ptr[1:] - ptr[:-1]).long()[sel]
+        p = torch.zeros(sel.numel() + 1, dtype=torch.int64, device=dev)
+        p[1:] = torch.cumsum(cnt, 0)
+        seg = torch.repeat_interleave(torch.arange(sel.numel(), device=dev), cnt)
+        within = torch.arange(int(p[-1]), device=dev) - p[:-1][seg]
+        items = idx[(ptr[:-1].long()[sel])[seg] + within]
+        return p.to(torch.int32), items.contiguous()
+
+    t = TileInputs()
+    t.src, t.tgt, t.corr3d, t.corr2d = src.contiguous(), tgt.contiguous(), corr3d.contiguous(), corr2d
+    t.sp_ptr, t.sp_idx = gather_csr(ptr_s, idx_s, m)
+    t.tp_ptr, t.tp_idx = gather_csr(ptr_t, idx_t, j)
+    tpo = torch.full((tgt.shape[0],), -1, dtype=torch.int32, device=dev)
+    seg_t = torch.repeat_interleave(torch.arange(lab_t.numel(), device=dev, dtype=torch.int32),
+                                    (ptr_t[1:] - ptr_t[:-1]).long())
+    tpo[idx_t.long()] = seg_t
+    t.tgt_patch_of_point = tpo
+    t.pair_tgt_patch = j.to(torch.int32).contiguous()
+    t.n_pairs = int(m.numel())
+    t.n_src_items = int(t.sp_ptr[-1]) if t.n_pairs else 0
+    t.n_tgt_items = int(t.tp_ptr[-1]) if t.n_pairs else 0
+    return t
+
+
+def displacement_field(tile, cfg=None, out=None, med_out=None):
+    """The hot path on one tile, device -> device, no host synchronisation.
+    Returns (FineResult, median_resolution device scalar)."""
+    cfg = cfg or FineConfig()
+    med = ops.median_resolution(tile.src, tile.tgt, out=med_out)                          # A1
+    r = ops.fine_matching(tile.src, tile.tgt, tile.sp_idx, tile.sp_ptr, tile.tp_idx, tile.tp_ptr,
+                          tile.tgt_patch_of_point, tile.pair_tgt_patch, corr3d=tile.corr3d,
+                          corr2d=tile.corr2d, d_median_resolution=med, n_src_items=tile.n_src_items,
+                          n_tgt_items=tile.n_tgt_items, out=out, **cfg.fine_kwargs())
+    return r, med
+
+
+class HostTile:
+    """Pinned host copy of a TileInputs (what a caller holding numpy / CPU tensors passes)."""
+
+    def __init__(self, tile):
+        self.meta = (tile.n_src_items, tile.n_tgt_items, tile.n_pairs)
+        self.t = {k: v.cpu().pin_memory() for k, v in tile.tensors()}
+
+    def nbytes(self):
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+
+def displacement_field_host(host_tile, cfg=None, device="cuda:0", host_out=None):
+    """Same call with HOST buffers: copies the inputs to the device, runs the path, copies the dense
+    DVF rows, per-patch transforms / status and the row counts back.  Returns a dict of pinned host
+    tensors (views sized by the true row counts) and the bytes moved (h2d, d2h)."""
+    dev = torch.device(device)
+    t = TileInputs()
+    for k in TileInputs.__slots__:
+        setattr(t, k, None)
+    h2d = 0
+    for k, v in host_tile.t.items():
+        setattr(t, k, v.to(dev, non_blocking=True))
+        h2d += v.numel() * v.element_size()
+    t.n_src_items, t.n_tgt_items, t.n_pairs = host_tile.meta
+    r, med = displacement_field(t, cfg)
+    counts = r.counts.cpu()                      # sync: the row counts size the copies below
+    nd, nsp = int(counts[0]), int(counts[1])
+    if host_out is None:
+        host_out = {}
+    res = {}
+    d2h = 16
+    for name, ten in (("dense", r.dense[:nd]), ("sparse", r.sparse[:nsp]), ("T", r.T), ("status", r.status)):
+        buf = host_out.get(name)
+        if buf is None or buf.shape[0] < ten.shape[0]:
+            buf = torch.empty(ten.shape, dtype=ten.dtype).pin_memory()
+            host_out[name] = buf
+        view = buf[:ten.shape[0]]
+        view.copy_(ten, non_blocking=True)
+        res[name] = view
+        d2h += ten.numel() * ten.element_size()
+    res["median_resolution"] = med.cpu()
+    d2h += 4
+    torch.cuda.current_stream(dev).synchronize()
+    return res, h2d, d2h

@@ -45,6 +45,17 @@ extern "C" {
 
 F4L_API int f4l_abi_version(void);
 F4L_API const char* f4l_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
+F4L_API long long f4l_launch_count(void);
+F4L_API void f4l_launch_count_reset(void);
+/* Optional in-stream timing of every kernel the library launches (CUDA events recorded on the
+ * launching stream around each launch).  Off by default; bench.py turns it on for its roofline
+ * leg only.  f4l_profile_collect() synchronises the events and returns the number of table rows;
+ * f4l_profile_get(i) reads row i: kernel name, accumulated milliseconds, launches. */
+F4L_API void f4l_profile_enable(int on);
+F4L_API int f4l_profile_collect(void);
+F4L_API int f4l_profile_get(int index, char* h_name, int name_cap, double* h_total_ms, long long* h_launches);
+F4L_API void f4l_profile_reset(void);
 
 /* ------------------------------------------------------------------------------------------
  * (d) Weighted Kabsch / Procrustes, one fit per segment.                           kernel K-d
@@ -96,7 +107,7 @@ F4L_API int f4l_segmented_median(const float* x, const int32_t* seg_start, const
  * (>=5 inliers and median < 0.5) -> refit with 0/1 weights.
  * Replaces src/models/outlier_classifier.py:71-105 (everything after the network forward).
  * corr (K,6) rows [src|tgt] f32, scores (K).  Outputs R (Q,9), t (Q,3), robust (Q) uint8,
- * res (K) residuals of the final fit or NULL, median (Q) or NULL. */
+ * res (K) residuals of the final fit (REQUIRED: also scratch), median (Q) of the first fit or NULL. */
 F4L_API int f4l_f2s3_prune_tail(const float* corr, const float* scores, const int32_t* seg_start,
                         const int32_t* seg_count, int32_t Q, float coeff, float* R, float* t,
                         uint8_t* robust, float* res, float* median, void* stream);
