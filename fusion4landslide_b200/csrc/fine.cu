@@ -9,7 +9,7 @@
 //
 // No host round trip happens between the stages: per-pair decisions (quality reject, too few
 // matches) are status bytes consumed by the later kernels, row counts are device scalars.
-#include "icp_device.cuh"
+#include "icp_warp.cuh"
 
 #define FINE_MODE_3D 0
 #define FINE_MODE_2D 1
@@ -87,6 +87,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
     for (int q = blockIdx.x; q < Q; q += gridDim.x) {
         __syncthreads();
         const int k0 = kstart[q], k = K[q];
+        if (k <= WICP_CAP) continue;          // small pairs are fitted by k_patch_fit_warp
         int st = 0;
         float ratio = 0.f, dmean = 0.f;
         if (prm.remove_low_quality && k >= prm.num_min_quality) {
@@ -144,6 +145,86 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
         __syncthreads();
         if (tid < 16) T32[(size_t)q * 16 + tid] = (float)T64q[tid];                                   // base.py:3366
         if (tid == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Small pairs (K <= WICP_CAP matched points): the whole fit by ONE warp -- stage the matched pairs
+// in the warp's shared-memory slice, rigidity check, Procrustes, ICP loop (icp_warp.cuh).
+#define FITW_WARPS 4
+__global__ void __launch_bounds__(FITW_WARPS * 32)
+k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
+                 const int32_t* __restrict__ cs, const int32_t* __restrict__ ct,
+                 const int32_t* __restrict__ kstart, const int32_t* __restrict__ K, int Q, f4l_fine_params prm,
+                 float* __restrict__ T32, double* __restrict__ T64, int8_t* __restrict__ status,
+                 double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
+                 float* __restrict__ ratio_inlier, float* __restrict__ dist_mean) {
+    extern __shared__ __align__(16) unsigned char fitw_raw[];
+    WarpIcpSmem* smem = reinterpret_cast<WarpIcpSmem*>(fitw_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpIcpSmem& sm = smem[wid];
+    for (int q = blockIdx.x * FITW_WARPS + wid; q < Q; q += gridDim.x * FITW_WARPS) {
+        const int k0 = kstart[q], k = K[q];
+        if (k > WICP_CAP) continue;           // fitted by the CTA kernel
+        __syncwarp();
+        int st = 0;
+        double* T64q = T64 + (size_t)q * 16;
+        float ra = 0.f, dm = 0.f;
+        if (prm.remove_low_quality && k >= prm.num_min_quality) {
+            for (int i = lane; i < k; i += 32) {
+                float x, y, z;
+                load_ptf(src_pts, cs, k0 + i, x, y, z);
+                sm.A[3 * i] = x; sm.A[3 * i + 1] = y; sm.A[3 * i + 2] = z;
+            }
+            for (int j = lane; j < k; j += 32) {
+                float x, y, z;
+                load_ptf(tgt_pts, ct, k0 + j, x, y, z);
+                sm.Bg[3 * j] = x; sm.Bg[3 * j + 1] = y; sm.Bg[3 * j + 2] = z;
+            }
+            __syncwarp();
+            double sum;
+            unsigned cnt;
+            warp_rigidity(sm, k, prm.thres_dist_diff, lane, sum, cnt);
+            const double ne = 0.5 * (double)k * (double)(k - 1);
+            dm = (float)(sum / ne);
+            ra = (float)((double)(2ull * cnt) / (ne * 2.0));
+            if (ra <= prm.thres_inlier_ratio || dm >= prm.thres_dist_diff) st = 1;                   // base.py:3320
+            __syncwarp();
+        }
+        if (st == 0 && k < prm.num_min_fine_match) st = 2;                                            // base.py:3338
+        if (lane == 0) { ratio_inlier[q] = ra; dist_mean[q] = dm; }
+        if (st != 0) {
+            if (lane < 16) {
+                const double v = (lane % 5 == 0) ? 1.0 : 0.0;
+                T64q[lane] = v;
+                T32[(size_t)q * 16 + lane] = (float)v;
+            }
+            if (lane == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
+            continue;
+        }
+        // D2: Procrustes (weights None, eps 1e-6)
+        double R[9], t[3], Tsvd[16];
+        warp_fit_segment(src_pts, tgt_pts, cs, ct, nullptr, k0, k, 1e-6, 0.f, 0, lane, R, t);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            Tsvd[r * 4 + 0] = R[r * 3 + 0]; Tsvd[r * 4 + 1] = R[r * 3 + 1];
+            Tsvd[r * 4 + 2] = R[r * 3 + 2]; Tsvd[r * 4 + 3] = t[r];
+        }
+        Tsvd[12] = 0; Tsvd[13] = 0; Tsvd[14] = 0; Tsvd[15] = 1;
+        IcpResult r;
+        r.fitness = 0; r.rmse = 0; r.iters = 0;
+        if (prm.icp_refine) {
+            r = warp_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, Tsvd, prm.icp_threshold, prm.icp_max_iter, 1e-6, 1e-6,
+                         T64q, nullptr, sm, lane);
+        } else {
+#pragma unroll
+            for (int a = 0; a < 16; ++a)
+                if (lane == a) T64q[a] = Tsvd[a];
+        }
+        __syncwarp();
+        if (lane < 16) T32[(size_t)q * 16 + lane] = (float)T64q[lane];                                // base.py:3366
+        if (lane == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
     }
 }
 
@@ -440,12 +521,19 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
     if (!attr_set) {
         cudaFuncSetAttribute(k_patch_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
         cudaFuncSetAttribute(k_apply_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_aa);
+        cudaFuncSetAttribute(k_patch_fit_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(FITW_WARPS * sizeof(WarpIcpSmem)));
         attr_set = true;
     }
     f4l_mark("k_select_corr", st);
     k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
                                                    bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
                                                    prm->mode, w.cs, w.ct, w.kstart, bf->K);
+    const int grid_w = f4l_div_up(Q, FITW_WARPS) < 148 * 8 ? f4l_div_up(Q, FITW_WARPS) : 148 * 8;
+    f4l_mark("k_patch_fit_warp", st);
+    k_patch_fit_warp<<<grid_w, FITW_WARPS * 32, FITW_WARPS * sizeof(WarpIcpSmem), st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q, *prm,
+                                                        bf->T, bf->T64, bf->status, bf->fitness, bf->rmse, bf->iters,
+                                                        bf->ratio_inlier, bf->dist_mean);
     const int grid_fit = Q < 148 * 16 ? Q : 148 * 16;
     f4l_mark("k_patch_fit", st);
     k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
@@ -469,3 +557,10 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
                                                    w.sparse_cnt, w.sparse_off, Q, *prm, bf->sparse);
     return f4l_finish("f4l_fine_matching", stream);
 }
+
+#ifdef F4L_DEBUG_SCANS
+extern "C" __attribute__((visibility("default"))) void f4l_debug_counters(unsigned long long* h_out, int reset) {
+    cudaMemcpyFromSymbol(h_out, g_dbg, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbg, z, sizeof(z)); }
+}
+#endif

@@ -1,5 +1,5 @@
 // K-e per-patch ICP (standalone entry point) and the segmented 1-NN used by assign_then_nn.
-#include "icp_device.cuh"
+#include "icp_warp.cuh"
 
 __global__ void __launch_bounds__(ICP_THREADS)
 k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
@@ -17,7 +17,9 @@ k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
         seg_bounds(s_start, s_count, q, s0, ns);
         seg_bounds(t_start, t_count, q, t0, nt);
         const double* T0q = T0 ? T0 + (size_t)q * 16 : nullptr;
-        if (seg_skip && seg_skip[q]) {
+        const bool skip = seg_skip && seg_skip[q];
+        if (!skip && ns >= 1 && nt >= 1 && ns <= WICP_CAP && nt <= WICP_CAP) continue;   // k_patch_icp_warp's
+        if (skip) {
             if (threadIdx.x < 16) {
                 double v = (threadIdx.x % 5 == 0) ? 1.0 : 0.0;
                 if (T0q) v = T0q[threadIdx.x];
@@ -31,6 +33,33 @@ k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
                                 rel_rmse, T + (size_t)q * 16, corr, pts, sh);
         if (threadIdx.x == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
         __syncthreads();
+    }
+}
+
+// small segments: one warp per segment (icp_warp.cuh)
+#define ICPW_WARPS 4
+__global__ void __launch_bounds__(ICPW_WARPS * 32)
+k_patch_icp_warp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
+                 const int32_t* __restrict__ s_start, const int32_t* __restrict__ s_count,
+                 const float* __restrict__ tgt, const int32_t* __restrict__ tgt_idx,
+                 const int32_t* __restrict__ t_start, const int32_t* __restrict__ t_count,
+                 const uint8_t* __restrict__ seg_skip, int Q, const double* __restrict__ T0, double max_dist,
+                 int max_iter, double rel_fit, double rel_rmse, double* __restrict__ T,
+                 double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
+                 int32_t* __restrict__ corr) {
+    extern __shared__ __align__(16) unsigned char icpw_raw[];
+    WarpIcpSmem* smem = reinterpret_cast<WarpIcpSmem*>(icpw_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int q = blockIdx.x * ICPW_WARPS + wid; q < Q; q += gridDim.x * ICPW_WARPS) {
+        int s0, ns, t0, nt;
+        seg_bounds(s_start, s_count, q, s0, ns);
+        seg_bounds(t_start, t_count, q, t0, nt);
+        const bool skip = seg_skip && seg_skip[q];
+        if (skip || ns < 1 || nt < 1 || ns > WICP_CAP || nt > WICP_CAP) continue;
+        __syncwarp();
+        IcpResult r = warp_icp(src, src_idx, s0, ns, tgt, tgt_idx, t0, nt, T0 ? T0 + (size_t)q * 16 : nullptr, max_dist,
+                               max_iter, rel_fit, rel_rmse, T + (size_t)q * 16, corr, smem[wid], lane);
+        if (lane == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
     }
 }
 
@@ -48,9 +77,16 @@ extern "C" int f4l_patch_icp(const float* src, const int32_t* src_idx, const int
     const size_t smem = (size_t)ICP_SMEM_PTS * 3 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
+        cudaFuncSetAttribute(k_patch_icp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(ICPW_WARPS * sizeof(WarpIcpSmem)));
         cudaFuncSetAttribute(k_patch_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
+    const int grid_w = f4l_div_up(Q, ICPW_WARPS) < 148 * 8 ? f4l_div_up(Q, ICPW_WARPS) : 148 * 8;
+    f4l_mark("k_patch_icp_warp", (cudaStream_t)stream);
+    k_patch_icp_warp<<<grid_w, ICPW_WARPS * 32, ICPW_WARPS * sizeof(WarpIcpSmem), (cudaStream_t)stream>>>(
+        src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
+        rel_fitness, rel_rmse, T, fitness, rmse, iters, corr);
     const int grid = Q < 148 * 16 ? Q : 148 * 16;
     f4l_mark("k_patch_icp", (cudaStream_t)stream);
     k_patch_icp<<<grid, ICP_THREADS, smem, (cudaStream_t)stream>>>(

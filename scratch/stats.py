@@ -1,0 +1,24 @@
+import torch, numpy as np, sys
+sys.path.insert(0, '.')
+from fusion4landslide_b200 import pipeline, synth
+dev = torch.device('cuda:0')
+d = synth.make_tile(781250, seed=0, device=dev, patch_pts=256)
+t = pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"])
+r, med = pipeline.displacement_field(t)
+torch.cuda.synchronize()
+it = r.iters.cpu().numpy(); K = r.K.cpu().numpy(); st = r.status.cpu().numpy()
+print('pairs', len(it), 'status counts', np.bincount(st, minlength=3), 'K mean/max', K.mean(), K.max())
+print('iters mean', it[st == 0].mean(), 'hist', np.bincount(it[st == 0], minlength=31))
+print('fitness mean', r.fitness.cpu().numpy()[st == 0].mean(), 'rmse mean', r.rmse.cpu().numpy()[st == 0].mean())
+print('n_src_items', t.n_src_items, 'counts', r.counts.tolist(), 'med', med.item())
+import ctypes
+from fusion4landslide_b200 import _lib
+L = _lib.lib()
+if hasattr(L, 'f4l_debug_counters'):
+    buf = (ctypes.c_ulonglong * 8)()
+    L.f4l_debug_counters(buf, 1)
+    r, med = pipeline.displacement_field(t)
+    torch.cuda.synchronize()
+    L.f4l_debug_counters(buf, 1)
+    v = list(buf)
+    print('scans', v[0], 'exact', v[1], 'iterations(matches)', v[2], 'points*iters', v[3], 'scan frac', v[0] / max(v[3], 1), 'mean moved um', v[4] / max(v[2], 1))
