@@ -153,7 +153,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
 // Small pairs (K <= WICP_CAP matched points): the whole fit by ONE warp -- stage the matched pairs
 // in the warp's shared-memory slice, rigidity check, Procrustes, ICP loop (icp_warp.cuh).
 #define FITW_WARPS 4
-__global__ void __launch_bounds__(FITW_WARPS * 32)
+__global__ void __launch_bounds__(FITW_WARPS * 32, 4)
 k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
                  const int32_t* __restrict__ cs, const int32_t* __restrict__ ct,
                  const int32_t* __restrict__ kstart, const int32_t* __restrict__ K, int Q, f4l_fine_params prm,

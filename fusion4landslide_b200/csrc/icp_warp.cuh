@@ -16,7 +16,7 @@
 #pragma once
 #include "icp_device.cuh"
 
-#define WICP_CAP 256
+#define WICP_CAP 224
 
 #ifdef F4L_DEBUG_SCANS
 __device__ unsigned long long g_dbg[8];   // 0: point scans, 1: exact-path scans, 2: iterations, 3: points*iters, 4: sum moved (um), 5: keep checks
@@ -283,26 +283,43 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
 }
 
 
-// Rigidity statistic (base.py:3308-3317) of the staged pairs by one warp: row i against all j > i.
+// Rigidity statistic (base.py:3308-3317) of the staged pairs by one warp.
+// Lane l owns the row pair (i, n-1-i): together they hold n-1 column terms, so the 32 lanes are
+// balanced; distances use sqrt.approx.f32 (<= 1 ulp; the reference's own cdist carries ~1e-3 m of
+// GEMM-formulation noise at these coordinates).
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void rigidity_row(const WarpIcpSmem& sm, int i, int n, float thres, float& sum, unsigned& cnt) {
+    const float ax = sm.A[3 * i], ay = sm.A[3 * i + 1], az = sm.A[3 * i + 2];
+    const float bx = sm.Bg[3 * i], by = sm.Bg[3 * i + 1], bz = sm.Bg[3 * i + 2];
+    float rowsum = 0.f;
+#pragma unroll 2
+    for (int j = i + 1; j < n; ++j) {
+        const float ex = ax - sm.A[3 * j], ey = ay - sm.A[3 * j + 1], ez = az - sm.A[3 * j + 2];
+        const float fx = bx - sm.Bg[3 * j], fy = by - sm.Bg[3 * j + 1], fz = bz - sm.Bg[3 * j + 2];
+        const float ds = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+        const float dt = sqrt_approx(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+        const float diff = fabsf(ds - dt);
+        rowsum += diff;
+        cnt += (diff <= thres) ? 1u : 0u;
+    }
+    sum += rowsum;
+}
+
 __device__ inline void warp_rigidity(const WarpIcpSmem& sm, int n, float thres, int lane, double& out_sum,
                                      unsigned& out_cnt) {
     float sum = 0.f;
     unsigned cnt = 0;
-    for (int i = 0; i < n - 1; ++i) {
-        const float ax = sm.A[3 * i], ay = sm.A[3 * i + 1], az = sm.A[3 * i + 2];
-        const float bx = sm.Bg[3 * i], by = sm.Bg[3 * i + 1], bz = sm.Bg[3 * i + 2];
-        float rowsum = 0.f;
-        for (int j = i + 1 + lane; j < n; j += 32) {
-            const float ex = ax - sm.A[3 * j], ey = ay - sm.A[3 * j + 1], ez = az - sm.A[3 * j + 2];
-            const float fx = bx - sm.Bg[3 * j], fy = by - sm.Bg[3 * j + 1], fz = bz - sm.Bg[3 * j + 2];
-            const float ds = sqrtf(ex * ex + ey * ey + ez * ez);
-            const float dt = sqrtf(fx * fx + fy * fy + fz * fz);
-            const float diff = fabsf(ds - dt);
-            rowsum += diff;
-            cnt += (diff <= thres) ? 1u : 0u;
-        }
-        sum += rowsum;
+    const int half = n >> 1;                       // row pairs (i, n-1-i), i < half; odd n: middle row alone
+    for (int i = lane; i < half; i += 32) {
+        rigidity_row(sm, i, n, thres, sum, cnt);
+        rigidity_row(sm, n - 1 - i, n, thres, sum, cnt);
     }
+    if ((n & 1) && lane == 0) rigidity_row(sm, half, n, thres, sum, cnt);
     out_sum = warp_sum((double)sum);
     out_cnt = (unsigned)warp_sum((int)cnt);
 }
