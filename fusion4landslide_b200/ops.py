@@ -154,6 +154,61 @@ def select_kth(x, k, k2=-1, stride=1, offset=0):
     return out
 
 
+_DESC_ALGO = {"auto": 0, "tensor": 1, "exact": 2}
+
+
+def desc_nn(a, b, a_xyz=None, b_xyz=None, max_mag=0.0, both_dirs=False, algo="auto"):
+    """K-b.  Exact descriptor-space nearest neighbour of every row of a (N,D) among b (M,D), D in {32,64}.
+    Returns row_idx (N) i32, row_d2 (N) f32 [, col_idx (M), col_d2 (M) when both_dirs]."""
+    N, D = a.shape
+    M = b.shape[0]
+    row_idx = _empty((N,), I32, a)
+    row_d2 = _empty((N,), F32, a)
+    col_idx = _empty((M,), I32, a) if both_dirs else None
+    col_d2 = _empty((M,), F32, a) if both_dirs else None
+    ws = _workspace(lib().f4l_desc_nn_workspace_bytes(N, M, D, int(both_dirs)), a.device)
+    check(lib().f4l_desc_nn(ptr(a, F32), N, ptr(b, F32), M, D, ptr(a_xyz, F32, True), ptr(b_xyz, F32, True),
+                            float(max_mag), int(both_dirs), _DESC_ALGO[algo], ptr(row_idx), ptr(row_d2),
+                            ptr(col_idx, I32, True), ptr(col_d2, F32, True), ptr(ws), ws.numel(),
+                            stream_ptr(a.device)), "f4l_desc_nn")
+    if both_dirs:
+        return row_idx, row_d2, col_idx, col_d2
+    return row_idx, row_d2
+
+
+def scatter_global_matches(labels, src_sub, tgt_sub, voxel2pts_src, voxel2pts_tgt, max_magnitude, n_raw):
+    """base.py:2872-2889.  Returns corres (n_raw,2) i64."""
+    corres = _empty((n_raw, 2), torch.int64, src_sub)
+    ws = _workspace(lib().f4l_scatter_global_matches_workspace_bytes(n_raw), src_sub.device)
+    check(lib().f4l_scatter_global_matches(ptr(labels, I32), ptr(src_sub, F32), ptr(tgt_sub, F32), labels.shape[0],
+                                           ptr(voxel2pts_src, torch.int64), ptr(voxel2pts_tgt, torch.int64),
+                                           float(max_magnitude), ptr(corres), n_raw, ptr(ws), ws.numel(),
+                                           stream_ptr(src_sub.device)), "f4l_scatter_global_matches")
+    return corres
+
+
+def piecewise_icp(src64, tgt64, smax, number_points_min, internal_min_points=250, want_tables=False):
+    """K-g.  The reference's Piecewise_ICP on device tensors (f64 (n,3)).  Returns dvfs ((n_src+8),6) f64,
+    mag (n_src+8) f64 (both upper bounds), counts (6) i32 [rows, stable rows, Cs, Ct, depth, unstable cells],
+    thr (1) f64 [, cent_src, cent_tgt, nn]."""
+    n_s, n_t = src64.shape[0], tgt64.shape[0]
+    dvfs = _empty((n_s + 8, 6), F64, src64)
+    mag = _empty((n_s + 8,), F64, src64)
+    counts = _empty((6,), I32, src64)
+    thr = _empty((1,), F64, src64)
+    cs = _empty((n_s + 8, 3), F64, src64) if want_tables else None
+    ct = _empty((n_t + 8, 3), F64, src64) if want_tables else None
+    nn = _empty((n_s + 8,), I32, src64) if want_tables else None
+    ws = _workspace(lib().f4l_piecewise_icp_workspace_bytes(n_s, n_t), src64.device)
+    check(lib().f4l_piecewise_icp(ptr(src64, F64), n_s, ptr(tgt64, F64), n_t, float(smax), int(number_points_min),
+                                  int(internal_min_points), ptr(dvfs), ptr(mag), ptr(counts), ptr(thr),
+                                  ptr(cs, F64, True), ptr(ct, F64, True), ptr(nn, I32, True), ptr(ws), ws.numel(),
+                                  stream_ptr(src64.device)), "f4l_piecewise_icp")
+    if want_tables:
+        return dvfs, mag, counts, thr, cs, ct, nn
+    return dvfs, mag, counts, thr
+
+
 class FineResult:
     """Outputs of the fused fine-matching stage (device tensors; row counts in `counts`)."""
     __slots__ = ("T", "T64", "status", "K", "fitness", "rmse", "iters", "ratio_inlier", "dist_mean",

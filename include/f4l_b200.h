@@ -224,31 +224,57 @@ F4L_API int f4l_fine_matching(const f4l_fine_params* h_params, const f4l_fine_bu
  * Replaces torch.cdist + min at base.py:2783-2815 (global_matches_from_3d exact branches),
  * the hnswlib query at src/f2s3.py:273-281 (exact instead of approximate) and, with
  * both_dirs + the xyz gate, the coarse mutual matching at base.py:2966-2995.
- *   a (N,D), b (M,D) f32.  a_xyz/b_xyz (.,3) + max_mag > 0: pairs with ||xyz_a - xyz_b|| > max_mag
- *   are excluded (base.py:2969).  row_idx (N) int32 argmin over b (-1 = all excluded),
- *   row_d2 (N) f32 squared L2; col_idx (M)/col_d2 (M) likewise when both_dirs (else NULL).
- *   Ties (and everything within the re-rank margin) are resolved in exact fp32 arithmetic
- *   towards the lower index (torch.min semantics). */
+ *   a (N,D), b (M,D) f32, finite.  a_xyz/b_xyz (.,3) + max_mag > 0: pairs with
+ *   ||xyz_a - xyz_b|| > max_mag are excluded (base.py:2969).  row_idx (N) int32 argmin over b
+ *   (-1 = all excluded), row_d2 (N) f32 squared L2; col_idx (M)/col_d2 (M) likewise for b over a
+ *   when both_dirs (else NULL).
+ *   algo: F4L_DESC_AUTO picks the tensor-core path (fp16 tcgen05.mma candidates within a proven
+ *   error margin, re-ranked in fp64) for >= 2^27 pairs without a gate, else the fp64 brute-force
+ *   kernel; F4L_DESC_TENSOR / F4L_DESC_EXACT force one.  Either way the result is the fp64 argmin
+ *   of the f32 inputs, exact ties resolved towards the lower index (torch.min semantics). */
+#define F4L_DESC_AUTO 0
+#define F4L_DESC_TENSOR 1
+#define F4L_DESC_EXACT 2
 F4L_API size_t f4l_desc_nn_workspace_bytes(int32_t N, int32_t M, int32_t D, int both_dirs);
 F4L_API int f4l_desc_nn(const float* a, int32_t N, const float* b, int32_t M, int32_t D,
-                const float* a_xyz, const float* b_xyz, float max_mag, int both_dirs,
+                const float* a_xyz, const float* b_xyz, float max_mag, int both_dirs, int algo,
                 int32_t* row_idx, float* row_d2, int32_t* col_idx, float* col_d2,
                 void* workspace, size_t workspace_bytes, void* stream);
 
-/* (b)+(c) scatter of global 3D matches: base.py:2872-2889.  corres (n_raw,2) int64. */
+/* (b)+(c) scatter of global 3D matches: base.py:2872-2889.  labels (n_sub) int32 from f4l_desc_nn,
+ * src_sub/tgt_sub (n_sub.,3) voxel points, voxel2pts_* int64 maps, corres (n_raw,2) int64 out:
+ * col0 = arange, col1 = matched raw target index or -1.  Several voxels mapping to one raw point
+ * (quirk q5, non-deterministic in the reference): the largest voxel index wins. */
+F4L_API size_t f4l_scatter_global_matches_workspace_bytes(int32_t n_raw);
 F4L_API int f4l_scatter_global_matches(const int32_t* labels, const float* src_sub, const float* tgt_sub,
                                int32_t n_sub, const int64_t* voxel2pts_src,
                                const int64_t* voxel2pts_tgt, float max_magnitude,
-                               int64_t* corres, int32_t n_raw, void* stream);
+                               int64_t* corres, int32_t n_raw, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Piecewise "ICP" cells (Open3D octree leaves at depth `depth`), fp64.               kernel K-g
- * Replaces src/piecewise_icp.py:89-132 (octree build + traversal + per-cell centroid).
- *   pts64 (n,3) f64 (the 8 bounding-box corners already appended), origin[3], size: octree cube.
- *   code (n) int64 leaf code (base-8 digits x+2y+4z, root first) or -1 if out of bounds.
- * The cell table is produced by f4l_cells_build. */
-F4L_API int f4l_cell_codes(const double* pts64, int32_t n, const double* h_origin, double size,
-                   int32_t depth, int64_t* code, void* stream);
+ * Piecewise "ICP" (rows G1, A5, F5): the whole of src/piecewise_icp.py:89-202 in one launch
+ * sequence, fp64 like Open3D / numpy.                                                kernel K-g
+ *   union bounding box, its 8 corners appended to both clouds (:96-105), depth =
+ *   ceil(log2(max_extent/smax)) (:108-109), Open3D octree leaf of every point (points on the max
+ *   faces are dropped), traversal with the early stop on internal nodes holding fewer than
+ *   internal_min_points points (hard-coded 250 at :52) and leaves with >= number_points_min (:55),
+ *   per-cell centroid (:58-61), 1-NN of every source centroid among the target centroids (:134-149),
+ *   thr = mean + std of the centroid distances, stable = d <= thr (:152-161), rows [p | p] for the
+ *   stable cells in lexicographic centroid order followed by rows [p | p + (c_t - c_s)] for the
+ *   unstable cells in traversal order (:166-202).
+ *   src64 (n_src,3), tgt64 (n_tgt,3) f64.  dvfs ((n_src+8),6) f64 and mag (n_src+8) f64 (or NULL) are
+ *   upper bounds; counts (6) int32 = {rows, stable rows, source cells, target cells, depth,
+ *   unstable cells}; thr_out (1) f64 or NULL; cent_src ((n_src+8),3) / cent_tgt ((n_tgt+8),3) /
+ *   nn_out (n_src+8) optional dumps of the cell tables (first counts[2] / counts[3] entries valid).
+ *   The reference raises when no cell is unstable (np.vstack of an empty list, :197); here
+ *   counts[5] == 0 reports that case and the host wrapper raises. */
+F4L_API size_t f4l_piecewise_icp_workspace_bytes(int32_t n_src, int32_t n_tgt);
+F4L_API int f4l_piecewise_icp(const double* src64, int32_t n_src, const double* tgt64, int32_t n_tgt,
+                      double smax, int32_t number_points_min, int32_t internal_min_points,
+                      double* dvfs, double* mag, int32_t* counts, double* thr_out, double* cent_src,
+                      double* cent_tgt, int32_t* nn_out, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }
