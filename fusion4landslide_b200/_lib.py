@@ -75,6 +75,8 @@ SIGNATURES = {
     "f4l_desc_nn": (c_int, [P, c_i32, P, c_i32, c_i32, P, P, c_f32, c_int, c_int, P, P, P, P, P, c_size, P]),
     "f4l_scatter_global_matches_workspace_bytes": (c_size, [c_i32]),
     "f4l_scatter_global_matches": (c_int, [P, P, P, c_i32, P, P, c_f32, P, c_i32, P, c_size, P]),
+    "f4l_vote_tgt_patch": (c_int, [P, P, P, c_i32, P, c_i32, P, c_i32, P, P, P, P]),
+    "f4l_magnitude_mask": (c_int, [P, c_i32, c_i32, c_f32, P, c_f32, c_int, P, P, P]),
     "f4l_piecewise_icp_workspace_bytes": (c_size, [c_i32, c_i32]),
     "f4l_piecewise_icp": (c_int, [P, c_i32, P, c_i32, c_f64, c_i32, c_i32, P, P, P, P, P, P, P, P, c_size, P]),
     "f4l_fine_matching_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),
@@ -128,6 +130,8 @@ def ptr(t, dtype=None, allow_none=False):
 
 
 def stream_ptr(device=None):
+    if device is not None and torch.device(device).type != "cuda":
+        raise F4LError("tensor must live on a CUDA device (no CPU fallback)")
     return torch.cuda.current_stream(device).cuda_stream
 
 

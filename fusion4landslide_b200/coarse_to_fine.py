@@ -1,0 +1,143 @@
+"""Host mirror of the hot-path pieces of src/coarse_to_fine_matching_base.py and
+src/coarse_to_fine_matching.py: the reference's free functions keep their names and signatures, the
+stage methods of `Coarse2Fine_Base` become functions over the same tensors (SURVEY 9.1 field names).
+
+    refine_dvfs_with_threshold                                   base.py:48-97            (A4)
+    merge_correspondences_by_priority_with_distance_threshold    coarse_to_fine_matching.py:40-118 (M1)
+    compute_median_resolution                                    base.py:2716-2754        (A1)
+    voxel_subsampling_maps                                       base.py:1038-1057        (A2)
+    global_matches_from_3d                                       base.py:2756-2923        (B2)
+    coarse_matching_3d / coarse_matching_2d                      base.py:2966-3011, 3016-3070 (B3, B4)
+    fine_matching_with_different_types                           base.py:3236-3457        (F2 F3 D2 E1 D5 A4)
+"""
+import torch
+
+from . import ops, pipeline
+from .functions import _dev_f32
+
+I32 = torch.int32
+
+
+def refine_dvfs_with_threshold(src_pts, transformed_src_pts, tgt_pts, distance_threshold=0.1, batch_size=1024):
+    """[src | nearest tgt of the transformed src] for matches with d^2 < distance_threshold^2 (strict),
+    (K,6).  `batch_size` is accepted for signature compatibility (one launch handles everything)."""
+    s = _dev_f32(src_pts)
+    ts = _dev_f32(transformed_src_pts, s.device)
+    t = _dev_f32(tgt_pts, s.device)
+    if s.shape[0] == 0 or t.shape[0] == 0:
+        return torch.empty((0, 6), device=s.device)
+    qp = torch.tensor([0, ts.shape[0]], dtype=I32, device=s.device)
+    rp = torch.tensor([0, t.shape[0]], dtype=I32, device=s.device)
+    thr = torch.tensor([distance_threshold], dtype=torch.float32, device=s.device)
+    nn, _ = ops.segmented_nn(ts, t, qp, rp, thr=thr)
+    keep = nn >= 0
+    return torch.cat([s[keep], t[nn[keep].long()]], dim=1)
+
+
+def merge_correspondences_by_priority_with_distance_threshold(corres_list, distance_threshold=1e-3, search_type="faiss"):
+    """Keep level 0 entirely; from each later level drop the rows whose source xyz has an already kept point
+    within `distance_threshold` (squared-distance test D < thr^2).  Every `search_type` of the reference maps
+    to the same exact grid search (its default 'faiss' HNSW index is approximate)."""
+    if search_type not in ("faiss", "kdtree", "cdist"):
+        raise ValueError("unknown search_type %r" % (search_type,))
+    if not corres_list:
+        raise IndexError("corres_list is empty")
+    merged = [corres_list[0]]
+    pool = _dev_f32(corres_list[0][:, :3])
+    thr2 = float(distance_threshold) ** 2
+    for level in range(1, len(corres_list)):
+        cur = corres_list[level]
+        xyz = _dev_f32(cur[:, :3], pool.device)
+        if xyz.shape[0] == 0:
+            merged.append(cur)
+            continue
+        if pool.shape[0] == 0:
+            valid = torch.ones(xyz.shape[0], dtype=torch.bool, device=pool.device)
+        else:
+            _, d2 = ops.knn_grid(xyz, pool, 1)
+            valid = ~(d2[:, 0] < thr2)
+        merged.append(cur[valid.to(cur.device)])
+        pool = torch.cat([pool, xyz[valid]], dim=0).contiguous()
+    return torch.cat(merged, dim=0)
+
+
+def compute_median_resolution(src_pts, tgt_pts):
+    """max over the epochs of the median distance to the nearest other point (k=2 self query); device scalar."""
+    return ops.median_resolution(_dev_f32(src_pts), _dev_f32(tgt_pts))
+
+
+def voxel_subsampling_maps(pts_sub, pts_raw):
+    """idx_voxel2pts (N_sub,) = nearest raw point of every voxel centroid, idx_pts2voxel (N,) = inverse map with
+    -1 default (base.py:1038-1057; duplicate targets: the largest voxel index wins, like a sequential scatter)."""
+    sub = _dev_f32(pts_sub)
+    raw = _dev_f32(pts_raw, sub.device)
+    idx, _ = ops.knn_grid(sub, raw, 1)
+    v2p = idx[:, 0].long()
+    p2v = torch.full((raw.shape[0],), -1, dtype=torch.int64, device=sub.device)
+    p2v.scatter_reduce_(0, v2p, torch.arange(sub.shape[0], device=sub.device), reduce="amax", include_self=True)
+    return v2p, p2v
+
+
+def global_matches_from_3d(feat_src, feat_tgt, src_pts_sub, tgt_pts_sub, idx_voxel2pts_src, idx_voxel2pts_tgt,
+                           n_src_raw, max_magnitude, algo="auto"):
+    """Exact descriptor 1-NN src->tgt, magnitude gate, scatter to raw indices: corres_3d_voxel_from_3d_idx
+    (N_raw,2) int64 with -1 = none.  Also returns the labels (N_sub,) int32."""
+    fs = _dev_f32(feat_src)
+    ft = _dev_f32(feat_tgt, fs.device)
+    labels, _ = ops.desc_nn(fs, ft, algo=algo)
+    corres = ops.scatter_global_matches(labels, _dev_f32(src_pts_sub, fs.device), _dev_f32(tgt_pts_sub, fs.device),
+                                        idx_voxel2pts_src.to(fs.device, torch.int64).contiguous(),
+                                        idx_voxel2pts_tgt.to(fs.device, torch.int64).contiguous(), max_magnitude,
+                                        int(n_src_raw))
+    return corres, labels
+
+
+def coarse_matching_3d(spt_coord_src, spt_feat_src, spt_coord_tgt, spt_feat_tgt, max_magnitude,
+                       coarse_refinement_3d_type="nn_mutual"):
+    """Feature-space NN between superpoints under the coordinate gate; 'nn_mutual' keeps mutual pairs only.
+    Returns (src patch positions m, tgt patch positions j*(m)) int64."""
+    fs = _dev_f32(spt_feat_src)
+    dev = fs.device
+    ri, _, ci, _ = ops.desc_nn(fs, _dev_f32(spt_feat_tgt, dev), a_xyz=_dev_f32(spt_coord_src, dev),
+                               b_xyz=_dev_f32(spt_coord_tgt, dev), max_mag=max_magnitude, both_dirs=True, algo="exact")
+    mask = ri >= 0
+    if coarse_refinement_3d_type == "nn_mutual":
+        m_of_j = ci[ri.clamp(min=0).long()]
+        mask &= m_of_j == torch.arange(ri.shape[0], device=dev, dtype=ci.dtype)
+    elif coarse_refinement_3d_type != "only_max_mag":
+        raise ValueError("unknown coarse_refinement_3d_type %r" % (coarse_refinement_3d_type,))
+    m = torch.nonzero(mask).reshape(-1)
+    return m, ri[m].long()
+
+
+def coarse_matching_2d(corres_3d_from_2d_idx, sp_idx, sp_ptr, idx_pts2spt_tgt, idx_spt_tgt):
+    """2D-vote coarse matching: for every source patch the target patch most of its 2D-lifted matches fall
+    into.  Returns (src patch positions, tgt patch positions in idx_spt_tgt, tie flags)."""
+    dev = corres_3d_from_2d_idx.device
+    lab_t = idx_pts2spt_tgt.to(dev, I32).contiguous()
+    spt_t = idx_spt_tgt.to(dev).long()
+    n_lab = int(max(int(spt_t.max().item()) if spt_t.numel() else -1, int(lab_t.max().item()) if lab_t.numel() else -1)) + 1
+    l2l = torch.full((max(n_lab, 1),), -1, dtype=I32, device=dev)
+    l2l[spt_t] = torch.arange(spt_t.numel(), device=dev, dtype=I32)
+    best, cnt, flag = ops.vote_tgt_patch(corres_3d_from_2d_idx.contiguous(), sp_idx, sp_ptr, lab_t, l2l)
+    if bool((flag == 255).any().item()):
+        raise RuntimeError("coarse_matching_2d: a source patch votes for more than 512 distinct target patches")
+    m = torch.nonzero(best >= 0).reshape(-1)
+    return m, best[m].long(), flag[m] == 1
+
+
+def fine_matching_with_different_types(src_pts, tgt_pts, label_src, label_tgt, corres_3d, corres_2d=None, pairs=None,
+                                       config=None, median_resolution=None, num_min_matches_for_small_patch=10):
+    """The per-patch-pair loop of base.py:3254-3438 as one launch sequence.  `pairs` = (src patch positions,
+    tgt patch positions) from the coarse stage (default: equal labels).  Returns (FineResult, TileInputs)."""
+    tile = pipeline.prepare_tile(_dev_f32(src_pts), _dev_f32(tgt_pts), label_src, label_tgt, corres_3d, corres_2d,
+                                 min_pts=num_min_matches_for_small_patch, pairs=pairs)
+    cfg = config or pipeline.FineConfig()
+    if median_resolution is None:
+        r, _ = pipeline.displacement_field(tile, cfg)
+    else:
+        r = ops.fine_matching(tile.src, tile.tgt, tile.sp_idx, tile.sp_ptr, tile.tp_idx, tile.tp_ptr,
+                              tile.tgt_patch_of_point, tile.pair_tgt_patch, corr3d=tile.corr3d, corr2d=tile.corr2d,
+                              d_median_resolution=median_resolution, n_src_items=tile.n_src_items,
+                              n_tgt_items=tile.n_tgt_items, **cfg.fine_kwargs())
+    return r, tile

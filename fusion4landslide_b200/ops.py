@@ -73,6 +73,8 @@ _WS = {}
 
 def _workspace(nbytes, device):
     """Grow-only per-device scratch buffer (torch caching allocator owns the memory)."""
+    if device.type != "cuda":
+        raise _lib.F4LError("tensor must live on a CUDA device (no CPU fallback)")
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -185,6 +187,30 @@ def scatter_global_matches(labels, src_sub, tgt_sub, voxel2pts_src, voxel2pts_tg
                                            float(max_magnitude), ptr(corres), n_raw, ptr(ws), ws.numel(),
                                            stream_ptr(src_sub.device)), "f4l_scatter_global_matches")
     return corres
+
+
+def vote_tgt_patch(corr2d, sp_idx, sp_ptr, label_tgt, label_to_local=None):
+    """B4.  Returns best (P) i32, best_count (P) i32, flag (P) u8."""
+    Pn = sp_ptr.numel() - 1
+    best = _empty((Pn,), I32, corr2d)
+    cnt = _empty((Pn,), I32, corr2d)
+    flag = _empty((Pn,), torch.uint8, corr2d)
+    check(lib().f4l_vote_tgt_patch(ptr(corr2d, torch.int64), ptr(sp_idx, I32), ptr(sp_ptr, I32), Pn, ptr(label_tgt, I32),
+                                   label_tgt.numel(), ptr(label_to_local, I32, True),
+                                   0 if label_to_local is None else label_to_local.numel(), ptr(best), ptr(cnt),
+                                   ptr(flag), stream_ptr(corr2d.device)), "f4l_vote_tgt_patch")
+    return best, cnt, flag
+
+
+def magnitude_mask(rows, max_mag=0.0, d_max=None, factor=1.0, strict=False, want_mag=True):
+    """F1.  rows (K,>=6) f32.  Returns mask (K) u8 [, mag (K) f32]."""
+    K = rows.shape[0]
+    mask = _empty((K,), torch.uint8, rows)
+    mag = _empty((K,), F32, rows) if want_mag else None
+    check(lib().f4l_magnitude_mask(ptr(rows, F32), K, rows.shape[1], float(max_mag), ptr(d_max, F32, True), float(factor),
+                                   int(strict), ptr(mag, F32, True), ptr(mask), stream_ptr(rows.device)),
+          "f4l_magnitude_mask")
+    return (mask, mag) if want_mag else mask
 
 
 def piecewise_icp(src64, tgt64, smax, number_points_min, internal_min_points=250, want_tables=False):

@@ -84,6 +84,35 @@ def displacement_field(tile, cfg=None, out=None, med_out=None):
     return r, med
 
 
+def make_streams(n, device):
+    """Side streams for tile-level concurrency (tiles are independent; the library keeps one workspace per
+    stream)."""
+    return [torch.cuda.Stream(device=device) for _ in range(max(1, int(n)))]
+
+
+def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None):
+    """The hot path over many tiles.  With `streams`, tile i runs on streams[i % n]: the small kernels and the
+    tail of one tile's patch loop overlap with the next tile's work.  The caller's current stream waits for all
+    of them at the end, so events recorded around this call time the whole batch."""
+    cfg = cfg or FineConfig()
+    res = []
+    if not streams or len(streams) == 1 and streams[0] is None:
+        for i, t in enumerate(tiles):
+            res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
+                                          med_out=None if meds is None else meds[i:i + 1]))
+        return res
+    cur = torch.cuda.current_stream(tiles[0].src.device) if tiles else None
+    for s in streams:
+        s.wait_stream(cur)
+    for i, t in enumerate(tiles):
+        with torch.cuda.stream(streams[i % len(streams)]):
+            res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
+                                          med_out=None if meds is None else meds[i:i + 1]))
+    for s in streams:
+        cur.wait_stream(s)
+    return res
+
+
 class HostTile:
     """Pinned host copy of a TileInputs (what a caller holding numpy / CPU tensors passes)."""
 
@@ -128,3 +157,87 @@ def displacement_field_host(host_tile, cfg=None, device="cuda:0", host_out=None)
     d2h += 4
     torch.cuda.current_stream(dev).synchronize()
     return res, h2d, d2h
+
+
+class HostPipeline:
+    """Host-buffer API over many tiles: pinned host inputs -> device, the path, results -> pinned host, with the
+    copies of one tile overlapping the kernels of the others (one side stream per slot).  Row counts are read
+    back per tile (a stream-local synchronisation) so that only the rows that exist cross PCIe."""
+
+    def __init__(self, host_tiles, cfg=None, device="cuda:0", n_streams=4, want_sparse=True):
+        self.host_tiles = host_tiles
+        self.cfg = cfg or FineConfig()
+        self.dev = torch.device(device)
+        self.streams = make_streams(n_streams, self.dev)
+        self.want_sparse = want_sparse
+        self.out = []
+        for ht in host_tiles:
+            n_s, _, q = ht.meta
+            o = {"dense": torch.empty((n_s, 6), dtype=torch.float32).pin_memory(),
+                 "T": torch.empty((q, 4, 4), dtype=torch.float32).pin_memory(),
+                 "status": torch.empty((q,), dtype=torch.int8).pin_memory(),
+                 "counts": torch.empty((4,), dtype=torch.int32).pin_memory(),
+                 "median_resolution": torch.empty((1,), dtype=torch.float32).pin_memory()}
+            if want_sparse:
+                o["sparse"] = torch.empty((2 * n_s, 6), dtype=torch.float32).pin_memory()
+            self.out.append(o)
+
+    def run(self):
+        """Returns (list of per-tile dicts of host views, h2d bytes, d2h bytes)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            s.wait_stream(cur)
+        h2d = d2h = 0
+        pending = []
+        for i, ht in enumerate(self.host_tiles):
+            st = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(st):
+                t = TileInputs()
+                for k in TileInputs.__slots__:
+                    setattr(t, k, None)
+                for k, v in ht.t.items():
+                    setattr(t, k, v.to(self.dev, non_blocking=True))
+                    h2d += v.numel() * v.element_size()
+                t.n_src_items, t.n_tgt_items, t.n_pairs = ht.meta
+                r, med = displacement_field(t, self.cfg)
+                o = self.out[i]
+                o["counts"].copy_(r.counts, non_blocking=True)
+                o["median_resolution"].copy_(med, non_blocking=True)
+                o["T"].copy_(r.T, non_blocking=True)
+                o["status"].copy_(r.status, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            pending.append((i, st, ev, r, t))
+            # drain the tile issued n_streams ago: its counts have landed by now
+            if len(pending) > len(self.streams):
+                d2h += self._drain(pending.pop(0))
+        while pending:
+            d2h += self._drain(pending.pop(0))
+        for s in self.streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        res = []
+        for o in self.out:
+            c = o["counts"].tolist()
+            v = {"dense": o["dense"][:c[0]], "T": o["T"], "status": o["status"], "median_resolution": o["median_resolution"]}
+            if self.want_sparse:
+                v["sparse"] = o["sparse"][:c[1]]
+            res.append(v)
+        return res, h2d, d2h
+
+    def _drain(self, item):
+        i, st, ev, r, t = item
+        ev.synchronize()
+        o = self.out[i]
+        c = o["counts"].tolist()
+        n = 4 * 4 + 4 + o["T"].numel() * 4 + o["status"].numel()
+        with torch.cuda.stream(st):
+            o["dense"][:c[0]].copy_(r.dense[:c[0]], non_blocking=True)
+            n += c[0] * 24
+            if self.want_sparse:
+                o["sparse"][:c[1]].copy_(r.sparse[:c[1]], non_blocking=True)
+                n += c[1] * 24
+            # keep the device tensors alive until the copies are done
+            r.dense.record_stream(st)
+            r.sparse.record_stream(st)
+        return n

@@ -252,6 +252,25 @@ F4L_API int f4l_scatter_global_matches(const int32_t* labels, const float* src_s
                                int64_t* corres, int32_t n_raw, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* (b') B4: 2D-vote coarse matching, base.py:3016-3070.  For each of the P source patches (CSR sp_ptr /
+ * sp_idx over source points) the target-patch label that most of its points' 2D-lifted matches
+ * (corr2d (n_src,2) int64, col1 = target point or -1) fall into: label_tgt (n_tgt) int32 is
+ * idx_pts2spt_tgt.  best (P) = that label, mapped through label_to_local (n_labels) when given
+ * (position of the label in idx_spt_tgt, -1 if the patch was removed: base.py:3062-3064), or -1 when the
+ * patch has no 2D match; best_count (P); flag (P): 1 = several labels share the top count (the
+ * reference's argsort order is unspecified; the smallest label is returned), 255 = not resolved
+ * (> 512 distinct labels in one patch). */
+F4L_API int f4l_vote_tgt_patch(const int64_t* corr2d, const int32_t* sp_idx, const int32_t* sp_ptr, int32_t P,
+                       const int32_t* label_tgt, int32_t n_tgt, const int32_t* label_to_local,
+                       int32_t n_labels, int32_t* best, int32_t* best_count, uint8_t* flag, void* stream);
+
+/* (c) F1: displacement-magnitude gates, base.py:2875-2876, :1635-1636, src/f2s3.py:392,419-441.
+ * rows (K,stride>=6) f32 [src | tgt | ...]; mag (K) f32 or NULL; mask (K) uint8 = mag <= limit (strict 0)
+ * or mag < limit (strict 1); limit = max_mag, or d_max[0]*factor when d_max (device scalar, e.g. the
+ * median from f4l_select_kth for the 30 x median gate) is given. */
+F4L_API int f4l_magnitude_mask(const float* rows, int32_t K, int32_t stride, float max_mag, const float* d_max,
+                       float factor, int strict, float* mag, uint8_t* mask, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Piecewise "ICP" (rows G1, A5, F5): the whole of src/piecewise_icp.py:89-202 in one launch
  * sequence, fp64 like Open3D / numpy.                                                kernel K-g
