@@ -313,8 +313,14 @@ k_sparse_offsets(const int32_t* __restrict__ sparse_cnt, int Q, int32_t* __restr
 
 // ------------------------------------------------------------------------------------------
 #define AA_THREADS 256
-#define AA_SMEM_PTS 8192
+#define AA_SMEM_PTS 2048
 
+// D5 + A4.  CTA per pair.  The target patch is staged in shared memory as pivot-local float4 (|coordinate|
+// of a patch is metres, so f32 keeps ~1e-7 m); every source point is transformed, written to the dense DVF
+// and scanned against the staged targets in f32 keeping the two smallest distances.  When the two are
+// separated by more than the f32 error bound the f32 argmin IS the fp64 argmin and only that one distance
+// is re-evaluated in fp64 from the original coordinates (threshold test d^2 < thr^2 of base.py:82 stays
+// exact); otherwise the point takes the exact fp64 scan (first minimal index).
 __global__ void __launch_bounds__(AA_THREADS)
 k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
                const int32_t* __restrict__ sp_idx, const int32_t* __restrict__ sp_ptr,
@@ -324,8 +330,9 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                const int32_t* __restrict__ dense_off, const int32_t* __restrict__ t2s_off, int Q,
                f4l_fine_params prm, const float* __restrict__ d_median_res, float* __restrict__ dense,
                float* __restrict__ tgt2src, int32_t* __restrict__ nn, int32_t* __restrict__ sparse_cnt) {
-    extern __shared__ float sref[];
+    extern __shared__ float4 sref[];
     __shared__ int s_cnt;
+    __shared__ unsigned s_maxabs;
     const int tid = threadIdx.x;
     for (int q = blockIdx.x; q < Q; q += gridDim.x) {
         __syncthreads();
@@ -344,12 +351,24 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
         }
         const bool assign_nn = prm.assign_type == 1;
         const bool staged = nt <= AA_SMEM_PTS;
-        if (tid == 0) s_cnt = 0;
+        if (tid == 0) { s_cnt = 0; s_maxabs = 0u; }
+        double cB[3] = {0, 0, 0};
+        if (nt > 0) {
+            float x, y, z;
+            load_ptf(tgt_pts, tp_idx, t0, x, y, z);
+            cB[0] = x; cB[1] = y; cB[2] = z;
+        }
+        __syncthreads();
         if ((assign_nn && staged) || prm.output_tgt2src) {
+            float mabs = 0.f;
             for (int j = tid; j < nt; j += AA_THREADS) {
                 float x, y, z;
                 load_ptf(tgt_pts, tp_idx, t0 + j, x, y, z);
-                if (assign_nn && staged) { sref[3 * j] = x; sref[3 * j + 1] = y; sref[3 * j + 2] = z; }
+                if (assign_nn && staged) {
+                    const float lx = (float)((double)x - cB[0]), ly = (float)((double)y - cB[1]), lz = (float)((double)z - cB[2]);
+                    sref[j] = make_float4(lx, ly, lz, 0.f);
+                    mabs = fmaxf(mabs, fmaxf(fabsf(lx), fmaxf(fabsf(ly), fabsf(lz))));
+                }
                 if (prm.output_tgt2src) {
                     // base.py:3389-3390: R^T (q - t), the subtraction in f32
                     const double dx = (double)(x - Tq[3]), dy = (double)(y - Tq[7]), dz = (double)(z - Tq[11]);
@@ -359,8 +378,12 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                     row[2] = make_float2(y, z);
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(F4L_FULL, mabs, o));
+            if ((tid & 31) == 0) atomicMax(&s_maxabs, __float_as_uint(mabs));
         }
         __syncthreads();
+        const float maxabs_t = __uint_as_float(s_maxabs);
         // adaptive threshold, base.py:3420-3423
         double thr = rmse[q] * 2.0;
         const double mres = d_median_res ? (double)d_median_res[0] : prm.median_max_resolution;
@@ -381,13 +404,43 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             if (assign_nn) {
                 double best = INFINITY;
                 int bj = -1;
-                for (int j = 0; j < nt; ++j) {
-                    float gx, gy, gz;
-                    if (staged) { gx = sref[3 * j]; gy = sref[3 * j + 1]; gz = sref[3 * j + 2]; }
-                    else load_ptf(tgt_pts, tp_idx, t0 + j, gx, gy, gz);
-                    const double dx = (double)mx - (double)gx, dy = (double)my - (double)gy, dz = (double)mz - (double)gz;
-                    const double d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 < best) { best = d2; bj = j; }
+                bool exact_scan = !staged;
+                if (staged && nt > 0) {
+                    const float qx = (float)((double)mx - cB[0]), qy = (float)((double)my - cB[1]), qz = (float)((double)mz - cB[2]);
+                    float d1 = INFINITY, d2 = INFINITY;
+                    int j1 = 0;
+#pragma unroll 4
+                    for (int j = 0; j < nt; ++j) {
+                        const float4 b = sref[j];
+                        const float dx = qx - b.x, dy = qy - b.y, dz = qz - b.z;
+                        const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        const bool better = dd < d1;
+                        d2 = better ? d1 : fminf(d2, dd);
+                        j1 = better ? j : j1;
+                        d1 = better ? dd : d1;
+                    }
+                    // |sqrt(dd) - true distance| <= eta for every candidate (coordinate rounding + f32 arithmetic)
+                    const float mabs = fmaxf(maxabs_t, fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
+                    const float eta = 1e-6f * (mabs + sqrtf(d2));
+                    const float r1 = sqrtf(d1);
+                    if (d2 > d1 + 4.f * eta * r1 + 4.f * eta * eta && d2 > d1) {
+                        float gx, gy, gz;
+                        load_ptf(tgt_pts, tp_idx, t0 + j1, gx, gy, gz);
+                        const double dx = (double)mx - (double)gx, dy = (double)my - (double)gy, dz = (double)mz - (double)gz;
+                        best = dx * dx + dy * dy + dz * dz;
+                        bj = j1;
+                    } else {
+                        exact_scan = true;
+                    }
+                }
+                if (exact_scan) {
+                    for (int j = 0; j < nt; ++j) {
+                        float gx, gy, gz;
+                        load_ptf(tgt_pts, tp_idx, t0 + j, gx, gy, gz);
+                        const double dx = (double)mx - (double)gx, dy = (double)my - (double)gy, dz = (double)mz - (double)gz;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        if (d2 < best) { best = d2; bj = j; }
+                    }
                 }
                 const bool ok = best < thr2;
                 nn[s0 + i] = ok ? bj : -1;
@@ -517,7 +570,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
     }
     static bool attr_set = false;
     const size_t smem_fit = (size_t)ICP_SMEM_PTS * 3 * sizeof(float);
-    const size_t smem_aa = (size_t)AA_SMEM_PTS * 3 * sizeof(float);
+    const size_t smem_aa = (size_t)AA_SMEM_PTS * sizeof(float4);
     if (!attr_set) {
         cudaFuncSetAttribute(k_patch_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
         cudaFuncSetAttribute(k_apply_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_aa);

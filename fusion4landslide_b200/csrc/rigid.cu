@@ -6,47 +6,142 @@
 #include "rigid_device.cuh"
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_segmented_kabsch(const float* __restrict__ src, const float* __restrict__ tgt,
-                   const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
-                   const float* __restrict__ w, const int32_t* __restrict__ seg_start,
-                   const int32_t* __restrict__ seg_count, int Q, double eps, float weight_thresh,
-                   int variant, float* __restrict__ R, float* __restrict__ t,
-                   double* __restrict__ T64, float* __restrict__ res, uint8_t* __restrict__ flag) {
+// K-d.  A warp owns a GROUP of 32 consecutive segments: the moments of each segment are accumulated
+// cooperatively (coalesced, every point read from HBM once) and reduce-scattered over the warp with 16
+// double shuffles; then every lane solves the 3x3 SVD of ITS segment, so the long fp64 dependency chain of
+// the Jacobi sweeps runs 32-wide instead of once per warp.
+#define KAB_WARPS 4
+
+// butterfly reduce-scatter of the 16 moments: afterwards lane l holds the warp total of m[(l >> 1) & 15]
+__device__ __forceinline__ double moments_reduce_scatter(const Moments& M, int lane) {
+    double v8[8], v4[4], v2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double send = b4 ? M.m[i] : M.m[i + 8];
+        const double keep = b4 ? M.m[i + 8] : M.m[i];
+        v8[i] = keep + __shfl_xor_sync(F4L_FULL, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = b3 ? v8[i] : v8[i + 4];
+        const double keep = b3 ? v8[i + 4] : v8[i];
+        v4[i] = keep + __shfl_xor_sync(F4L_FULL, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = b2 ? v4[i] : v4[i + 2];
+        const double keep = b2 ? v4[i + 2] : v4[i];
+        v2[i] = keep + __shfl_xor_sync(F4L_FULL, send, 4);
+    }
+    double v = (b1 ? v2[1] : v2[0]) + __shfl_xor_sync(F4L_FULL, b1 ? v2[0] : v2[1], 2);
+    v += __shfl_xor_sync(F4L_FULL, v, 1);
+    return v;
+}
+
+// pass 1: warp per segment, coalesced single read of the points, 16 raw moments to scratch
+__global__ void __launch_bounds__(KAB_WARPS * 32)
+k_kabsch_moments(const float* __restrict__ src, const float* __restrict__ tgt,
+                 const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
+                 const float* __restrict__ w, const int32_t* __restrict__ seg_start,
+                 const int32_t* __restrict__ seg_count, int Q, float weight_thresh, int variant,
+                 double* __restrict__ mom) {
     const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int q = blockIdx.x * KAB_WARPS + (threadIdx.x >> 5);
     if (q >= Q) return;
     int s0, n;
     seg_bounds(seg_start, seg_count, q, s0, n);
-    double Rm[9], tv[3];
-    bool bad = warp_fit_segment(src, tgt, src_idx, tgt_idx, w, s0, n, eps, weight_thresh, variant, lane, Rm, tv);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) R[(size_t)q * 9 + i] = (float)Rm[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) t[(size_t)q * 3 + i] = (float)tv[i];
-        if (T64) {
-            double* T = T64 + (size_t)q * 16;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                T[i * 4 + 0] = Rm[i * 3 + 0]; T[i * 4 + 1] = Rm[i * 3 + 1]; T[i * 4 + 2] = Rm[i * 3 + 2];
-                T[i * 4 + 3] = tv[i];
-            }
-            T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
-        }
-        if (flag) flag[q] = bad ? 1 : 0;
-    }
-    if (res) {
+    Moments M;
+    moments_zero(M);
+    if (n > 0) {
+        double ps[3], pt[3];
+        load_pt(src, src_idx, s0, ps[0], ps[1], ps[2]);
+        load_pt(tgt, tgt_idx, s0, pt[0], pt[1], pt[2]);
+#pragma unroll 2
         for (int i = lane; i < n; i += 32) {
             const int k = s0 + i;
             double sx, sy, sz, tx, ty, tz;
             load_pt(src, src_idx, k, sx, sy, sz);
             load_pt(tgt, tgt_idx, k, tx, ty, tz);
-            double rx = Rm[0] * sx + Rm[1] * sy + Rm[2] * sz + tv[0] - tx;
-            double ry = Rm[3] * sx + Rm[4] * sy + Rm[5] * sz + tv[1] - ty;
-            double rz = Rm[6] * sx + Rm[7] * sy + Rm[8] * sz + tv[2] - tz;
-            res[k] = (float)sqrt(rx * rx + ry * ry + rz * rz);
+            double wi = 1.0;
+            if (w) {
+                float wf = __ldg(w + k);
+                if (variant == 0 && wf < weight_thresh) wf = 0.f;
+                wi = (double)wf;
+            }
+            moments_add(M, wi, sx - ps[0], sy - ps[1], sz - ps[2], tx - pt[0], ty - pt[1], tz - pt[2]);
         }
+    }
+    const double v = moments_reduce_scatter(M, lane);
+    if (!(lane & 1)) mom[(size_t)q * 16 + (lane >> 1)] = v;
+}
+
+// pass 2: THREAD per segment: reference formulas + 3x3 SVD, 32 segments per warp in flight
+__global__ void __launch_bounds__(128)
+k_kabsch_fit(const float* __restrict__ src, const float* __restrict__ tgt, const int32_t* __restrict__ src_idx,
+             const int32_t* __restrict__ tgt_idx, const int32_t* __restrict__ seg_start,
+             const int32_t* __restrict__ seg_count, int Q, double eps, int variant, double* __restrict__ mom,
+             float* __restrict__ R, float* __restrict__ t, double* __restrict__ T64, uint8_t* __restrict__ flag) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int s0, n;
+    seg_bounds(seg_start, seg_count, q, s0, n);
+    double Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tv[3] = {0, 0, 0};
+    bool bad = true;
+    if (n > 0) {
+        Moments M;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M.m[i] = mom[(size_t)q * 16 + i];
+        double ps[3], pt[3];
+        load_pt(src, src_idx, s0, ps[0], ps[1], ps[2]);
+        load_pt(tgt, tgt_idx, s0, pt[0], pt[1], pt[2]);
+        bad = fit_from_moments(M, ps, pt, eps, variant, Rm, tv);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[(size_t)q * 9 + i] = (float)Rm[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[(size_t)q * 3 + i] = (float)tv[i];
+    if (T64) {
+        double* T = T64 + (size_t)q * 16;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            T[i * 4 + 0] = Rm[i * 3 + 0]; T[i * 4 + 1] = Rm[i * 3 + 1]; T[i * 4 + 2] = Rm[i * 3 + 2];
+            T[i * 4 + 3] = tv[i];
+        }
+        T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+    }
+    if (flag) flag[q] = bad ? 1 : 0;
+    // fp64 fit for the residual pass (overwrites this segment's moments)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) mom[(size_t)q * 16 + i] = Rm[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) mom[(size_t)q * 16 + 9 + i] = tv[i];
+}
+
+// pass 3 (optional): residuals ||R s + t - tgt||, warp per segment
+__global__ void __launch_bounds__(KAB_WARPS * 32)
+k_kabsch_residuals(const float* __restrict__ src, const float* __restrict__ tgt, const int32_t* __restrict__ src_idx,
+                   const int32_t* __restrict__ tgt_idx, const int32_t* __restrict__ seg_start,
+                   const int32_t* __restrict__ seg_count, int Q, const double* __restrict__ fit, float* __restrict__ res) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * KAB_WARPS + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    int s0, n;
+    seg_bounds(seg_start, seg_count, q, s0, n);
+    double Rs[9], ts[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rs[i] = fit[(size_t)q * 16 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ts[i] = fit[(size_t)q * 16 + 9 + i];
+    for (int i = lane; i < n; i += 32) {
+        const int k = s0 + i;
+        double sx, sy, sz, tx, ty, tz;
+        load_pt(src, src_idx, k, sx, sy, sz);
+        load_pt(tgt, tgt_idx, k, tx, ty, tz);
+        const double rx = Rs[0] * sx + Rs[1] * sy + Rs[2] * sz + ts[0] - tx;
+        const double ry = Rs[3] * sx + Rs[4] * sy + Rs[5] * sz + ts[1] - ty;
+        const double rz = Rs[6] * sx + Rs[7] * sy + Rs[8] * sz + ts[2] - tz;
+        res[k] = (float)sqrt(rx * rx + ry * ry + rz * rz);
     }
 }
 
@@ -59,11 +154,37 @@ extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const in
     if (Q == 0) return F4L_OK;
     F4L_REQUIRE(src && tgt && seg_start && R && t, "null pointer");
     F4L_REQUIRE(variant == F4L_KABSCH_PROCRUSTES || variant == F4L_KABSCH_F2S3, "unknown variant");
-    const int warps = 4;
-    f4l_mark("k_segmented_kabsch", (cudaStream_t)stream);
-    k_segmented_kabsch<<<f4l_div_up(Q, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q, (double)eps, weight_thresh, variant, R, t,
-        T64, res, flag);
+    cudaStream_t st = (cudaStream_t)stream;
+    // 128 B of scratch per segment (raw moments, then the fp64 fit), stream-ordered pool allocation
+    double* mom = nullptr;
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        // keep freed blocks in the default pool instead of returning them to the OS at every synchronisation
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = 1ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready = true;
+    }
+    if (cudaMallocAsync((void**)&mom, (size_t)Q * 16 * sizeof(double), st) != cudaSuccess) {
+        f4l_set_error("f4l_segmented_kabsch: cudaMallocAsync of %zu bytes failed", (size_t)Q * 128);
+        cudaGetLastError();
+        return F4L_E_CUDA;
+    }
+    f4l_mark("k_kabsch_moments", st);
+    k_kabsch_moments<<<f4l_div_up(Q, KAB_WARPS), KAB_WARPS * 32, 0, st>>>(src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q,
+                                                                         weight_thresh, variant, mom);
+    f4l_mark("k_kabsch_fit", st);
+    k_kabsch_fit<<<f4l_div_up(Q, 128), 128, 0, st>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count, Q, (double)eps, variant,
+                                                    mom, R, t, T64, flag);
+    if (res) {
+        f4l_mark("k_kabsch_residuals", st);
+        k_kabsch_residuals<<<f4l_div_up(Q, KAB_WARPS), KAB_WARPS * 32, 0, st>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count,
+                                                                               Q, mom, res);
+    }
+    cudaFreeAsync(mom, st);
     return f4l_finish("f4l_segmented_kabsch", stream);
 }
 
