@@ -104,6 +104,11 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
 #pragma unroll
         for (int r = 0; r < 3; ++r) a[c][r] = H[r * 3 + c];
     double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // v[c][r]
+    // Rotation angles without divisions or square roots on the dependency chain: with a = beta - alpha,
+    // b = 2 gamma, r = sqrt(a^2 + b^2) the Hestenes rotation (smaller root of tan 2x = b/a) is
+    //   cos 2x = |a|/r,  c = sqrt((1 + cos 2x)/2),  s = sign(a) b / (2 r c)
+    // -- two rsqrt per rotation instead of three divisions and three square roots (fp64 div/sqrt are
+    // multi-hundred-cycle sequences and this chain is pure latency for the warp that owns the patch).
     for (int sweep = 0; sweep < 40; ++sweep) {
         bool rotated = false;
 #pragma unroll
@@ -113,12 +118,14 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
             double alpha = a[p][0] * a[p][0] + a[p][1] * a[p][1] + a[p][2] * a[p][2];
             double beta = a[q][0] * a[q][0] + a[q][1] * a[q][1] + a[q][2] * a[q][2];
             double gamma = a[p][0] * a[q][0] + a[p][1] * a[q][1] + a[p][2] * a[q][2];
-            if (gamma == 0.0 || fabs(gamma) <= 1.2e-16 * sqrt(alpha * beta)) continue;
+            if (gamma == 0.0 || gamma * gamma <= 1.44e-32 * (alpha * beta)) continue;
             rotated = true;
-            double zeta = (beta - alpha) / (2.0 * gamma);
-            double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            double c = 1.0 / sqrt(1.0 + t * t);
-            double s = c * t;
+            const double da = beta - alpha, db = 2.0 * gamma;
+            const double inv_r = rsqrt(da * da + db * db);
+            const double x = 0.5 + 0.5 * fabs(da) * inv_r;       // cos^2 of the rotation angle, in [0.5, 1]
+            const double inv_c = rsqrt(x);
+            const double c = x * inv_c;
+            const double s = copysign(0.5, da) * db * inv_r * inv_c;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 double ap = a[p][r], aq = a[q][r];
@@ -131,9 +138,12 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
         }
         if (!rotated) break;
     }
-    double sv[3];
+    double sv[3], n2[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sv[c] = sqrt(a[c][0] * a[c][0] + a[c][1] * a[c][1] + a[c][2] * a[c][2]);
+    for (int c = 0; c < 3; ++c) {
+        n2[c] = a[c][0] * a[c][0] + a[c][1] * a[c][1] + a[c][2] * a[c][2];
+        sv[c] = n2[c] > 0.0 ? n2[c] * rsqrt(n2[c]) : 0.0;
+    }
     // sort columns by singular value, descending (3-element network)
     int o0 = 0, o1 = 1, o2 = 2;
     if (sv[o0] < sv[o1]) { int tmp = o0; o0 = o1; o1 = tmp; }
@@ -146,7 +156,7 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
     for (int c = 0; c < 3; ++c) {
         const int k = ord[c];
         S[c] = sv[k];
-        double inv = sv[k] > tiny ? 1.0 / sv[k] : 0.0;
+        double inv = sv[k] > tiny ? rsqrt(n2[k]) : 0.0;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             u[c][r] = a[k][r] * inv;

@@ -12,21 +12,31 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from fusion4landslide_b200 import ops, synth  # noqa: E402
+from fusion4landslide_b200 import _lib, ops, synth  # noqa: E402
+
+LAST_KERNELS = {}
 
 
 def timed(fn, reps, flush):
+    """Median over reps of the SUM of the library's in-stream per-kernel times (CUDA events recorded on the
+    launching stream around every kernel of the call), L2 flushed before each rep.  The per-kernel split of the
+    last rep is left in LAST_KERNELS; host launch overhead is excluded (it dominates at these sizes)."""
+    L = _lib.lib()
     fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         flush.zero_()                       # 256 MB write: evicts the 126 MB L2
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        L.f4l_profile_reset()
+        L.f4l_profile_enable(1)
+        fn()
+        torch.cuda.synchronize()
+        L.f4l_profile_enable(0)
+        tab = _lib.profile_table()
+        ts.append(sum(v[0] for v in tab.values()))
+        LAST_KERNELS.clear()
+        LAST_KERNELS.update({k: round(v[0], 5) for k, v in tab.items()})
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -52,7 +62,8 @@ def main():
 
     def rec(name, ms, nbytes, extra=None):
         gbs = nbytes / ms / 1e6
-        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GB/s": gbs, "frac_of_measured_hbm": gbs / peak}
+        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GB/s": gbs, "frac_of_measured_hbm": gbs / peak,
+                     "kernels_ms": dict(LAST_KERNELS)}
         if extra:
             out[name].update(extra)
 
