@@ -18,6 +18,7 @@
 struct GridParams {
     float minx, miny, minz;
     float inv_cell, cell;
+    float inv[3];        // per-axis 1/cell; 0 on a flattened axis (all points fall in layer 0)
     int nx, ny, nz;
     int ncells;
     int pad;
@@ -30,6 +31,7 @@ __global__ void k_bbox_init(unsigned* bb) {
 }
 
 __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ p, int n, unsigned* bb) {
+    __shared__ float smn[8][3], smx[8][3];
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -47,12 +49,18 @@ __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ p, int n
             mx[a] = fmaxf(mx[a], __shfl_xor_sync(F4L_FULL, mx[a], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMin(bb + a, f2ord(mn[a]));
-            atomicMax(bb + 3 + a, f2ord(mx[a]));
-        }
+        for (int a = 0; a < 3; ++a) { smn[wid][a] = mn[a]; smx[wid][a] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {                 // one atomic pair per axis per CTA
+        const int a = threadIdx.x;
+        float lo = smn[0][a], hi = smx[0][a];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fminf(lo, smn[w][a]); hi = fmaxf(hi, smx[w][a]); }
+        atomicMin(bb + a, f2ord(lo));
+        atomicMax(bb + 3 + a, f2ord(hi));
     }
 }
 
@@ -69,24 +77,33 @@ __global__ void k_grid_params(const unsigned* bb, int m, float cell_in, int max_
     float longest = fmaxf(ex[0], fmaxf(ex[1], ex[2]));
     if (!(c > 0.f)) c = fmaxf(longest, 1e-3f);
     c = fmaxf(c, longest * 1e-4f);   // never more than 10^4 cells per axis
-    int nx, ny, nz;
+    // surface-like clouds (terrain scans): the thin axis is not binned at all -- a 2D table is 10-50x
+    // smaller (memset / scan / cell lookups) and a query visits 3 row ranges per ring instead of 9.
+    // The ring test below only ever uses binned axes, so the search stays exact.
+    int thin = 0;
+    if (ex[1] < ex[thin]) thin = 1;
+    if (ex[2] < ex[thin]) thin = 2;
+    float mid = INFINITY;
+    for (int a = 0; a < 3; ++a)
+        if (a != thin) mid = fminf(mid, ex[a]);
+    const bool flat = ex[thin] <= 0.25f * mid;
+    int nn[3];
     for (int it = 0; it < 64; ++it) {
-        nx = (int)floorf(ex[0] / c) + 1;
-        ny = (int)floorf(ex[1] / c) + 1;
-        nz = (int)floorf(ex[2] / c) + 1;
-        if ((long long)nx * ny * nz <= (long long)max_cells) break;
+        for (int a = 0; a < 3; ++a) nn[a] = (flat && a == thin) ? 1 : (int)floorf(ex[a] / c) + 1;
+        if ((long long)nn[0] * nn[1] * nn[2] <= (long long)max_cells) break;
         c *= 1.2599211f;
     }
     gp->minx = mn[0]; gp->miny = mn[1]; gp->minz = mn[2];
     gp->cell = c; gp->inv_cell = 1.0f / c;
-    gp->nx = nx; gp->ny = ny; gp->nz = nz;
-    gp->ncells = nx * ny * nz;
+    for (int a = 0; a < 3; ++a) gp->inv[a] = (flat && a == thin) ? 0.f : 1.0f / c;
+    gp->nx = nn[0]; gp->ny = nn[1]; gp->nz = nn[2];
+    gp->ncells = nn[0] * nn[1] * nn[2];
 }
 
 __device__ __forceinline__ void cell_of(const GridParams& g, float x, float y, float z, int& cx, int& cy, int& cz) {
-    cx = min(max((int)floorf((x - g.minx) * g.inv_cell), 0), g.nx - 1);
-    cy = min(max((int)floorf((y - g.miny) * g.inv_cell), 0), g.ny - 1);
-    cz = min(max((int)floorf((z - g.minz) * g.inv_cell), 0), g.nz - 1);
+    cx = min(max((int)floorf((x - g.minx) * g.inv[0]), 0), g.nx - 1);
+    cy = min(max((int)floorf((y - g.miny) * g.inv[1]), 0), g.ny - 1);
+    cz = min(max((int)floorf((z - g.minz) * g.inv[2]), 0), g.nz - 1);
 }
 
 __global__ void __launch_bounds__(256)
@@ -228,7 +245,7 @@ __global__ void k_fill_none(int n, int k, int* idx, float* d2) {
 // ---- workspace layout ------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline int knn_max_cells(int M) {
-    long long c = 8LL * (long long)M + 4096;
+    long long c = 2LL * (long long)M + 4096;
     if (c > (1LL << 27)) c = 1LL << 27;
     return (int)c;
 }

@@ -40,7 +40,7 @@ __device__ __forceinline__ double moments_reduce_scatter(const Moments& M, int l
 }
 
 // pass 1: warp per segment, coalesced single read of the points, 16 raw moments to scratch
-__global__ void __launch_bounds__(KAB_WARPS * 32)
+__global__ void __launch_bounds__(KAB_WARPS * 32, 6)
 k_kabsch_moments(const float* __restrict__ src, const float* __restrict__ tgt,
                  const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
                  const float* __restrict__ w, const int32_t* __restrict__ seg_start,
@@ -57,19 +57,31 @@ k_kabsch_moments(const float* __restrict__ src, const float* __restrict__ tgt,
         double ps[3], pt[3];
         load_pt(src, src_idx, s0, ps[0], ps[1], ps[2]);
         load_pt(tgt, tgt_idx, s0, pt[0], pt[1], pt[2]);
-#pragma unroll 2
-        for (int i = lane; i < n; i += 32) {
-            const int k = s0 + i;
-            double sx, sy, sz, tx, ty, tz;
-            load_pt(src, src_idx, k, sx, sy, sz);
-            load_pt(tgt, tgt_idx, k, tx, ty, tz);
-            double wi = 1.0;
-            if (w) {
-                float wf = __ldg(w + k);
-                if (variant == 0 && wf < weight_thresh) wf = 0.f;
-                wi = (double)wf;
+        // 4 points per lane per trip, all 24 (+4) loads issued before the fp64 math: the kernel is a pure
+        // stream (every point read once), so the bytes in flight per warp set the achieved bandwidth
+        for (int i0 = lane; i0 < n; i0 += 128) {
+            float f[4][6], wf[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = s0 + i0 + 32 * u;
+                const bool ok = i0 + 32 * u < n;
+                if (ok) {
+                    load_ptf(src, src_idx, k, f[u][0], f[u][1], f[u][2]);
+                    load_ptf(tgt, tgt_idx, k, f[u][3], f[u][4], f[u][5]);
+                    wf[u] = w ? __ldg(w + k) : 1.f;
+                } else {
+                    f[u][0] = f[u][1] = f[u][2] = f[u][3] = f[u][4] = f[u][5] = 0.f;
+                    wf[u] = -1.f;                      // marks an absent point
+                }
             }
-            moments_add(M, wi, sx - ps[0], sy - ps[1], sz - ps[2], tx - pt[0], ty - pt[1], tz - pt[2]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (wf[u] < 0.f && !(i0 + 32 * u < n)) continue;
+                float wv = wf[u];
+                if (variant == 0 && w && wv < weight_thresh) wv = 0.f;
+                moments_add(M, (double)wv, (double)f[u][0] - ps[0], (double)f[u][1] - ps[1], (double)f[u][2] - ps[2],
+                            (double)f[u][3] - pt[0], (double)f[u][4] - pt[1], (double)f[u][5] - pt[2]);
+            }
         }
     }
     const double v = moments_reduce_scatter(M, lane);
@@ -211,33 +223,43 @@ k_apply_transforms(const float* __restrict__ pts, const int32_t* __restrict__ id
         Rm[i * 3 + 0] = Tq[i * 4 + 0]; Rm[i * 3 + 1] = Tq[i * 4 + 1]; Rm[i * 3 + 2] = Tq[i * 4 + 2];
         tv[i] = Tq[i * 4 + 3];
     }
-    for (int i = lane; i < n; i += 32) {
-        double x, y, z;
-        load_pt(pts, idx, s0 + i, x, y, z);
-        float2* row = reinterpret_cast<float2*>(dvf + (size_t)(o0 + i) * 6);
-        float ox, oy, oz;
-        if (!inverse) {
-            ox = (float)(Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0]);
-            oy = (float)(Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1]);
-            oz = (float)(Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2]);
-            row[0] = make_float2((float)x, (float)y);
-            row[1] = make_float2((float)z, ox);
-            row[2] = make_float2(oy, oz);
-        } else {
-            // f32 subtraction first, as base.py:3389-3390 does: R^T (p - t)
-            double dx = (double)((float)x - (float)tv[0]);
-            double dy = (double)((float)y - (float)tv[1]);
-            double dz = (double)((float)z - (float)tv[2]);
-            ox = (float)(Rm[0] * dx + Rm[3] * dy + Rm[6] * dz);
-            oy = (float)(Rm[1] * dx + Rm[4] * dy + Rm[7] * dz);
-            oz = (float)(Rm[2] * dx + Rm[5] * dy + Rm[8] * dz);
-            row[0] = make_float2(ox, oy);
-            row[1] = make_float2(oz, (float)x);
-            row[2] = make_float2((float)y, (float)z);
+    for (int i0 = lane; i0 < n; i0 += 128) {
+        float px[4], py[4], pz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {              // all loads of the trip in flight before any math / store
+            px[u] = py[u] = pz[u] = 0.f;
+            if (i0 + 32 * u < n) load_ptf(pts, idx, s0 + i0 + 32 * u, px[u], py[u], pz[u]);
         }
-        if (mag) {
-            float ex = ox - (float)x, ey = oy - (float)y, ez = oz - (float)z;
-            mag[o0 + i] = sqrtf(ex * ex + ey * ey + ez * ez);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i >= n) continue;
+            const double x = px[u], y = py[u], z = pz[u];
+            float2* row = reinterpret_cast<float2*>(dvf + (size_t)(o0 + i) * 6);
+            float ox, oy, oz;
+            if (!inverse) {
+                ox = (float)(Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0]);
+                oy = (float)(Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1]);
+                oz = (float)(Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2]);
+                row[0] = make_float2((float)x, (float)y);
+                row[1] = make_float2((float)z, ox);
+                row[2] = make_float2(oy, oz);
+            } else {
+                // f32 subtraction first, as base.py:3389-3390 does: R^T (p - t)
+                double dx = (double)((float)x - (float)tv[0]);
+                double dy = (double)((float)y - (float)tv[1]);
+                double dz = (double)((float)z - (float)tv[2]);
+                ox = (float)(Rm[0] * dx + Rm[3] * dy + Rm[6] * dz);
+                oy = (float)(Rm[1] * dx + Rm[4] * dy + Rm[7] * dz);
+                oz = (float)(Rm[2] * dx + Rm[5] * dy + Rm[8] * dz);
+                row[0] = make_float2(ox, oy);
+                row[1] = make_float2(oz, (float)x);
+                row[2] = make_float2((float)y, (float)z);
+            }
+            if (mag) {
+                float ex = ox - (float)x, ey = oy - (float)y, ez = oz - (float)z;
+                mag[o0 + i] = sqrtf(ex * ex + ey * ey + ez * ez);
+            }
         }
     }
 }
