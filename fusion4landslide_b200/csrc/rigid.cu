@@ -39,49 +39,66 @@ __device__ __forceinline__ double moments_reduce_scatter(const Moments& M, int l
     return v;
 }
 
-// pass 1: warp per segment, coalesced single read of the points, 16 raw moments to scratch
-__global__ void __launch_bounds__(KAB_WARPS * 32, 6)
+// pass 1: warp per segment, every point read from HBM exactly once, 16 raw moments to scratch.
+// The kernel is a pure stream with ~25 fp64 ops per 24 bytes, so what limits it is bytes in flight, and
+// with fp64 accumulators registers cap the occupancy: each warp therefore stages its segment through shared
+// memory with cp.async (LDGSTS, 4-byte granules so that unaligned / gathered segments work) -- a whole
+// 256-point chunk (6 KB) is in flight per warp without holding a single register.
+#define KAB_CHUNK 256
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(KAB_WARPS * 32)
 k_kabsch_moments(const float* __restrict__ src, const float* __restrict__ tgt,
                  const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
                  const float* __restrict__ w, const int32_t* __restrict__ seg_start,
                  const int32_t* __restrict__ seg_count, int Q, float weight_thresh, int variant,
                  double* __restrict__ mom) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * KAB_WARPS + (threadIdx.x >> 5);
+    __shared__ float stage[KAB_WARPS][2][KAB_CHUNK * 3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = blockIdx.x * KAB_WARPS + wid;
     if (q >= Q) return;
     int s0, n;
     seg_bounds(seg_start, seg_count, q, s0, n);
+    float* ss = stage[wid][0];
+    float* st = stage[wid][1];
     Moments M;
     moments_zero(M);
     if (n > 0) {
         double ps[3], pt[3];
         load_pt(src, src_idx, s0, ps[0], ps[1], ps[2]);
         load_pt(tgt, tgt_idx, s0, pt[0], pt[1], pt[2]);
-        // 4 points per lane per trip, all 24 (+4) loads issued before the fp64 math: the kernel is a pure
-        // stream (every point read once), so the bytes in flight per warp set the achieved bandwidth
-        for (int i0 = lane; i0 < n; i0 += 128) {
-            float f[4][6], wf[4];
+        for (int c0 = 0; c0 < n; c0 += KAB_CHUNK) {
+            const int cnt = min(KAB_CHUNK, n - c0);
+            if (!src_idx && !tgt_idx) {
+                // packed pairs: the chunk is one contiguous run of 3*cnt floats per array
+                const float* gs = src + (size_t)(s0 + c0) * 3;
+                const float* gt = tgt + (size_t)(s0 + c0) * 3;
+                for (int e = lane; e < 3 * cnt; e += 32) { cp_async4(ss + e, gs + e); cp_async4(st + e, gt + e); }
+            } else {
+                for (int j = lane; j < cnt; j += 32) {
+                    const size_t a = src_idx ? (size_t)src_idx[s0 + c0 + j] : (size_t)(s0 + c0 + j);
+                    const size_t b = tgt_idx ? (size_t)tgt_idx[s0 + c0 + j] : (size_t)(s0 + c0 + j);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = s0 + i0 + 32 * u;
-                const bool ok = i0 + 32 * u < n;
-                if (ok) {
-                    load_ptf(src, src_idx, k, f[u][0], f[u][1], f[u][2]);
-                    load_ptf(tgt, tgt_idx, k, f[u][3], f[u][4], f[u][5]);
-                    wf[u] = w ? __ldg(w + k) : 1.f;
-                } else {
-                    f[u][0] = f[u][1] = f[u][2] = f[u][3] = f[u][4] = f[u][5] = 0.f;
-                    wf[u] = -1.f;                      // marks an absent point
+                    for (int k = 0; k < 3; ++k) { cp_async4(ss + 3 * j + k, src + a * 3 + k); cp_async4(st + 3 * j + k, tgt + b * 3 + k); }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (wf[u] < 0.f && !(i0 + 32 * u < n)) continue;
-                float wv = wf[u];
-                if (variant == 0 && w && wv < weight_thresh) wv = 0.f;
-                moments_add(M, (double)wv, (double)f[u][0] - ps[0], (double)f[u][1] - ps[1], (double)f[u][2] - ps[2],
-                            (double)f[u][3] - pt[0], (double)f[u][4] - pt[1], (double)f[u][5] - pt[2]);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            for (int j = lane; j < cnt; j += 32) {
+                double wi = 1.0;
+                if (w) {
+                    float wf = __ldg(w + s0 + c0 + j);
+                    if (variant == 0 && wf < weight_thresh) wf = 0.f;
+                    wi = (double)wf;
+                }
+                moments_add(M, wi, (double)ss[3 * j] - ps[0], (double)ss[3 * j + 1] - ps[1], (double)ss[3 * j + 2] - ps[2],
+                            (double)st[3 * j] - pt[0], (double)st[3 * j + 1] - pt[1], (double)st[3 * j + 2] - pt[2]);
             }
+            __syncwarp();
         }
     }
     const double v = moments_reduce_scatter(M, lane);
@@ -209,6 +226,7 @@ k_apply_transforms(const float* __restrict__ pts, const int32_t* __restrict__ id
                    const int32_t* __restrict__ out_start, const uint8_t* __restrict__ seg_skip, int Q,
                    const float* __restrict__ T, int inverse, float* __restrict__ dvf,
                    float* __restrict__ mag) {
+    __shared__ __align__(16) float s_rows[8][192];
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
@@ -223,44 +241,47 @@ k_apply_transforms(const float* __restrict__ pts, const int32_t* __restrict__ id
         Rm[i * 3 + 0] = Tq[i * 4 + 0]; Rm[i * 3 + 1] = Tq[i * 4 + 1]; Rm[i * 3 + 2] = Tq[i * 4 + 2];
         tv[i] = Tq[i * 4 + 3];
     }
-    for (int i0 = lane; i0 < n; i0 += 128) {
-        float px[4], py[4], pz[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {              // all loads of the trip in flight before any math / store
-            px[u] = py[u] = pz[u] = 0.f;
-            if (i0 + 32 * u < n) load_ptf(pts, idx, s0 + i0 + 32 * u, px[u], py[u], pz[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + 32 * u;
-            if (i >= n) continue;
-            const double x = px[u], y = py[u], z = pz[u];
-            float2* row = reinterpret_cast<float2*>(dvf + (size_t)(o0 + i) * 6);
-            float ox, oy, oz;
+    // rows of a warp trip are contiguous in the output (32 x 24 B): stage them in shared memory and write them
+    // back as three fully coalesced float2 stores instead of three 24-byte-strided ones
+    float* buf = s_rows[threadIdx.x >> 5];
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const int cnt = min(32, n - i0);
+        float ox = 0.f, oy = 0.f, oz = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
+        if (i < n) {
+            load_ptf(pts, idx, s0 + i, fx, fy, fz);
+            const double x = fx, y = fy, z = fz;
             if (!inverse) {
                 ox = (float)(Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0]);
                 oy = (float)(Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1]);
                 oz = (float)(Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2]);
-                row[0] = make_float2((float)x, (float)y);
-                row[1] = make_float2((float)z, ox);
-                row[2] = make_float2(oy, oz);
+                buf[lane * 6 + 0] = fx; buf[lane * 6 + 1] = fy; buf[lane * 6 + 2] = fz;
+                buf[lane * 6 + 3] = ox; buf[lane * 6 + 4] = oy; buf[lane * 6 + 5] = oz;
             } else {
                 // f32 subtraction first, as base.py:3389-3390 does: R^T (p - t)
-                double dx = (double)((float)x - (float)tv[0]);
-                double dy = (double)((float)y - (float)tv[1]);
-                double dz = (double)((float)z - (float)tv[2]);
+                const double dx = (double)(fx - (float)tv[0]);
+                const double dy = (double)(fy - (float)tv[1]);
+                const double dz = (double)(fz - (float)tv[2]);
                 ox = (float)(Rm[0] * dx + Rm[3] * dy + Rm[6] * dz);
                 oy = (float)(Rm[1] * dx + Rm[4] * dy + Rm[7] * dz);
                 oz = (float)(Rm[2] * dx + Rm[5] * dy + Rm[8] * dz);
-                row[0] = make_float2(ox, oy);
-                row[1] = make_float2(oz, (float)x);
-                row[2] = make_float2((float)y, (float)z);
+                buf[lane * 6 + 0] = ox; buf[lane * 6 + 1] = oy; buf[lane * 6 + 2] = oz;
+                buf[lane * 6 + 3] = fx; buf[lane * 6 + 4] = fy; buf[lane * 6 + 5] = fz;
             }
             if (mag) {
-                float ex = ox - (float)x, ey = oy - (float)y, ez = oz - (float)z;
+                const float ex = ox - fx, ey = oy - fy, ez = oz - fz;
                 mag[o0 + i] = sqrtf(ex * ex + ey * ey + ez * ez);
             }
         }
+        __syncwarp();
+        float2* out2 = reinterpret_cast<float2*>(dvf + (size_t)(o0 + i0) * 6);
+        const float2* b2 = reinterpret_cast<const float2*>(buf);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int e = lane + 32 * u;
+            if (e < cnt * 3) out2[e] = b2[e];
+        }
+        __syncwarp();
     }
 }
 
