@@ -77,6 +77,10 @@ SIGNATURES = {
     "f4l_scatter_global_matches": (c_int, [P, P, P, c_i32, P, P, c_f32, P, c_i32, P, c_size, P]),
     "f4l_vote_tgt_patch": (c_int, [P, P, P, c_i32, P, c_i32, P, c_i32, P, P, P, P]),
     "f4l_magnitude_mask": (c_int, [P, c_i32, c_i32, c_f32, P, c_f32, c_int, P, P, P]),
+    "f4l_labels_to_csr_workspace_bytes": (c_size, [c_i32]),
+    "f4l_labels_to_csr": (c_int, [P, c_i32, c_i32, P, P, P, P, P, P, c_size, P]),
+    "f4l_gather_pairs_csr_workspace_bytes": (c_size, [c_i32]),
+    "f4l_gather_pairs_csr": (c_int, [P, P, P, c_i32, P, P, c_i32, P, c_size, P]),
     "f4l_piecewise_icp_workspace_bytes": (c_size, [c_i32, c_i32]),
     "f4l_piecewise_icp": (c_int, [P, c_i32, P, c_i32, c_f64, c_i32, c_i32, P, P, P, P, P, P, P, P, c_size, P]),
     "f4l_fine_matching_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),

@@ -68,6 +68,15 @@ def rigidity_check(src, tgt, seg_start, thres_dist_diff, seg_count=None, src_idx
     return ratio, dmean
 
 
+def segmented_median(x, seg_start, seg_count=None):
+    """torch.median (lower median) of each segment of x (K) f32 -> (Q) f32."""
+    Q = seg_start.numel() if seg_count is not None else seg_start.numel() - 1
+    med = _empty((Q,), F32, x)
+    check(lib().f4l_segmented_median(ptr(x, F32), ptr(seg_start, I32), ptr(seg_count, I32, True), Q, ptr(med),
+                                     stream_ptr(x.device)), "f4l_segmented_median")
+    return med
+
+
 _WS = {}
 
 
@@ -187,6 +196,40 @@ def scatter_global_matches(labels, src_sub, tgt_sub, voxel2pts_src, voxel2pts_tg
                                            float(max_magnitude), ptr(corres), n_raw, ptr(ws), ws.numel(),
                                            stream_ptr(src_sub.device)), "f4l_scatter_global_matches")
     return corres
+
+
+def labels_to_csr(labels, min_pts=10):
+    """prepare_pts2spt_dict (base.py:1301-1351).  labels (N) i64 -> patch_label (P) i64, ptr (P+1) i32, idx (items) i32,
+    patch_of_point (N) i32.  Reads the two sizes back (this step precedes the path)."""
+    n = labels.shape[0]
+    dev = labels.device
+    lab = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    p = torch.empty((n + 1,), dtype=I32, device=dev)
+    idx = torch.empty((max(n, 1),), dtype=I32, device=dev)
+    pop = torch.empty((max(n, 1),), dtype=I32, device=dev)
+    counts = torch.empty((2,), dtype=I32, device=dev)
+    ws = _workspace(lib().f4l_labels_to_csr_workspace_bytes(n), dev)
+    check(lib().f4l_labels_to_csr(ptr(labels, torch.int64), n, int(min_pts), ptr(lab), ptr(p), ptr(idx), ptr(pop), ptr(counts),
+                                  ptr(ws), ws.numel(), stream_ptr(dev)), "f4l_labels_to_csr")
+    P_, items = counts.tolist()
+    return lab[:P_], p[:P_ + 1], idx[:items], pop[:n]
+
+
+def gather_pairs_csr(p, idx, sel):
+    """Concatenated point lists of the selected patches: (out_ptr (Q+1) i32, out_idx i32, total items)."""
+    Q = sel.numel()
+    dev = p.device
+    sel = sel.to(I32).contiguous()
+    out_ptr = torch.empty((Q + 1,), dtype=I32, device=dev)
+    ws = _workspace(lib().f4l_gather_pairs_csr_workspace_bytes(Q), dev)
+    check(lib().f4l_gather_pairs_csr(ptr(p, I32), ptr(idx, I32), ptr(sel, I32), Q, ptr(out_ptr), None, 0, ptr(ws), ws.numel(),
+                                     stream_ptr(dev)), "f4l_gather_pairs_csr")
+    total = int(out_ptr[-1].item()) if Q else 0
+    out_idx = torch.empty((max(total, 1),), dtype=I32, device=dev)
+    if total:
+        check(lib().f4l_gather_pairs_csr(ptr(p, I32), ptr(idx, I32), ptr(sel, I32), Q, ptr(out_ptr), ptr(out_idx), total,
+                                         ptr(ws), ws.numel(), stream_ptr(dev)), "f4l_gather_pairs_csr")
+    return out_ptr, out_idx[:total], total
 
 
 def vote_tgt_patch(corr2d, sp_idx, sp_ptr, label_tgt, label_to_local=None):

@@ -40,35 +40,23 @@ class TileInputs:
 
 
 def prepare_tile(src, tgt, label_src, label_tgt, corr3d, corr2d=None, min_pts=10, pairs=None):
-    """labels -> CSR patch lists + matched patch pairs.  `pairs` = (src patch pos, tgt patch pos) from the
-    coarse matching; default: patches carrying the same label (synthetic ground truth pairing)."""
-    lab_s, ptr_s, idx_s = synth.patches_from_labels(label_src, min_pts)      # idx_spt2pts_src
-    lab_t, ptr_t, idx_t = synth.patches_from_labels(label_tgt, min_pts)      # idx_spt2pts_tgt
-    m, j = pairs if pairs is not None else synth.pair_patches(lab_s, lab_t)
+    """labels -> CSR patch lists + matched patch pairs, on the GPU (f4l_labels_to_csr, f4l_gather_pairs_csr).
+    `pairs` = (src patch pos, tgt patch pos) from the coarse matching; default: patches carrying the same
+    label (the synthetic ground-truth pairing).  CPU tensors are handled by synth.prepare_tile_host (the CPU
+    arm of bench.py builds the oracle's inputs with it)."""
+    if not src.is_cuda:
+        return synth.prepare_tile_host(src, tgt, label_src, label_tgt, corr3d, corr2d, min_pts, pairs, TileInputs)
     dev = src.device
-
-    def gather_csr(ptr, idx, sel):
-        cnt = (ptr[1:] - ptr[:-1]).long()[sel]
-        p = torch.zeros(sel.numel() + 1, dtype=torch.int64, device=dev)
-        p[1:] = torch.cumsum(cnt, 0)
-        seg = torch.repeat_interleave(torch.arange(sel.numel(), device=dev), cnt)
-        within = torch.arange(int(p[-1]), device=dev) - p[:-1][seg]
-        items = idx[(ptr[:-1].long()[sel])[seg] + within]
-        return p.to(torch.int32), items.contiguous()
-
+    lab_s, ptr_s, idx_s, _ = ops.labels_to_csr(label_src.to(dev, torch.int64).contiguous(), min_pts)   # idx_spt2pts_src
+    lab_t, ptr_t, idx_t, tpo = ops.labels_to_csr(label_tgt.to(dev, torch.int64).contiguous(), min_pts)  # idx_spt2pts_tgt
+    m, j = pairs if pairs is not None else synth.pair_patches(lab_s, lab_t)
     t = TileInputs()
     t.src, t.tgt, t.corr3d, t.corr2d = src.contiguous(), tgt.contiguous(), corr3d.contiguous(), corr2d
-    t.sp_ptr, t.sp_idx = gather_csr(ptr_s, idx_s, m)
-    t.tp_ptr, t.tp_idx = gather_csr(ptr_t, idx_t, j)
-    tpo = torch.full((tgt.shape[0],), -1, dtype=torch.int32, device=dev)
-    seg_t = torch.repeat_interleave(torch.arange(lab_t.numel(), device=dev, dtype=torch.int32),
-                                    (ptr_t[1:] - ptr_t[:-1]).long())
-    tpo[idx_t.long()] = seg_t
-    t.tgt_patch_of_point = tpo
+    t.sp_ptr, t.sp_idx, t.n_src_items = ops.gather_pairs_csr(ptr_s, idx_s, m)
+    t.tp_ptr, t.tp_idx, t.n_tgt_items = ops.gather_pairs_csr(ptr_t, idx_t, j)
+    t.tgt_patch_of_point = tpo.contiguous()
     t.pair_tgt_patch = j.to(torch.int32).contiguous()
     t.n_pairs = int(m.numel())
-    t.n_src_items = int(t.sp_ptr[-1]) if t.n_pairs else 0
-    t.n_tgt_items = int(t.tp_ptr[-1]) if t.n_pairs else 0
     return t
 
 

@@ -172,3 +172,36 @@ def pair_patches(lab_s, lab_t):
     ok = lab_t[pos] == lab_s if lab_t.numel() else torch.zeros_like(lab_s, dtype=torch.bool)
     m = torch.nonzero(ok).flatten()
     return m, pos[m]
+
+
+def prepare_tile_host(src, tgt, label_src, label_tgt, corr3d, corr2d, min_pts, pairs, cls):
+    """Torch-only twin of pipeline.prepare_tile for HOST tensors: builds the oracle / CPU-arm inputs (patch
+    lists of the matched pairs) without touching the CUDA library.  `cls` = pipeline.TileInputs."""
+    lab_s, ptr_s, idx_s = patches_from_labels(label_src, min_pts)
+    lab_t, ptr_t, idx_t = patches_from_labels(label_tgt, min_pts)
+    m, j = pairs if pairs is not None else pair_patches(lab_s, lab_t)
+    dev = src.device
+
+    def gather_csr(ptr, idx, sel):
+        cnt = (ptr[1:] - ptr[:-1]).long()[sel]
+        p = torch.zeros(sel.numel() + 1, dtype=torch.int64, device=dev)
+        p[1:] = torch.cumsum(cnt, 0)
+        seg = torch.repeat_interleave(torch.arange(sel.numel(), device=dev), cnt)
+        within = torch.arange(int(p[-1]), device=dev) - p[:-1][seg]
+        items = idx[(ptr[:-1].long()[sel])[seg] + within]
+        return p.to(torch.int32), items.contiguous()
+
+    t = cls()
+    t.src, t.tgt, t.corr3d, t.corr2d = src.contiguous(), tgt.contiguous(), corr3d.contiguous(), corr2d
+    t.sp_ptr, t.sp_idx = gather_csr(ptr_s, idx_s, m)
+    t.tp_ptr, t.tp_idx = gather_csr(ptr_t, idx_t, j)
+    tpo = torch.full((tgt.shape[0],), -1, dtype=torch.int32, device=dev)
+    seg_t = torch.repeat_interleave(torch.arange(lab_t.numel(), device=dev, dtype=torch.int32),
+                                    (ptr_t[1:] - ptr_t[:-1]).long())
+    tpo[idx_t.long()] = seg_t
+    t.tgt_patch_of_point = tpo
+    t.pair_tgt_patch = j.to(torch.int32).contiguous()
+    t.n_pairs = int(m.numel())
+    t.n_src_items = int(t.sp_ptr[-1]) if t.n_pairs else 0
+    t.n_tgt_items = int(t.tp_ptr[-1]) if t.n_pairs else 0
+    return t

@@ -272,6 +272,25 @@ F4L_API int f4l_magnitude_mask(const float* rows, int32_t K, int32_t stride, flo
                        float factor, int strict, float* mag, uint8_t* mask, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Label -> CSR tables, the step right before the path.
+ * f4l_labels_to_csr replaces prepare_pts2spt_dict, base.py:1301-1351 (collections.Counter + one boolean
+ * mask per patch): labels (n) int64 -> patches with count > min_pts in ascending label order, the points
+ * of a patch in ascending index order.  Outputs sized for the worst case: patch_label (n) int64,
+ * ptr (n+1) int32, idx (n) int32, patch_of_point (n) int32 (-1 = point of a removed patch),
+ * counts (2) int32 = {patches P, items ptr[P]}.
+ * f4l_gather_pairs_csr builds the concatenated point lists of matched patch pairs (spt_corres_src/tgt,
+ * base.py:3156-3157): sel (Q) patch positions -> out_ptr (Q+1), out_idx (out_ptr[Q]); pass out_idx = NULL
+ * to only compute out_ptr. */
+F4L_API size_t f4l_labels_to_csr_workspace_bytes(int32_t n);
+F4L_API int f4l_labels_to_csr(const int64_t* labels, int32_t n, int32_t min_pts, int64_t* patch_label,
+                      int32_t* ptr, int32_t* idx, int32_t* patch_of_point, int32_t* counts,
+                      void* workspace, size_t workspace_bytes, void* stream);
+F4L_API size_t f4l_gather_pairs_csr_workspace_bytes(int32_t Q);
+F4L_API int f4l_gather_pairs_csr(const int32_t* ptr, const int32_t* idx, const int32_t* sel, int32_t Q,
+                         int32_t* out_ptr, int32_t* out_idx, int32_t out_capacity, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Piecewise "ICP" (rows G1, A5, F5): the whole of src/piecewise_icp.py:89-202 in one launch
  * sequence, fp64 like Open3D / numpy.                                                kernel K-g
  *   union bounding box, its 8 corners appended to both clouds (:96-105), depth =

@@ -136,3 +136,23 @@ def test_fine_matching_empty(cuda):
     r = ops.fine_matching(pts, pts, z, p, z, p, torch.zeros(5, dtype=torch.int32, device=cuda), z,
                           corr3d=torch.zeros(5, 2, dtype=torch.int64, device=cuda), n_src_items=0, n_tgt_items=0)
     assert r.counts.tolist() == [0, 0, 0, 0]
+
+
+def test_prepare_tile_kernels_match_host_twin(cuda):
+    """f4l_labels_to_csr / f4l_gather_pairs_csr (prepare_pts2spt_dict, base.py:1301-1351) against the torch
+    restatement used for the CPU arm: identical tables."""
+    from fusion4landslide_b200 import pipeline, synth
+    d = synth.make_tile(50_000, seed=3, patch_pts=120)
+    lab_s = d["label_src"].clone()
+    lab_s[::97] = -5                               # a negative label and ...
+    lab_s[5::1013] = 10**12 + 7                    # ... a huge one with <= 10 points
+    host = pipeline.prepare_tile(d["src"], d["tgt"], lab_s, d["label_tgt"], d["corr3d"])
+    dev = pipeline.prepare_tile(d["src"].to(cuda), d["tgt"].to(cuda), lab_s.to(cuda), d["label_tgt"].to(cuda),
+                                d["corr3d"].to(cuda))
+    torch.cuda.synchronize()
+    assert (host.n_pairs, host.n_src_items, host.n_tgt_items) == (dev.n_pairs, dev.n_src_items, dev.n_tgt_items)
+    for k in ("sp_ptr", "sp_idx", "tp_ptr", "tp_idx", "tgt_patch_of_point", "pair_tgt_patch"):
+        assert torch.equal(getattr(host, k), getattr(dev, k).cpu()), k
+    from fusion4landslide_b200 import ops
+    e = ops.labels_to_csr(torch.zeros((0,), dtype=torch.int64, device=cuda))
+    assert e[0].numel() == 0 and e[1].tolist() == [0] and e[2].numel() == 0

@@ -71,6 +71,32 @@ def test_weighted_procrustes_and_refine(cuda, golden_dir):
     assert _act_err(T[:3, :3].cpu().numpy(), T[:3, 3].cpu().numpy(), To[:3, :3], To[:3, 3], s) < TOL
 
 
+def test_rgb_guided_refine(cuda):
+    """src/rgb_guided.py:99-125: res < 2.5 * median(res) mask and the 70 % quality flag."""
+    from fusion4landslide_b200 import rgb_guided
+    rng = np.random.default_rng(8)
+    cases = []
+    for n, frac in ((200, 0.05), (64, 0.45), (11, 0.0)):
+        s, t = _patch(rng, n, rng.uniform(0, 60, 3), outliers=frac)
+        cases.append(np.hstack([s, t]).astype(np.float32))
+    ptr = np.zeros(len(cases) + 1, np.int32)
+    ptr[1:] = np.cumsum([c.shape[0] for c in cases])
+    allc = np.concatenate(cases)
+    R, t, mask, mask2, res, med = rgb_guided.refine_local_rigid_correspondences_batched(
+        torch.from_numpy(allc).to(cuda), torch.from_numpy(ptr).to(cuda))
+    for i, c in enumerate(cases):
+        Ro, to = rigid.weighted_procrustes(c[:, :3], c[:, 3:6], None, 0.0, 1e-6)
+        ro = np.linalg.norm(c[:, :3].astype(np.float64) @ Ro.T + to - c[:, 3:6], axis=1)
+        mo = ro < 2.5 * rigid.lower_median(ro)
+        got = mask[ptr[i]:ptr[i + 1]].cpu().numpy()
+        borderline = np.abs(ro - 2.5 * rigid.lower_median(ro)) < 1e-5
+        assert ((got == mo) | borderline).all()
+        assert bool(mask2[i]) == bool(mo.mean() >= 0.70) or abs(mo.mean() - 0.70) < 0.02
+        assert _act_err(R[i].cpu().numpy(), t[i].cpu().numpy(), Ro, to, c[:, :3]) < TOL
+        kept, T, m1, m2 = rgb_guided.refine_local_rigid_correspondences(torch.from_numpy(c).to(cuda))
+        assert kept.shape[0] == int(got.sum()) and T.is_cuda and bool(m2) == bool(mask2[i])
+
+
 def test_icp_registration_dict(cuda):
     from fusion4landslide_b200.o3d_tools import icp_registration
     rng = np.random.default_rng(2)
