@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="side streams for tile-level concurrency (1 = serial)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the exchange (N > 1)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = the D5 kernel stores every dense row into all peers' fields over NVLink "
+                         "(exchange.PeerExchange), 'nccl' = all_gather_into_tensor after the step (baseline)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="patch pairs in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -191,70 +195,106 @@ def run_b200(a):
         caps = torch.tensor([cap_rows, cap_pairs], device=dev, dtype=torch.int64)
         dist.all_reduce(caps, op=dist.ReduceOp.MAX)
         cap_rows, cap_pairs = int(caps[0]), int(caps[1])
-    dense_arena = torch.empty((cap_rows, 6), dtype=torch.float32, device=dev)
+    fused = world > 1 and a.exchange == "fused" and not a.no_gather
+    ex = None
+    if fused:
+        from fusion4landslide_b200.exchange import PeerExchange
+        ex = PeerExchange(cap_rows, dev, n_buffers=2)        # double-buffered by step parity
+        arenas = [ex.local_arena(0), ex.local_arena(1)]
+    else:
+        arenas = [torch.empty((cap_rows, 6), dtype=torch.float32, device=dev)]
+    dense_arena = arenas[0]
     T_arena = torch.empty((cap_pairs, 4, 4), dtype=torch.float32, device=dev)
     n_tiles_max = (a.tiles + world - 1) // world
     counts_arena = torch.zeros((n_tiles_max, 4), dtype=torch.int32, device=dev)
-    outs, meds = [], torch.empty((max(len(tiles), 1),), dtype=torch.float32, device=dev)
-    ro = po = 0
+    meds = torch.empty((max(len(tiles), 1),), dtype=torch.float32, device=dev)
     from fusion4landslide_b200.ops import FineResult
-    for i, t in enumerate(tiles):
-        r = FineResult()
-        Q = t.n_pairs
-        r.T = T_arena[po:po + Q]
-        r.T64 = torch.empty((Q, 4, 4), dtype=torch.float64, device=dev)
-        r.status = torch.empty((Q,), dtype=torch.int8, device=dev)
-        r.K = torch.empty((Q,), dtype=torch.int32, device=dev)
-        r.fitness = torch.empty((Q,), dtype=torch.float64, device=dev)
-        r.rmse = torch.empty((Q,), dtype=torch.float64, device=dev)
-        r.iters = torch.empty((Q,), dtype=torch.int32, device=dev)
-        r.ratio_inlier = torch.empty((Q,), dtype=torch.float32, device=dev)
-        r.dist_mean = torch.empty((Q,), dtype=torch.float32, device=dev)
-        r.dense = dense_arena[ro:ro + t.n_src_items]
-        r.sparse = torch.empty((2 * t.n_src_items, 6), dtype=torch.float32, device=dev)
-        r.tgt2src = None
-        r.counts = counts_arena[i]
-        outs.append(r)
-        ro += t.n_src_items
-        po += Q
+    outs_par, peers_par = [], []
+    shared = None
+    for par, arena in enumerate(arenas):
+        outs, peers = [], []
+        ro = po = 0
+        for i, t in enumerate(tiles):
+            r = FineResult()
+            Q = t.n_pairs
+            if par == 0:
+                r.T = T_arena[po:po + Q]
+                r.T64 = torch.empty((Q, 4, 4), dtype=torch.float64, device=dev)
+                r.status = torch.empty((Q,), dtype=torch.int8, device=dev)
+                r.K = torch.empty((Q,), dtype=torch.int32, device=dev)
+                r.fitness = torch.empty((Q,), dtype=torch.float64, device=dev)
+                r.rmse = torch.empty((Q,), dtype=torch.float64, device=dev)
+                r.iters = torch.empty((Q,), dtype=torch.int32, device=dev)
+                r.ratio_inlier = torch.empty((Q,), dtype=torch.float32, device=dev)
+                r.dist_mean = torch.empty((Q,), dtype=torch.float32, device=dev)
+                r.sparse = torch.empty((2 * t.n_src_items, 6), dtype=torch.float32, device=dev)
+                r.tgt2src = None
+                r.counts = counts_arena[i]
+            else:                                           # parity 1 differs only in the dense arena
+                for k in FineResult.__slots__:
+                    setattr(r, k, getattr(outs_par[0][i], k))
+            r.dense = arena[ro:ro + t.n_src_items]
+            outs.append(r)
+            peers.append(ex.peer_ptrs(par, ro) if fused else None)
+            ro += t.n_src_items
+            po += Q
+        outs_par.append(outs)
+        peers_par.append(peers if fused else None)
+    outs = outs_par[0]
     if world > 1:
-        gathered_dense = torch.empty((world * cap_rows, 6), dtype=torch.float32, device=dev)
+        gathered_dense = None if fused else torch.empty((world * cap_rows, 6), dtype=torch.float32, device=dev)
         gathered_T = torch.empty((world * cap_pairs, 4, 4), dtype=torch.float32, device=dev)
         gathered_counts = torch.empty((world * n_tiles_max * 4,), dtype=torch.int32, device=dev)
 
     streams = pipeline.make_streams(a.streams, dev) if a.streams > 1 else None
 
-    def step_tiles():
-        pipeline.displacement_field_tiles(tiles, cfg, outs, meds, streams)
+    def step_tiles(par=0):
+        pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par])
 
     # The per-tile launch sequence is static (all buffers preallocated, no host round trip inside the path):
-    # capture one step -- all tiles, all side streams -- into a CUDA graph and replay it.
-    graph = None
+    # capture one step -- all tiles, all side streams -- into a CUDA graph and replay it (one graph per
+    # exchange-buffer parity).
+    graphs = None
     if not a.no_graph:
-        step_tiles()                                   # sizes the per-stream workspaces outside the capture
+        step_tiles(0)                                  # sizes the per-stream workspaces outside the capture
         torch.cuda.synchronize()
         try:
-            cap = torch.cuda.Stream(device=dev)
-            cap.wait_stream(torch.cuda.current_stream(dev))
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=cap):
-                step_tiles()
-            torch.cuda.current_stream(dev).wait_stream(cap)
-            graph = g
+            graphs = []
+            for par in range(len(arenas)):
+                cap = torch.cuda.Stream(device=dev)
+                cap.wait_stream(torch.cuda.current_stream(dev))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    step_tiles(par)
+                torch.cuda.current_stream(dev).wait_stream(cap)
+                graphs.append(g)
         except Exception as e:                         # report, then fall back to plain launches
             sys.stderr.write("bench.py: CUDA graph capture failed (%s); launching kernel by kernel\n" % (e,))
-            graph = None
+            graphs = None
             torch.cuda.synchronize()
+    graph = graphs
+    step_no = [0]
+
+    def compute(par):
+        if graphs is not None:
+            graphs[par].replay()
+        else:
+            step_tiles(par)
+
+    def exchange():
+        # fused: the dense rows are already in every rank's field; this small all-gather is also the barrier
+        # that orders all ranks' pushed rows before anyone reads the field
+        dist.all_gather_into_tensor(gathered_T, T_arena)
+        if not fused:
+            dist.all_gather_into_tensor(gathered_dense, dense_arena)
+        dist.all_gather_into_tensor(gathered_counts, counts_arena.reshape(-1))
 
     def step():
-        if graph is not None:
-            graph.replay()
-        else:
-            step_tiles()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered_T, T_arena)
-            dist.all_gather_into_tensor(gathered_dense, dense_arena)
-            dist.all_gather_into_tensor(gathered_counts, counts_arena.reshape(-1))
+        par = step_no[0] % len(arenas)
+        step_no[0] += 1
+        compute(par)
+        if world > 1 and not a.no_gather:
+            exchange()
 
     def barrier():
         if world > 1:
@@ -296,6 +336,35 @@ def run_b200(a):
         dist.all_reduce(stat)
     dvf_points, src_points, launches_all = int(stat[0]), int(stat[1]), int(stat[2])
     value = dvf_points / (ms_step * 1e-3)
+
+    # ---- breakdown (N > 1): one extra step with the compute and the exchange timed apart ---------
+    breakdown = None
+    if world > 1 and not a.no_gather:
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        ea.record()
+        compute(step_no[0] % len(arenas))
+        step_no[0] += 1
+        eb.record()
+        exchange()
+        ec.record()
+        barrier()
+        bd = torch.tensor([ea.elapsed_time(eb), eb.elapsed_time(ec)], device=dev, dtype=torch.float64)
+        dist.all_reduce(bd, op=dist.ReduceOp.MAX)
+        breakdown = {"compute_ms": float(bd[0]), "exchange_ms": float(bd[1]), "exchange": a.exchange,
+                     "exchange_bytes_received_per_rank": int((world - 1) * (cap_rows * 24 + cap_pairs * 64))}
+        if fused:
+            # check the fused exchange against NCCL: gather the local arenas of the last step the plain way
+            last = (step_no[0] - 1) % len(arenas)
+            ref = torch.empty((world * cap_rows, 6), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(ref, arenas[last])
+            ref = ref.view(world, cap_rows, 6)
+            cnt = gathered_counts.view(world, n_tiles_max, 4)[:, :, 0].sum(1).tolist()
+            ok = all(torch.equal(ex.field(last)[r, :cnt[r]], ref[r, :cnt[r]]) for r in range(world))
+            okt = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            breakdown["fused_field_equals_nccl_all_gather"] = bool(int(okt[0]))
+            del ref
 
     # ---- e2e: same step through the host-buffer API (H2D inputs + D2H results inside the timing) ----
     e2e = None
@@ -378,13 +447,15 @@ def run_b200(a):
             "vs_baseline": None, "dtype": "f32 i/o, f64 accumulation", "data": "synthetic",
             "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts,
                        "src_points_per_step": src_points, "dvf_points_per_step": dvf_points,
-                       "parallelism": "tile-sharded x%d, all-gather of transforms + dense DVF" % world,
+                       "parallelism": ("tile-sharded x%d; dense DVF rows stored into every GPU's field by the producing kernel over "
+                                       "NVLink (peer memory), transforms + row counts all-gathered over NCCL" % world) if fused
+                       else "tile-sharded x%d, NCCL all-gather of transforms + dense DVF" % world,
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
                              (sum(t.nbytes() for t in tiles) * world / 1e9),
                        "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type, "streams": a.streams,
                        "cuda_graph": graph is not None},
             "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline,
-            "kernels": kernel_table, "cpu_baseline": cpu,
+            "kernels": kernel_table, "cpu_baseline": cpu, "breakdown": breakdown,
         }
         print(json.dumps(line))
     if world > 1:

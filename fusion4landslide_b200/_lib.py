@@ -20,6 +20,10 @@ c_f64 = ctypes.c_double
 c_size = ctypes.c_size_t
 
 
+MAX_PEERS = 7          # F4L_MAX_PEERS
+PEER_HANDLE_BYTES = 64  # F4L_PEER_HANDLE_BYTES
+
+
 class FineParams(ctypes.Structure):
     """f4l_fine_params (include/f4l_b200.h)."""
     _fields_ = [
@@ -42,6 +46,7 @@ class FineBuffers(ctypes.Structure):
         ("fitness", c_void_p), ("rmse", c_void_p), ("iters", c_void_p),
         ("ratio_inlier", c_void_p), ("dist_mean", c_void_p),
         ("dense", c_void_p), ("sparse", c_void_p), ("tgt2src", c_void_p), ("counts", c_void_p),
+        ("n_peers", c_i32), ("peer_dense", c_void_p * MAX_PEERS),
     ]
 
 
@@ -83,6 +88,11 @@ SIGNATURES = {
     "f4l_gather_pairs_csr": (c_int, [P, P, P, c_i32, P, P, c_i32, P, c_size, P]),
     "f4l_piecewise_icp_workspace_bytes": (c_size, [c_i32, c_i32]),
     "f4l_piecewise_icp": (c_int, [P, c_i32, P, c_i32, c_f64, c_i32, c_i32, P, P, P, P, P, P, P, P, c_size, P]),
+    "f4l_peer_alloc": (c_int, [c_size, ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    "f4l_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "f4l_peer_close": (c_int, [P]),
+    "f4l_peer_free": (c_int, [P]),
+    "f4l_peer_enable_access": (c_int, [c_i32]),
     "f4l_fine_matching_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),
     "f4l_fine_matching": (c_int, [ctypes.POINTER(FineParams), ctypes.POINTER(FineBuffers), P, c_size, P]),
 }

@@ -313,6 +313,7 @@ k_sparse_offsets(const int32_t* __restrict__ sparse_cnt, int Q, int32_t* __restr
 
 // ------------------------------------------------------------------------------------------
 #define AA_THREADS 256
+struct PeerDense { float* p[F4L_MAX_PEERS]; };
 #define AA_SMEM_PTS 2048
 
 // D5 + A4.  CTA per pair.  The target patch is staged in shared memory as pivot-local float4 (|coordinate|
@@ -329,8 +330,12 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                const int8_t* __restrict__ status, const float* __restrict__ T32, const double* __restrict__ rmse,
                const int32_t* __restrict__ dense_off, const int32_t* __restrict__ t2s_off, int Q,
                f4l_fine_params prm, const float* __restrict__ d_median_res, float* __restrict__ dense,
-               float* __restrict__ tgt2src, int32_t* __restrict__ nn, int32_t* __restrict__ sparse_cnt) {
+               float* __restrict__ tgt2src, int32_t* __restrict__ nn, int32_t* __restrict__ sparse_cnt,
+               int n_peers, PeerDense peers) {
     extern __shared__ float4 sref[];
+    // dense rows of one chunk of AA_THREADS source points: written out as contiguous float2 runs to the local
+    // arena AND to the same rows of every peer GPU's arena (the displacement-field all-gather, fused)
+    __shared__ __align__(16) float srow[AA_THREADS * 6];
     __shared__ int s_cnt;
     __shared__ unsigned s_maxabs;
     const int tid = threadIdx.x;
@@ -391,13 +396,16 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
         thr = fmax(thr, mres);
         const double thr2 = thr * thr;
         int kept = 0;
-        for (int i = tid; i < ns; i += AA_THREADS) {
+        const size_t row0 = (size_t)dense_off[q];
+        for (int base = 0; base < ns; base += AA_THREADS) {
+          const int i = base + tid;
+          if (i < ns) {
             double x, y, z;
             load_pt(src_pts, sp_idx, s0 + i, x, y, z);
             const float mx = (float)(R[0] * x + R[1] * y + R[2] * z + tv[0]);
             const float my = (float)(R[3] * x + R[4] * y + R[5] * z + tv[1]);
             const float mz = (float)(R[6] * x + R[7] * y + R[8] * z + tv[2]);
-            float2* row = reinterpret_cast<float2*>(dense + (size_t)(dense_off[q] + i) * 6);
+            float2* row = reinterpret_cast<float2*>(srow + tid * 6);
             row[0] = make_float2((float)x, (float)y);
             row[1] = make_float2((float)z, mx);
             row[2] = make_float2(my, mz);
@@ -446,6 +454,19 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                 nn[s0 + i] = ok ? bj : -1;
                 kept += ok ? 1 : 0;
             }
+          }
+          __syncthreads();
+          {   // flush the chunk: rows [base, base + rows) are one contiguous run of rows * 3 float2
+              const int n2 = min(AA_THREADS, ns - base) * 3;
+              const float2* s2 = reinterpret_cast<const float2*>(srow);
+              float2* d2 = reinterpret_cast<float2*>(dense + (row0 + base) * 6);
+              for (int t = tid; t < n2; t += AA_THREADS) d2[t] = s2[t];
+              for (int p = 0; p < n_peers; ++p) {
+                  float2* r2 = reinterpret_cast<float2*>(peers.p[p] + (row0 + base) * 6);
+                  for (int t = tid; t < n2; t += AA_THREADS) r2[t] = s2[t];
+              }
+          }
+          __syncthreads();
         }
         if (assign_nn) {
             kept = warp_sum(kept);
@@ -563,6 +584,12 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
                     bf->ratio_inlier && bf->dist_mean && bf->dense && bf->sparse, "null output");
     F4L_REQUIRE(!prm->output_tgt2src || bf->tgt2src, "tgt2src is null");
     F4L_REQUIRE(!prm->icp_refine || prm->icp_threshold > 0.0, "icp_threshold must be > 0");
+    F4L_REQUIRE(bf->n_peers >= 0 && bf->n_peers <= F4L_MAX_PEERS, "n_peers out of range");
+    PeerDense peers;
+    for (int p = 0; p < F4L_MAX_PEERS; ++p) {
+        peers.p[p] = p < bf->n_peers ? bf->peer_dense[p] : nullptr;
+        F4L_REQUIRE(p >= bf->n_peers || peers.p[p], "peer_dense pointer is null");
+    }
     FineWs w = fine_layout(workspace, n_src_items, Q, prm->mode);
     if (!workspace || workspace_bytes < w.total) {
         f4l_set_error("f4l_fine_matching: workspace too small (%zu < %zu)", workspace_bytes, w.total);
@@ -601,7 +628,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
                                                         bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T,
                                                         bf->rmse, w.dense_off, w.t2s_off, Q, *prm,
                                                         bf->d_median_resolution, bf->dense, bf->tgt2src, w.nn,
-                                                        w.sparse_cnt);
+                                                        w.sparse_cnt, bf->n_peers, peers);
     f4l_mark("k_sparse_offsets", st);
     k_sparse_offsets<<<1, 1024, 0, st>>>(w.sparse_cnt, Q, w.sparse_off, bf->counts);
     f4l_mark("k_emit_sparse", st);

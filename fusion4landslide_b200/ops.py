@@ -299,9 +299,11 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
                   num_min_matches_for_quality_check=10, thres_dist_diff=0.5, thres_inlier_ratio=0.15,
                   num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
                   output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
-                  d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None):
+                  d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None,
+                  peer_dense=None):
     """Fused fine-matching stage of one tile (f4l_fine_matching).  n_*_items = sp_ptr[-1], tp_ptr[-1]
-    (pass them to avoid a device->host read)."""
+    (pass them to avoid a device->host read).  peer_dense: device pointers (ints) of the slot of `out.dense`
+    in every peer GPU's exchange buffer (exchange.PeerExchange); the D5 kernel stores each dense row there too."""
     dev = src_pts.device
     Q = sp_ptr.numel() - 1
     if n_src_items is None:
@@ -338,6 +340,12 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
         ptr(r.T), ptr(r.T64), ptr(r.status), ptr(r.K), ptr(r.fitness), ptr(r.rmse), ptr(r.iters),
         ptr(r.ratio_inlier), ptr(r.dist_mean), ptr(r.dense), ptr(r.sparse),
         ptr(r.tgt2src, F32, True), ptr(r.counts))
+    if peer_dense:
+        if len(peer_dense) > _lib.MAX_PEERS:
+            raise _lib.F4LError("at most %d peers" % _lib.MAX_PEERS)
+        bf.n_peers = len(peer_dense)
+        for i, pp in enumerate(peer_dense):
+            bf.peer_dense[i] = int(pp)
     nbytes = lib().f4l_fine_matching_workspace_bytes(n_src_items, n_tgt_items, Q, _MODES[mode])
     ws = _workspace(nbytes, dev)
     import ctypes

@@ -60,15 +60,15 @@ def prepare_tile(src, tgt, label_src, label_tgt, corr3d, corr2d=None, min_pts=10
     return t
 
 
-def displacement_field(tile, cfg=None, out=None, med_out=None):
+def displacement_field(tile, cfg=None, out=None, med_out=None, peer_dense=None):
     """The hot path on one tile, device -> device, no host synchronisation.
-    Returns (FineResult, median_resolution device scalar)."""
+    Returns (FineResult, median_resolution device scalar).  peer_dense: see ops.fine_matching."""
     cfg = cfg or FineConfig()
     med = ops.median_resolution(tile.src, tile.tgt, out=med_out)                          # A1
     r = ops.fine_matching(tile.src, tile.tgt, tile.sp_idx, tile.sp_ptr, tile.tp_idx, tile.tp_ptr,
                           tile.tgt_patch_of_point, tile.pair_tgt_patch, corr3d=tile.corr3d,
                           corr2d=tile.corr2d, d_median_resolution=med, n_src_items=tile.n_src_items,
-                          n_tgt_items=tile.n_tgt_items, out=out, **cfg.fine_kwargs())
+                          n_tgt_items=tile.n_tgt_items, out=out, peer_dense=peer_dense, **cfg.fine_kwargs())
     return r, med
 
 
@@ -78,16 +78,19 @@ def make_streams(n, device):
     return [torch.cuda.Stream(device=device) for _ in range(max(1, int(n)))]
 
 
-def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None):
+def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None):
     """The hot path over many tiles.  With `streams`, tile i runs on streams[i % n]: the small kernels and the
     tail of one tile's patch loop overlap with the next tile's work.  The caller's current stream waits for all
-    of them at the end, so events recorded around this call time the whole batch."""
+    of them at the end, so events recorded around this call time the whole batch.  `peers[i]`: peer pointers
+    of tile i's dense slot (exchange.PeerExchange.peer_ptrs) -- the dense rows then land in every GPU's
+    gathered field while the tile is computed."""
     cfg = cfg or FineConfig()
     res = []
     if not streams or len(streams) == 1 and streams[0] is None:
         for i, t in enumerate(tiles):
             res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
-                                          med_out=None if meds is None else meds[i:i + 1]))
+                                          med_out=None if meds is None else meds[i:i + 1],
+                                          peer_dense=None if peers is None else peers[i]))
         return res
     cur = torch.cuda.current_stream(tiles[0].src.device) if tiles else None
     for s in streams:
@@ -95,7 +98,8 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
     for i, t in enumerate(tiles):
         with torch.cuda.stream(streams[i % len(streams)]):
             res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
-                                          med_out=None if meds is None else meds[i:i + 1]))
+                                          med_out=None if meds is None else meds[i:i + 1],
+                                          peer_dense=None if peers is None else peers[i]))
     for s in streams:
         cur.wait_stream(s)
     return res

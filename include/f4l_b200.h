@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define F4L_ABI_VERSION 1
+#define F4L_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define F4L_API __attribute__((visibility("default")))
@@ -171,6 +171,7 @@ F4L_API int f4l_patch_icp(const float* src, const int32_t* src_idx, const int32_
  *   F2 select correspondences of each pair, F3 rigidity check, D2 Procrustes, E1 ICP on the
  *   matched points, D5 apply to all src patch points (+ inverse for tgt2src), A4 assign_then_nn.
  * See f4l_fine_params and the buffer list below. */
+#define F4L_MAX_PEERS 7
 typedef struct f4l_fine_params {
     int32_t mode;                 /* 0 only_3d, 1 only_2d, 2 fusion (3D rows then 2D rows) */
     int32_t remove_low_quality;   /* method.remove_low_quality_patch_matches */
@@ -212,6 +213,12 @@ typedef struct f4l_fine_buffers {
     float* sparse;         /* (2*sum n_s, 6) */
     float* tgt2src;        /* (sum n_t, 6) or NULL */
     int32_t* counts;       /* (4): dense rows, sparse rows, tgt2src rows, fitted pairs */
+    /* multi-GPU exchange fused into the D5 kernel: every dense row is also stored, with the
+       same row offset, into the buffers of n_peers other GPUs (peer-mapped device pointers, see
+       f4l_peer_*): the all-gather of the displacement field happens inside the producing kernel over
+       NVLink, tile by tile.  n_peers == 0: no exchange. */
+    int32_t n_peers;
+    float* peer_dense[F4L_MAX_PEERS];
 } f4l_fine_buffers;
 
 F4L_API size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t n_tgt_items, int32_t Q,
@@ -313,6 +320,24 @@ F4L_API int f4l_piecewise_icp(const double* src64, int32_t n_src, const double* 
                       double* dvfs, double* mag, int32_t* counts, double* thr_out, double* cent_src,
                       double* cent_tgt, int32_t* nn_out, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-visible device buffers for the fused displacement-field exchange (the reference
+ * has no multi-GPU path: main_fusion.py:134-148 walks the tiles serially).  One process per GPU:
+ *   f4l_peer_alloc   cudaMalloc on the current device + export a 64-byte CUDA IPC handle
+ *   f4l_peer_open    map another process's buffer (handle received out of band, e.g. all_gather)
+ *                    into this process; the pointer is usable by kernels on the current device
+ *   f4l_peer_close   unmap a pointer obtained from f4l_peer_open
+ *   f4l_peer_free    free a buffer obtained from f4l_peer_alloc (after every peer closed it)
+ *   f4l_peer_enable_access   same-process multi-device use: let the current device store into
+ *                    memory of `peer_device` (cudaDeviceEnablePeerAccess; already-enabled is ok)
+ * All are host-synchronous set-up calls, never on the per-step path. */
+#define F4L_PEER_HANDLE_BYTES 64
+F4L_API int f4l_peer_alloc(size_t bytes, void** d_ptr, unsigned char* h_handle /* 64 bytes */);
+F4L_API int f4l_peer_open(const unsigned char* h_handle, void** d_ptr);
+F4L_API int f4l_peer_close(void* d_ptr);
+F4L_API int f4l_peer_free(void* d_ptr);
+F4L_API int f4l_peer_enable_access(int32_t peer_device);
 
 #ifdef __cplusplus
 }

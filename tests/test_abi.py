@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert not untyped, untyped
     extra = [n for n in _lib.SIGNATURES if n not in names]
     assert not extra, extra
-    assert L.f4l_abi_version() == 1
+    assert L.f4l_abi_version() == 2
     assert L.f4l_launch_count() >= 0
 
 

@@ -1,0 +1,72 @@
+"""Fused displacement-field exchange: the D5 kernel stores every dense row into the peers'
+fields as well.  On a one-GPU box the "peers" are two more buffers on the same device (same code path in
+the kernel, bit-exact copies expected); with >= 2 GPUs the buffers live on the other device (P2P stores in
+one process) and, separately, in another process (CUDA IPC, the PeerExchange class bench.py uses)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tile(dev, n=30_000, seed=11):
+    from fusion4landslide_b200 import pipeline, synth
+    d = synth.make_tile(n, seed=seed, patch_pts=200)
+    return pipeline.prepare_tile(d["src"].to(dev), d["tgt"].to(dev), d["label_src"].to(dev), d["label_tgt"].to(dev),
+                                 d["corr3d"].to(dev))
+
+
+def test_peer_buffer_alloc_alias_free(cuda):
+    import ctypes
+    from fusion4landslide_b200 import _lib, exchange
+    p, handle, t = exchange.alloc_peer_buffer(4096, cuda)
+    assert len(handle) == _lib.PEER_HANDLE_BYTES and t.numel() == 4096 and t.data_ptr() == p
+    t.fill_(7)
+    torch.cuda.synchronize()
+    assert int(t.sum()) == 7 * 4096
+    del t
+    _lib.check(_lib.lib().f4l_peer_free(ctypes.c_void_p(p)), "f4l_peer_free")
+
+
+def test_fused_push_equals_local_rows_same_device(cuda):
+    from fusion4landslide_b200 import pipeline
+    tile = _tile(cuda)
+    off = 37                                             # odd row offset: 8-byte aligned slots only
+    peers = [torch.full((tile.n_src_items + off + 5, 6), -7.0, device=cuda) for _ in range(2)]
+    ptrs = [p.data_ptr() + off * 24 for p in peers]
+    r, _ = pipeline.displacement_field(tile, peer_dense=ptrs)
+    r0, _ = pipeline.displacement_field(tile)            # no peers: same local rows
+    torch.cuda.synchronize()
+    n = int(r.counts[0])
+    assert n > 0 and torch.equal(r.dense[:n], r0.dense[:n])
+    for p in peers:
+        assert torch.equal(p[off:off + n], r.dense[:n])
+        assert bool((p[:off] == -7.0).all()) and bool((p[off + n:] == -7.0).all())      # nothing outside the slot
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_push_to_other_device_one_process(cuda):
+    from fusion4landslide_b200 import _lib, pipeline
+    with torch.cuda.device(0):
+        _lib.check(_lib.lib().f4l_peer_enable_access(1), "f4l_peer_enable_access")
+    tile = _tile(cuda)
+    remote = torch.zeros((tile.n_src_items, 6), device="cuda:1")
+    torch.cuda.synchronize(1)
+    r, _ = pipeline.displacement_field(tile, peer_dense=[remote.data_ptr()])
+    torch.cuda.synchronize(0)
+    n = int(r.counts[0])
+    assert n > 0 and torch.equal(remote[:n].to(cuda), r.dense[:n])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_exchange_two_processes():
+    """torchrun x2: every rank's field must hold both ranks' dense rows (tools/check_exchange.py)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "check_exchange.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "exchange ok" in out.stdout
