@@ -10,6 +10,7 @@
 // No host round trip happens between the stages: per-pair decisions (quality reject, too few
 // matches) are status bytes consumed by the later kernels, row counts are device scalars.
 #include "icp_warp.cuh"
+#include "patch_grid.cuh"
 
 #define FINE_MODE_3D 0
 #define FINE_MODE_2D 1
@@ -317,8 +318,9 @@ struct PeerDense { float* p[F4L_MAX_PEERS]; };
 #define AA_SMEM_PTS 2048
 
 // D5 + A4.  CTA per pair.  The target patch is staged in shared memory as pivot-local float4 (|coordinate|
-// of a patch is metres, so f32 keeps ~1e-7 m); every source point is transformed, written to the dense DVF
-// and scanned against the staged targets in f32 keeping the two smallest distances.  When the two are
+// of a patch is metres, so f32 keeps ~1e-7 m), binned on a small uniform grid (patch_grid.cuh: counting sort
+// in shared memory, three passes over the patch's targets); every source point is transformed, written to the
+// dense DVF and looks for its two nearest targets in f32, ring by ring of grid cells.  When the two are
 // separated by more than the f32 error bound the f32 argmin IS the fp64 argmin and only that one distance
 // is re-evaluated in fp64 from the original coordinates (threshold test d^2 < thr^2 of base.py:82 stays
 // exact); otherwise the point takes the exact fp64 scan (first minimal index).
@@ -338,6 +340,8 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
     __shared__ __align__(16) float srow[AA_THREADS * 6];
     __shared__ int s_cnt;
     __shared__ unsigned s_maxabs;
+    __shared__ unsigned s_bb[6];
+    __shared__ int s_start[260], s_fill[256], s_wsum[AA_THREADS / 32];
     const int tid = threadIdx.x;
     for (int q = blockIdx.x; q < Q; q += gridDim.x) {
         __syncthreads();
@@ -357,6 +361,7 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
         const bool assign_nn = prm.assign_type == 1;
         const bool staged = nt <= AA_SMEM_PTS;
         if (tid == 0) { s_cnt = 0; s_maxabs = 0u; }
+        if (tid < 6) s_bb[tid] = tid < 3 ? 0xffffffffu : 0u;
         double cB[3] = {0, 0, 0};
         if (nt > 0) {
             float x, y, z;
@@ -364,14 +369,20 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             cB[0] = x; cB[1] = y; cB[2] = z;
         }
         __syncthreads();
-        if ((assign_nn && staged) || prm.output_tgt2src) {
+        const bool binned = assign_nn && staged && nt > 0;
+        if (binned || prm.output_tgt2src) {
+            // pass 1 over the targets: bounding box + largest |coordinate| in the pivot-local frame (and the
+            // inverse rows, which need every target once anyway)
             float mabs = 0.f;
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
             for (int j = tid; j < nt; j += AA_THREADS) {
                 float x, y, z;
                 load_ptf(tgt_pts, tp_idx, t0 + j, x, y, z);
-                if (assign_nn && staged) {
+                if (binned) {
                     const float lx = (float)((double)x - cB[0]), ly = (float)((double)y - cB[1]), lz = (float)((double)z - cB[2]);
-                    sref[j] = make_float4(lx, ly, lz, 0.f);
+                    mn[0] = fminf(mn[0], lx); mx[0] = fmaxf(mx[0], lx);
+                    mn[1] = fminf(mn[1], ly); mx[1] = fmaxf(mx[1], ly);
+                    mn[2] = fminf(mn[2], lz); mx[2] = fmaxf(mx[2], lz);
                     mabs = fmaxf(mabs, fmaxf(fabsf(lx), fmaxf(fabsf(ly), fabsf(lz))));
                 }
                 if (prm.output_tgt2src) {
@@ -383,9 +394,67 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                     row[2] = make_float2(y, z);
                 }
             }
+            if (binned) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(F4L_FULL, mabs, o));
-            if ((tid & 31) == 0) atomicMax(&s_maxabs, __float_as_uint(mabs));
+                for (int o = 16; o > 0; o >>= 1) {
+                    mabs = fmaxf(mabs, __shfl_xor_sync(F4L_FULL, mabs, o));
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        mn[a] = fminf(mn[a], __shfl_xor_sync(F4L_FULL, mn[a], o));
+                        mx[a] = fmaxf(mx[a], __shfl_xor_sync(F4L_FULL, mx[a], o));
+                    }
+                }
+                if ((tid & 31) == 0) {
+                    atomicMax(&s_maxabs, __float_as_uint(mabs));
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        atomicMin(&s_bb[a], f2ord(mn[a]));
+                        atomicMax(&s_bb[3 + a], f2ord(mx[a]));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        PatchGrid grid;
+        if (binned) {
+            // pass 2: cell histogram;  scan;  pass 3: counting-sort scatter into sref (x fastest cell order)
+            const float bmn[3] = {ord2f(s_bb[0]), ord2f(s_bb[1]), ord2f(s_bb[2])};
+            const float bmx[3] = {ord2f(s_bb[3]), ord2f(s_bb[4]), ord2f(s_bb[5])};
+            grid = make_patch_grid(bmn, bmx, nt, 16);
+            const int ncells = grid.ncu * grid.ncv;
+            s_fill[tid] = 0;
+            __syncthreads();
+            for (int j = tid; j < nt; j += AA_THREADS) {
+                float x, y, z;
+                load_ptf(tgt_pts, tp_idx, t0 + j, x, y, z);
+                atomicAdd(&s_fill[pg_cell(grid, (float)((double)x - cB[0]), (float)((double)y - cB[1]), (float)((double)z - cB[2]))], 1);
+            }
+            __syncthreads();
+            const int cnt = s_fill[tid];
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(F4L_FULL, inc, o);
+                if ((tid & 31) >= o) inc += v;
+            }
+            if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+            __syncthreads();
+            int before = 0;
+#pragma unroll
+            for (int w = 0; w < AA_THREADS / 32; ++w) before += (w < (tid >> 5)) ? s_wsum[w] : 0;
+            const int excl = before + inc - cnt;
+            s_start[tid] = excl;
+            s_fill[tid] = excl;
+            if (tid == 0) s_start[256] = nt;
+            __syncthreads();
+            for (int j = tid; j < nt; j += AA_THREADS) {
+                float x, y, z;
+                load_ptf(tgt_pts, tp_idx, t0 + j, x, y, z);
+                const float lx = (float)((double)x - cB[0]), ly = (float)((double)y - cB[1]), lz = (float)((double)z - cB[2]);
+                const int pos = atomicAdd(&s_fill[pg_cell(grid, lx, ly, lz)], 1);
+                sref[pos] = make_float4(lx, ly, lz, __int_as_float(j));
+            }
+            (void)ncells;
         }
         __syncthreads();
         const float maxabs_t = __uint_as_float(s_maxabs);
@@ -415,23 +484,16 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                 bool exact_scan = !staged;
                 if (staged && nt > 0) {
                     const float qx = (float)((double)mx - cB[0]), qy = (float)((double)my - cB[1]), qz = (float)((double)mz - cB[2]);
-                    float d1 = INFINITY, d2 = INFINITY;
-                    int j1 = 0;
-#pragma unroll 4
-                    for (int j = 0; j < nt; ++j) {
-                        const float4 b = sref[j];
-                        const float dx = qx - b.x, dy = qy - b.y, dz = qz - b.z;
-                        const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        const bool better = dd < d1;
-                        d2 = better ? d1 : fminf(d2, dd);
-                        j1 = better ? j : j1;
-                        d1 = better ? dd : d1;
-                    }
                     // |sqrt(dd) - true distance| <= eta for every candidate (coordinate rounding + f32 arithmetic)
                     const float mabs = fmaxf(maxabs_t, fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz))));
-                    const float eta = 1e-6f * (mabs + sqrtf(d2));
-                    const float r1 = sqrtf(d1);
-                    if (d2 > d1 + 4.f * eta * r1 + 4.f * eta * eta && d2 > d1) {
+                    auto certain = [mabs](float a1, float a2) {
+                        const float eta = 1e-6f * (mabs + sqrtf(a2));
+                        const float r1 = sqrtf(a1);
+                        return a2 > a1 + 4.f * eta * r1 + 4.f * eta * eta && a2 > a1;
+                    };
+                    float d1, d2;
+                    int j1;
+                    if (pg_top2(grid, sref, s_start, qx, qy, qz, certain, d1, j1, d2)) {
                         float gx, gy, gz;
                         load_ptf(tgt_pts, tp_idx, t0 + j1, gx, gy, gz);
                         const double dx = (double)mx - (double)gx, dy = (double)my - (double)gy, dz = (double)mz - (double)gz;

@@ -143,42 +143,47 @@ k_bin_scatter_advance(const float* __restrict__ p, int n, const int* __restrict_
 }
 
 // ---- search --------------------------------------------------------------------------------
+// The k best candidates are kept as 64-bit keys (bits(d^2) << 32 | original index): squared distances are
+// non-negative floats, whose bit patterns order like unsigned integers, so ONE unsigned 64-bit compare is the
+// lexicographic (distance, index) order -- deterministic under any visiting order, ties towards the lower
+// index -- and an insertion is a branch-free min/max chain.
+typedef unsigned long long u64;
+#define KNN_KEY_NONE 0x7f800000ffffffffull      // (inf, -1)
+
 template <int K>
 struct TopK {
-    float d[K];
-    int i[K];
+    u64 v[K];
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int a = 0; a < K; ++a) { d[a] = INFINITY; i[a] = -1; }
+        for (int a = 0; a < K; ++a) v[a] = KNN_KEY_NONE;
     }
-    __device__ __forceinline__ void push(float dd, int ii) {
-        // lexicographic (d, idx) ordering -> deterministic under any visiting order
-        if (dd > d[K - 1] || (dd == d[K - 1] && (ii > i[K - 1] && i[K - 1] >= 0))) return;
-        d[K - 1] = dd;
-        i[K - 1] = ii;
+    __device__ __forceinline__ void push(u64 key) {
 #pragma unroll
-        for (int a = K - 1; a > 0; --a) {
-            bool sw = d[a] < d[a - 1] || (d[a] == d[a - 1] && i[a] < i[a - 1]);
-            if (sw) {
-                float td = d[a]; d[a] = d[a - 1]; d[a - 1] = td;
-                int ti = i[a]; i[a] = i[a - 1]; i[a - 1] = ti;
-            }
+        for (int a = 0; a < K; ++a) {
+            const u64 lo = key < v[a] ? key : v[a];
+            key = key < v[a] ? v[a] : key;
+            v[a] = lo;
         }
     }
+    __device__ __forceinline__ float d(int a) const { return __uint_as_float((unsigned)(v[a] >> 32)); }
+    __device__ __forceinline__ int i(int a) const { return (int)(unsigned)(v[a] & 0xffffffffull); }
 };
 
 template <int K>
 __device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, int b, int e, float qx,
                                            float qy, float qz, TopK<K>& tk) {
     for (int j = b; j < e; ++j) {
-        float4 c = __ldg(sorted + j);
-        float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-        float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        tk.push(dd, __float_as_int(c.w));
+        const float4 c = __ldg(sorted + j);
+        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+        const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        tk.push(((u64)__float_as_uint(dd) << 32) | (u64)__float_as_uint(c.w));
     }
 }
 
-template <int K>
+// MODE 0: (idx, d2)[N,k] in the callers' query order.  MODE 1 (median resolution, A1): only the k-th squared
+// distance of every query, in CELL order (out_d2[t]) -- the consumer is a rank select, which does not care
+// about the order, so the 4 B results are written coalesced instead of 8k B scattered.
+template <int K, int MODE>
 __global__ void __launch_bounds__(128)
 k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __restrict__ sorted,
               const int* __restrict__ cell_start, const GridParams* __restrict__ gp, int k, float max_r2,
@@ -192,8 +197,10 @@ k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __
     cell_of(g, q.x, q.y, q.z, cx, cy, cz);
     TopK<K> tk;
     tk.init();
+    const int kk = K < k ? K : k;
     const int maxR = max(g.nx, max(g.ny, g.nz));
-    for (int R = 0; R <= maxR; ++R) {
+    // ring 1 is the whole 3 x 3 (x 3) block: one contiguous range per grid row
+    for (int R = 1; R <= maxR; ++R) {
         const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
         const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
         const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
@@ -202,7 +209,7 @@ k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __
             for (int y = y0; y <= y1; ++y) {
                 const bool shell = zshell || (y == cy - R) || (y == cy + R);
                 const int row = (z * g.ny + y) * g.nx;
-                if (shell || R == 0) {
+                if (shell || R == 1) {
                     scan_range<K>(sorted, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1), q.x, q.y, q.z, tk);
                 } else {
                     if (cx - R >= 0)
@@ -225,16 +232,33 @@ k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __
         // conservative (cell borders are computed in f32): shrink the margin by a few ulps
         margin = fmaxf(margin - 4e-7f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + g.cell), 0.f);
         const float m2 = margin * margin;
-        const float kth = tk.d[K - 1 < k - 1 ? K - 1 : k - 1];
-        if (kth < m2 || m2 >= max_r2) break;
+        if (tk.d(kk - 1) < m2 || m2 >= max_r2) break;
     }
-    for (int a = 0; a < k; ++a) {
-        float dd = a < K ? tk.d[a] : INFINITY;
-        int ii = a < K ? tk.i[a] : -1;
-        if (!(dd < max_r2)) { dd = INFINITY; ii = -1; }
-        out_idx[(size_t)qi * k + a] = ii;
-        out_d2[(size_t)qi * k + a] = dd;
+    if (MODE == 1) {
+        const float dd = tk.d(kk - 1);
+        out_d2[t] = dd < max_r2 ? dd : INFINITY;
+        return;
     }
+    if (K == 2 && k == 2) {                 // the common pair: one 8-byte store per array
+        float d0 = tk.d(0), d1 = tk.d(1);
+        int i0 = tk.i(0), i1 = tk.i(1);
+        if (!(d0 < max_r2)) { d0 = INFINITY; i0 = -1; }
+        if (!(d1 < max_r2)) { d1 = INFINITY; i1 = -1; }
+        reinterpret_cast<int2*>(out_idx)[qi] = make_int2(i0, i1);
+        reinterpret_cast<float2*>(out_d2)[qi] = make_float2(d0, d1);
+        return;
+    }
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        if (a < k) {
+            float dd = tk.d(a);
+            int ii = tk.i(a);
+            if (!(dd < max_r2)) { dd = INFINITY; ii = -1; }
+            out_idx[(size_t)qi * k + a] = ii;
+            out_d2[(size_t)qi * k + a] = dd;
+        }
+    }
+    for (int a = K; a < k; ++a) { out_idx[(size_t)qi * k + a] = -1; out_d2[(size_t)qi * k + a] = INFINITY; }
 }
 
 __global__ void k_fill_none(int n, int k, int* idx, float* d2) {
@@ -245,7 +269,7 @@ __global__ void k_fill_none(int n, int k, int* idx, float* d2) {
 // ---- workspace layout ------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline int knn_max_cells(int M) {
-    long long c = 2LL * (long long)M + 4096;
+    long long c = (long long)M / 2 + 4096;      // auto cell size: ~M/4 cells on surface-like clouds
     if (c > (1LL << 27)) c = 1LL << 27;
     return (int)c;
 }
@@ -306,20 +330,11 @@ static int bin_points(const float* p, int n, const KnnWs& w, int mc, float4* sor
     return f4l_check_launch("f4l_knn_grid/bin");
 }
 
-extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
-                            float cell, int32_t* idx, float* d2, void* workspace, size_t workspace_bytes,
-                            void* stream) {
-    F4L_REQUIRE(N >= 0 && M >= 0, "negative size");
-    F4L_REQUIRE(k >= 1 && k <= 8, "k must be in [1,8]");
-    if (N == 0) return F4L_OK;
-    F4L_REQUIRE(q && idx && d2, "null pointer");
+// mode 0: f4l_knn_grid.  mode 1: only the k-th squared distance per query, in cell order, into d2 (N floats).
+static int knn_grid_impl(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
+                         float cell, int32_t* idx, float* d2, void* workspace, size_t workspace_bytes,
+                         void* stream, int mode) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (M == 0) {
-        f4l_mark("k_fill_none", st);
-        k_fill_none<<<f4l_div_up((long long)N * k, 256), 256, 0, st>>>(N, k, idx, d2);
-        return f4l_finish("f4l_knn_grid/fill", stream);
-    }
-    F4L_REQUIRE(r && workspace, "null pointer");
     KnnWs w = knn_layout(workspace, N, M);
     if (workspace_bytes < w.total) {
         f4l_set_error("f4l_knn_grid: workspace too small (%zu < %zu)", workspace_bytes, w.total);
@@ -355,11 +370,37 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
     const float max_r2 = max_radius > 0.f ? max_radius * max_radius : INFINITY;
     const int blocks = f4l_div_up(N, 128);
     f4l_mark("k_grid_search", st);
-    if (k == 1) k_grid_search<1><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
-    else if (k == 2) k_grid_search<2><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
-    else if (k <= 4) k_grid_search<4><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
-    else k_grid_search<8><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2);
+#define KNN_LAUNCH(KK, MM) k_grid_search<KK, MM><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2)
+    if (mode == 1) {
+        if (k == 1) KNN_LAUNCH(1, 1);
+        else if (k == 2) KNN_LAUNCH(2, 1);
+        else if (k <= 4) KNN_LAUNCH(4, 1);
+        else KNN_LAUNCH(8, 1);
+    } else {
+        if (k == 1) KNN_LAUNCH(1, 0);
+        else if (k == 2) KNN_LAUNCH(2, 0);
+        else if (k <= 4) KNN_LAUNCH(4, 0);
+        else KNN_LAUNCH(8, 0);
+    }
+#undef KNN_LAUNCH
     return f4l_finish("f4l_knn_grid/search", stream);
+}
+
+extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
+                            float cell, int32_t* idx, float* d2, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    F4L_REQUIRE(N >= 0 && M >= 0, "negative size");
+    F4L_REQUIRE(k >= 1 && k <= 8, "k must be in [1,8]");
+    if (N == 0) return F4L_OK;
+    F4L_REQUIRE(q && idx && d2, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        f4l_mark("k_fill_none", st);
+        k_fill_none<<<f4l_div_up((long long)N * k, 256), 256, 0, st>>>(N, k, idx, d2);
+        return f4l_finish("f4l_knn_grid/fill", stream);
+    }
+    F4L_REQUIRE(r && workspace, "null pointer");
+    return knn_grid_impl(q, N, r, M, k, max_radius, cell, idx, d2, workspace, workspace_bytes, stream, 0);
 }
 
 // ---- radix select (k-th smallest) -------------------------------------------------------------
@@ -510,10 +551,11 @@ extern "C" int f4l_median_resolution(const float* src, int32_t n_src, const floa
     for (int e = 0; e < 2; ++e) {
         const float* p = e ? tgt : src;
         const int m = e ? n_tgt : n_src;
-        int rc = f4l_knn_grid(p, m, p, m, 2, 0.f, 0.f, idx, d2, knn_ws, knn_bytes, stream);
+        // squared distance to the nearest OTHER point (k = 2 self query), in cell order
+        int rc = knn_grid_impl(p, m, p, m, 2, 0.f, 0.f, idx, d2, knn_ws, knn_bytes, stream, 1);
         if (rc) return rc;
         // np.median: mean of elements (m-1)/2 and m/2 of the sorted 2nd-neighbour distances
-        rc = f4l_select_kth(d2, m, 2, 1, (m - 1) / 2, m / 2, sel, sel_ws, sel_bytes, stream);
+        rc = f4l_select_kth(d2, m, 1, 0, (m - 1) / 2, m / 2, sel, sel_ws, sel_bytes, stream);
         if (rc) return rc;
         f4l_mark("k_medres_finish", (cudaStream_t)stream);
         k_medres_finish<<<1, 1, 0, (cudaStream_t)stream>>>(sel, out, e);

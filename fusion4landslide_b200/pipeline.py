@@ -6,6 +6,8 @@ is the path: A1 median resolution (k=2 self-kNN on both epochs) + the fused fine
 `displacement_field_host` is the same call for a caller that holds HOST buffers (pinned):
 host->device copies of the inputs and device->host copies of the results are part of the call.
 """
+import os
+
 import torch
 
 from . import ops, synth
@@ -95,11 +97,26 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
     cur = torch.cuda.current_stream(tiles[0].src.device) if tiles else None
     for s in streams:
         s.wait_stream(cur)
-    for i, t in enumerate(tiles):
-        with torch.cuda.stream(streams[i % len(streams)]):
-            res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
-                                          med_out=None if meds is None else meds[i:i + 1],
-                                          peer_dense=None if peers is None else peers[i]))
+    if os.environ.get("F4L_TILE_ORDER", "") == "phased":
+        # experiment: every tile's A1 chain first, then every tile's fine matching (same stream per tile)
+        med_l = []
+        for i, t in enumerate(tiles):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                med_l.append(ops.median_resolution(t.src, t.tgt, out=None if meds is None else meds[i:i + 1]))
+        for i, t in enumerate(tiles):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                r = ops.fine_matching(t.src, t.tgt, t.sp_idx, t.sp_ptr, t.tp_idx, t.tp_ptr, t.tgt_patch_of_point,
+                                      t.pair_tgt_patch, corr3d=t.corr3d, corr2d=t.corr2d, d_median_resolution=med_l[i],
+                                      n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items,
+                                      out=None if outs is None else outs[i],
+                                      peer_dense=None if peers is None else peers[i], **cfg.fine_kwargs())
+                res.append((r, med_l[i]))
+    else:
+        for i, t in enumerate(tiles):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
+                                              med_out=None if meds is None else meds[i:i + 1],
+                                              peer_dense=None if peers is None else peers[i]))
     for s in streams:
         cur.wait_stream(s)
     return res
