@@ -143,10 +143,13 @@ def algorithmic_bytes(name, q):
     N, M, P = q["n_src"], q["n_tgt"], q["pairs"]
     ns, nt, K = q["src_items"], q["tgt_items"], q["matched"]
     table = {
-        # sorted float4 refs once + sorted float4 queries once + k=2 (idx i32 + d2 f32) out; per epoch call
-        "k_grid_search": 16 * N + 16 * N + 8 * 2 * N,
-        "k_bin_count": 12 * N + 4 * N,
-        "k_bin_scatter": 12 * N + 4 * N + 16 * N,
+        # A1 (medres.cu) handles BOTH epochs per launch.  search: every float4 row once as reference and once as
+        # query (12N + 12M + 8kN with N = M per epoch, k = 2 -> 40 B/point; the kernel moves 16 + 4)
+        "k_a1_search": 40 * (N + M),
+        "k_a1_bbox": 12 * (N + M),
+        "k_a1_count": 12 * (N + M),
+        "k_a1_scatter": (12 + 16) * (N + M),
+        "k_a1_select": 4 * (N + M),
         # corr col1 (8 B) + labels (4 B) + point index (4 B) per src patch item, 8 B per selected pair
         "k_select_corr": 16 * ns + 8 * K,
         # matched pairs: 8 B indices + 24 B coordinates, outputs 64+128+... per pair
@@ -430,7 +433,8 @@ def run_b200(a):
                             "same step; this kernel is FP/issue-bound (K^2 rigidity + the on-chip ICP loop: ncu DRAM < 1 % of "
                             "peak, issue slots ~50 %), so its HBM fraction is small by construction -- see DESIGN.md section 4"}
         # also report the two kernels the north star names (kNN search, Kabsch/ICP reduction)
-        for name in ("k_grid_search", "k_patch_fit_warp", "k_patch_fit", "k_apply_assign"):
+        for name in ("k_a1_search", "k_a1_scatter", "k_a1_count", "k_a1_bbox", "k_patch_fit_warp", "k_patch_fit",
+                     "k_apply_assign"):
             if name in kernel_table:
                 b = algorithmic_bytes(name, q)
                 kernel_table[name]["hbm_frac"] = b / (kernel_table[name]["ms_avg"] * 1e-3) / 1e9 / peak

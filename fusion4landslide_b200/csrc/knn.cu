@@ -13,16 +13,7 @@
 // distance are broken towards the lower original index, independent of the in-cell order.
 #include <cub/device/device_scan.cuh>
 
-#include "common.cuh"
-
-struct GridParams {
-    float minx, miny, minz;
-    float inv_cell, cell;
-    float inv[3];        // per-axis 1/cell; 0 on a flattened axis (all points fall in layer 0)
-    int nx, ny, nz;
-    int ncells;
-    int pad;
-};
+#include "knn_grid.cuh"
 
 // ---- bounding box ------------------------------------------------------------------------
 __global__ void k_bbox_init(unsigned* bb) {
@@ -64,46 +55,23 @@ __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ p, int n
     }
 }
 
-// one thread: choose the cell size (surface-like data: ~2x the mean spacing on the largest face
-// of the box) and clamp the table to max_cells.
-__global__ void k_grid_params(const unsigned* bb, int m, float cell_in, int max_cells, GridParams* gp) {
-    float mn[3], ex[3];
+__global__ void k_grid_params(const unsigned* bb, int m, float cell_in, float factor, int max_cells, GridParams* gp) {
+    float mn[3], mx[3];
     for (int a = 0; a < 3; ++a) {
         mn[a] = ord2f(bb[a]);
-        ex[a] = fmaxf(ord2f(bb[3 + a]) - mn[a], 0.f);
+        mx[a] = ord2f(bb[3 + a]);
     }
-    float face = fmaxf(ex[0] * ex[1], fmaxf(ex[0] * ex[2], ex[1] * ex[2]));
-    float c = cell_in > 0.f ? cell_in : 2.0f * sqrtf(face / fmaxf((float)m, 1.f));
-    float longest = fmaxf(ex[0], fmaxf(ex[1], ex[2]));
-    if (!(c > 0.f)) c = fmaxf(longest, 1e-3f);
-    c = fmaxf(c, longest * 1e-4f);   // never more than 10^4 cells per axis
-    // surface-like clouds (terrain scans): the thin axis is not binned at all -- a 2D table is 10-50x
-    // smaller (memset / scan / cell lookups) and a query visits 3 row ranges per ring instead of 9.
-    // The ring test below only ever uses binned axes, so the search stays exact.
-    int thin = 0;
-    if (ex[1] < ex[thin]) thin = 1;
-    if (ex[2] < ex[thin]) thin = 2;
-    float mid = INFINITY;
-    for (int a = 0; a < 3; ++a)
-        if (a != thin) mid = fminf(mid, ex[a]);
-    const bool flat = ex[thin] <= 0.25f * mid;
-    int nn[3];
-    for (int it = 0; it < 64; ++it) {
-        for (int a = 0; a < 3; ++a) nn[a] = (flat && a == thin) ? 1 : (int)floorf(ex[a] / c) + 1;
-        if ((long long)nn[0] * nn[1] * nn[2] <= (long long)max_cells) break;
-        c *= 1.2599211f;
-    }
-    gp->minx = mn[0]; gp->miny = mn[1]; gp->minz = mn[2];
-    gp->cell = c; gp->inv_cell = 1.0f / c;
-    for (int a = 0; a < 3; ++a) gp->inv[a] = (flat && a == thin) ? 0.f : 1.0f / c;
-    gp->nx = nn[0]; gp->ny = nn[1]; gp->nz = nn[2];
-    gp->ncells = nn[0] * nn[1] * nn[2];
+    grid_params_compute(mn, mx, m, cell_in, factor, max_cells, gp);
 }
 
-__device__ __forceinline__ void cell_of(const GridParams& g, float x, float y, float z, int& cx, int& cy, int& cz) {
-    cx = min(max((int)floorf((x - g.minx) * g.inv[0]), 0), g.nx - 1);
-    cy = min(max((int)floorf((y - g.miny) * g.inv[1]), 0), g.ny - 1);
-    cz = min(max((int)floorf((z - g.minz) * g.inv[2]), 0), g.nz - 1);
+#include <stdlib.h>
+float f4l_knn_cell_factor() {
+    static const float f = [] {
+        const char* s = getenv("F4L_KNN_CELL_FACTOR");
+        float v = s ? (float)atof(s) : 0.f;
+        return (v >= 0.5f && v <= 8.f) ? v : 1.5f;
+    }();
+    return f;
 }
 
 __global__ void __launch_bounds__(256)
@@ -142,48 +110,9 @@ k_bin_scatter_advance(const float* __restrict__ p, int n, const int* __restrict_
     }
 }
 
-// ---- search --------------------------------------------------------------------------------
-// The k best candidates are kept as 64-bit keys (bits(d^2) << 32 | original index): squared distances are
-// non-negative floats, whose bit patterns order like unsigned integers, so ONE unsigned 64-bit compare is the
-// lexicographic (distance, index) order -- deterministic under any visiting order, ties towards the lower
-// index -- and an insertion is a branch-free min/max chain.
-typedef unsigned long long u64;
-#define KNN_KEY_NONE 0x7f800000ffffffffull      // (inf, -1)
-
+// (idx, d2)[N,k] in the callers' query order.  (The median-resolution variant, which needs only the k-th squared
+// distance of every query, lives in medres.cu.)
 template <int K>
-struct TopK {
-    u64 v[K];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int a = 0; a < K; ++a) v[a] = KNN_KEY_NONE;
-    }
-    __device__ __forceinline__ void push(u64 key) {
-#pragma unroll
-        for (int a = 0; a < K; ++a) {
-            const u64 lo = key < v[a] ? key : v[a];
-            key = key < v[a] ? v[a] : key;
-            v[a] = lo;
-        }
-    }
-    __device__ __forceinline__ float d(int a) const { return __uint_as_float((unsigned)(v[a] >> 32)); }
-    __device__ __forceinline__ int i(int a) const { return (int)(unsigned)(v[a] & 0xffffffffull); }
-};
-
-template <int K>
-__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, int b, int e, float qx,
-                                           float qy, float qz, TopK<K>& tk) {
-    for (int j = b; j < e; ++j) {
-        const float4 c = __ldg(sorted + j);
-        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-        const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        tk.push(((u64)__float_as_uint(dd) << 32) | (u64)__float_as_uint(c.w));
-    }
-}
-
-// MODE 0: (idx, d2)[N,k] in the callers' query order.  MODE 1 (median resolution, A1): only the k-th squared
-// distance of every query, in CELL order (out_d2[t]) -- the consumer is a rank select, which does not care
-// about the order, so the 4 B results are written coalesced instead of 8k B scattered.
-template <int K, int MODE>
 __global__ void __launch_bounds__(128)
 k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __restrict__ sorted,
               const int* __restrict__ cell_start, const GridParams* __restrict__ gp, int k, float max_r2,
@@ -198,47 +127,7 @@ k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __
     TopK<K> tk;
     tk.init();
     const int kk = K < k ? K : k;
-    const int maxR = max(g.nx, max(g.ny, g.nz));
-    // ring 1 is the whole 3 x 3 (x 3) block: one contiguous range per grid row
-    for (int R = 1; R <= maxR; ++R) {
-        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
-        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
-        const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
-        for (int z = z0; z <= z1; ++z) {
-            const bool zshell = (z == cz - R) || (z == cz + R);
-            for (int y = y0; y <= y1; ++y) {
-                const bool shell = zshell || (y == cy - R) || (y == cy + R);
-                const int row = (z * g.ny + y) * g.nx;
-                if (shell || R == 1) {
-                    scan_range<K>(sorted, __ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1), q.x, q.y, q.z, tk);
-                } else {
-                    if (cx - R >= 0)
-                        scan_range<K>(sorted, __ldg(cell_start + row + cx - R), __ldg(cell_start + row + cx - R + 1), q.x, q.y, q.z, tk);
-                    if (cx + R <= g.nx - 1)
-                        scan_range<K>(sorted, __ldg(cell_start + row + cx + R), __ldg(cell_start + row + cx + R + 1), q.x, q.y, q.z, tk);
-                }
-            }
-        }
-        // distance from the query to the border of the searched block (infinite where the block
-        // reaches the grid border: no reference point lies outside the grid's bounding box)
-        float margin = INFINITY;
-        if (cx - R > 0) margin = fminf(margin, q.x - (g.minx + (float)(cx - R) * g.cell));
-        if (cx + R < g.nx - 1) margin = fminf(margin, (g.minx + (float)(cx + R + 1) * g.cell) - q.x);
-        if (cy - R > 0) margin = fminf(margin, q.y - (g.miny + (float)(cy - R) * g.cell));
-        if (cy + R < g.ny - 1) margin = fminf(margin, (g.miny + (float)(cy + R + 1) * g.cell) - q.y);
-        if (cz - R > 0) margin = fminf(margin, q.z - (g.minz + (float)(cz - R) * g.cell));
-        if (cz + R < g.nz - 1) margin = fminf(margin, (g.minz + (float)(cz + R + 1) * g.cell) - q.z);
-        if (margin == INFINITY) break;
-        // conservative (cell borders are computed in f32): shrink the margin by a few ulps
-        margin = fmaxf(margin - 4e-7f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + g.cell), 0.f);
-        const float m2 = margin * margin;
-        if (tk.d(kk - 1) < m2 || m2 >= max_r2) break;
-    }
-    if (MODE == 1) {
-        const float dd = tk.d(kk - 1);
-        out_d2[t] = dd < max_r2 ? dd : INFINITY;
-        return;
-    }
+    grid_ring_search(sorted, cell_start, g, q.x, q.y, q.z, cx, cy, cz, kk, max_r2, tk);
     if (K == 2 && k == 2) {                 // the common pair: one 8-byte store per array
         float d0 = tk.d(0), d1 = tk.d(1);
         int i0 = tk.i(0), i1 = tk.i(1);
@@ -267,13 +156,6 @@ __global__ void k_fill_none(int n, int k, int* idx, float* d2) {
 }
 
 // ---- workspace layout ------------------------------------------------------------------------
-static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-static inline int knn_max_cells(int M) {
-    long long c = (long long)M / 2 + 4096;      // auto cell size: ~M/4 cells on surface-like clouds
-    if (c > (1LL << 27)) c = 1LL << 27;
-    return (int)c;
-}
-
 struct KnnWs {
     GridParams* gp;
     unsigned* bb;
@@ -330,10 +212,9 @@ static int bin_points(const float* p, int n, const KnnWs& w, int mc, float4* sor
     return f4l_check_launch("f4l_knn_grid/bin");
 }
 
-// mode 0: f4l_knn_grid.  mode 1: only the k-th squared distance per query, in cell order, into d2 (N floats).
 static int knn_grid_impl(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
                          float cell, int32_t* idx, float* d2, void* workspace, size_t workspace_bytes,
-                         void* stream, int mode) {
+                         void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KnnWs w = knn_layout(workspace, N, M);
     if (workspace_bytes < w.total) {
@@ -346,7 +227,7 @@ static int knn_grid_impl(const float* q, int32_t N, const float* r, int32_t M, i
     f4l_mark("k_bbox", st);
     k_bbox<<<min(f4l_div_up(M, 256), 148 * 4), 256, 0, st>>>(r, M, w.bb);
     f4l_mark("k_grid_params", st);
-    k_grid_params<<<1, 1, 0, st>>>(w.bb, M, cell, mc, w.gp);
+    k_grid_params<<<1, 1, 0, st>>>(w.bb, M, cell, f4l_knn_cell_factor(), mc, w.gp);
     int rc = bin_points(r, M, w, mc, w.sorted_r, st);
     if (rc) return rc;
     // keep the reference table: the query binning below needs its own counters
@@ -370,18 +251,11 @@ static int knn_grid_impl(const float* q, int32_t N, const float* r, int32_t M, i
     const float max_r2 = max_radius > 0.f ? max_radius * max_radius : INFINITY;
     const int blocks = f4l_div_up(N, 128);
     f4l_mark("k_grid_search", st);
-#define KNN_LAUNCH(KK, MM) k_grid_search<KK, MM><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2)
-    if (mode == 1) {
-        if (k == 1) KNN_LAUNCH(1, 1);
-        else if (k == 2) KNN_LAUNCH(2, 1);
-        else if (k <= 4) KNN_LAUNCH(4, 1);
-        else KNN_LAUNCH(8, 1);
-    } else {
-        if (k == 1) KNN_LAUNCH(1, 0);
-        else if (k == 2) KNN_LAUNCH(2, 0);
-        else if (k <= 4) KNN_LAUNCH(4, 0);
-        else KNN_LAUNCH(8, 0);
-    }
+#define KNN_LAUNCH(KK) k_grid_search<KK><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2)
+    if (k == 1) KNN_LAUNCH(1);
+    else if (k == 2) KNN_LAUNCH(2);
+    else if (k <= 4) KNN_LAUNCH(4);
+    else KNN_LAUNCH(8);
 #undef KNN_LAUNCH
     return f4l_finish("f4l_knn_grid/search", stream);
 }
@@ -400,7 +274,7 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
         return f4l_finish("f4l_knn_grid/fill", stream);
     }
     F4L_REQUIRE(r && workspace, "null pointer");
-    return knn_grid_impl(q, N, r, M, k, max_radius, cell, idx, d2, workspace, workspace_bytes, stream, 0);
+    return knn_grid_impl(q, N, r, M, k, max_radius, cell, idx, d2, workspace, workspace_bytes, stream);
 }
 
 // ---- radix select (k-th smallest) -------------------------------------------------------------
@@ -517,48 +391,3 @@ extern "C" int f4l_select_kth(const float* x, int32_t n, int32_t stride, int32_t
     return f4l_finish("f4l_select_kth", stream);
 }
 
-// ---- A1: median point-cloud resolution ------------------------------------------------------------
-// max over the two epochs of the median distance to the nearest other point
-// (base.py:2716-2754, src/f2s3.py:481-508).  out[0] = resolution (device scalar).
-__global__ void k_medres_finish(const float* sel, float* out, int accumulate) {
-    // sel[0], sel[1]: the two middle squared distances (equal ranks when the count is odd)
-    double m = 0.5 * (sqrt((double)sel[0]) + sqrt((double)sel[1]));
-    float v = (float)m;
-    out[0] = accumulate ? fmaxf(out[0], v) : v;
-}
-
-extern "C" size_t f4l_median_resolution_workspace_bytes(int32_t n_src, int32_t n_tgt) {
-    int n = n_src > n_tgt ? n_src : n_tgt;
-    return f4l_knn_grid_workspace_bytes(n, n) + align_up((size_t)n * 2 * 4) * 2 + f4l_select_kth_workspace_bytes(n) + 256;
-}
-
-extern "C" int f4l_median_resolution(const float* src, int32_t n_src, const float* tgt, int32_t n_tgt, float* out,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
-    F4L_REQUIRE(src && tgt && out && workspace, "null pointer");
-    F4L_REQUIRE(n_src >= 2 && n_tgt >= 2, "need at least 2 points per epoch");
-    if (workspace_bytes < f4l_median_resolution_workspace_bytes(n_src, n_tgt)) {
-        f4l_set_error("f4l_median_resolution: workspace too small");
-        return F4L_E_WORKSPACE;
-    }
-    const int n = n_src > n_tgt ? n_src : n_tgt;
-    char* b = (char*)workspace;
-    size_t off = 0;
-    void* knn_ws = b + off; size_t knn_bytes = f4l_knn_grid_workspace_bytes(n, n); off += align_up(knn_bytes);
-    int32_t* idx = (int32_t*)(b + off); off += align_up((size_t)n * 2 * 4);
-    float* d2 = (float*)(b + off); off += align_up((size_t)n * 2 * 4);
-    void* sel_ws = b + off; size_t sel_bytes = f4l_select_kth_workspace_bytes(n); off += align_up(sel_bytes);
-    float* sel = (float*)(b + off);
-    for (int e = 0; e < 2; ++e) {
-        const float* p = e ? tgt : src;
-        const int m = e ? n_tgt : n_src;
-        // squared distance to the nearest OTHER point (k = 2 self query), in cell order
-        int rc = knn_grid_impl(p, m, p, m, 2, 0.f, 0.f, idx, d2, knn_ws, knn_bytes, stream, 1);
-        if (rc) return rc;
-        // np.median: mean of elements (m-1)/2 and m/2 of the sorted 2nd-neighbour distances
-        rc = f4l_select_kth(d2, m, 1, 0, (m - 1) / 2, m / 2, sel, sel_ws, sel_bytes, stream);
-        if (rc) return rc;
-        f4l_mark("k_medres_finish", (cudaStream_t)stream);
-        k_medres_finish<<<1, 1, 0, (cudaStream_t)stream>>>(sel, out, e);
-    }
-    return f4l_finish("f4l_median_resolution", stream);
-}
