@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libf4l_b200.so")
+LIB_PATH = os.environ.get("F4L_LIB") or os.path.join(_HERE, "libf4l_b200.so")   # F4L_LIB: A/B experiments only
 
 _lib = None
 

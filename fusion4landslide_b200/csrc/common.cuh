@@ -1,5 +1,6 @@
 // Shared device helpers for libf4l_b200 (sm_100a only).
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -97,13 +98,28 @@ __device__ __forceinline__ void seg_bounds(const int32_t* start, const int32_t* 
 // ---- 3x3 SVD, fp64, one-sided Jacobi (Hestenes) ---------------------------------------------
 // H (row-major) = U diag(S) V^T with S descending (torch.svd convention).  U, V row-major.
 // Rank-deficient columns of U are completed to an orthonormal basis.
-__device__ inline void svd3x3(const double H[9], double U[9], double S[3], double V[9]) {
+// warm (optional, 9 doubles, in/out): an orthonormal basis (v[c][r] at warm[c*3+r]) that nearly diagonalises
+// H^T H -- the basis a previous, similar H converged to.  The iteration then starts from a = H warm instead of
+// a = H, and one or two sweeps are enough (an ICP loop fits a slowly changing covariance up to 31 times).  The
+// converged basis is written back.  Any orthonormal start gives the same decomposition up to rounding.
+__device__ inline void svd3x3(const double H[9], double U[9], double S[3], double V[9], double* warm = nullptr) {
     double a[3][3];  // a[c][r]: column c
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) a[c][r] = H[r * 3 + c];
     double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // v[c][r]
+    if (warm) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) v[c][r] = warm[c * 3 + r];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) a[c][r] = H[r * 3 + 0] * v[c][0] + H[r * 3 + 1] * v[c][1] + H[r * 3 + 2] * v[c][2];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) a[c][r] = H[r * 3 + c];
+    }
     // Rotation angles without divisions or square roots on the dependency chain: with a = beta - alpha,
     // b = 2 gamma, r = sqrt(a^2 + b^2) the Hestenes rotation (smaller root of tan 2x = b/a) is
     //   cos 2x = |a|/r,  c = sqrt((1 + cos 2x)/2),  s = sign(a) b / (2 r c)
@@ -138,29 +154,47 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
         }
         if (!rotated) break;
     }
+    if (warm) {
+        __syncwarp();       // a warp may share one slot (all lanes hold the same values): no lane reads after a write
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) warm[c * 3 + r] = v[c][r];
+    }
     double sv[3], n2[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         n2[c] = a[c][0] * a[c][0] + a[c][1] * a[c][1] + a[c][2] * a[c][2];
         sv[c] = n2[c] > 0.0 ? n2[c] * rsqrt(n2[c]) : 0.0;
     }
-    // sort columns by singular value, descending (3-element network)
-    int o0 = 0, o1 = 1, o2 = 2;
-    if (sv[o0] < sv[o1]) { int tmp = o0; o0 = o1; o1 = tmp; }
-    if (sv[o1] < sv[o2]) { int tmp = o1; o1 = o2; o2 = tmp; }
-    if (sv[o0] < sv[o1]) { int tmp = o0; o0 = o1; o1 = tmp; }
-    const int ord[3] = {o0, o1, o2};
+    // sort columns by singular value, descending: a 3-element network of conditional column swaps (selects on
+    // registers -- indexing a[][] / v[][] with a run-time column number would push both arrays, and with them
+    // every rotation of the sweeps above, into local memory)
+#define F4L_SVD_CSWAP(i, j)                                                                  \
+    {                                                                                        \
+        const bool sw = sv[i] < sv[j];                                                       \
+        double tmp;                                                                          \
+        tmp = sv[i]; sv[i] = sw ? sv[j] : tmp; sv[j] = sw ? tmp : sv[j];                     \
+        tmp = n2[i]; n2[i] = sw ? n2[j] : tmp; n2[j] = sw ? tmp : n2[j];                     \
+        _Pragma("unroll") for (int r = 0; r < 3; ++r) {                                      \
+            tmp = a[i][r]; a[i][r] = sw ? a[j][r] : tmp; a[j][r] = sw ? tmp : a[j][r];       \
+            tmp = v[i][r]; v[i][r] = sw ? v[j][r] : tmp; v[j][r] = sw ? tmp : v[j][r];       \
+        }                                                                                    \
+    }
+    F4L_SVD_CSWAP(0, 1)
+    F4L_SVD_CSWAP(1, 2)
+    F4L_SVD_CSWAP(0, 1)
+#undef F4L_SVD_CSWAP
     double u[3][3];
     const double tiny = 1e-300;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const int k = ord[c];
-        S[c] = sv[k];
-        double inv = sv[k] > tiny ? rsqrt(n2[k]) : 0.0;
+        S[c] = sv[c];
+        double inv = sv[c] > tiny ? rsqrt(n2[c]) : 0.0;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            u[c][r] = a[k][r] * inv;
-            V[r * 3 + c] = v[k][r];
+            u[c][r] = a[c][r] * inv;
+            V[r * 3 + c] = v[c][r];
         }
     }
     // complete U for (numerically) zero singular values
@@ -173,11 +207,10 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
         if (!(S[1] > rel)) {
             // any unit vector orthogonal to u0
             int m = 0;
-            if (fabs(u[0][1]) < fabs(u[0][m])) m = 1;
-            if (fabs(u[0][2]) < fabs(u[0][m])) m = 2;
-            double e[3] = {0, 0, 0};
-            e[m] = 1.0;
-            double d = u[0][m];
+            double d = u[0][0];
+            if (fabs(u[0][1]) < fabs(d)) { m = 1; d = u[0][1]; }
+            if (fabs(u[0][2]) < fabs(d)) { m = 2; d = u[0][2]; }
+            const double e[3] = {m == 0 ? 1.0 : 0.0, m == 1 ? 1.0 : 0.0, m == 2 ? 1.0 : 0.0};
             double w0 = e[0] - d * u[0][0], w1 = e[1] - d * u[0][1], w2 = e[2] - d * u[0][2];
             double nrm = rsqrt(w0 * w0 + w1 * w1 + w2 * w2);
             u[1][0] = w0 * nrm; u[1][1] = w1 * nrm; u[1][2] = w2 * nrm;

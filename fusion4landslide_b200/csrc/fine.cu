@@ -154,7 +154,10 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
 // Small pairs (K <= WICP_CAP matched points): the whole fit by ONE warp -- stage the matched pairs
 // in the warp's shared-memory slice, rigidity check, Procrustes, ICP loop (icp_warp.cuh).
 #define FITW_WARPS 4
-__global__ void __launch_bounds__(FITW_WARPS * 32, 4)
+#ifndef FITW_MIN_BLOCKS
+#define FITW_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(FITW_WARPS * 32, FITW_MIN_BLOCKS)
 k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
                  const int32_t* __restrict__ cs, const int32_t* __restrict__ ct,
                  const int32_t* __restrict__ kstart, const int32_t* __restrict__ K, int Q, f4l_fine_params prm,
@@ -169,30 +172,28 @@ k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tg
         const int k0 = kstart[q], k = K[q];
         if (k > WICP_CAP) continue;           // fitted by the CTA kernel
         __syncwarp();
+        DBG_T0
+#ifdef F4L_DEBUG_SCANS
+        const long long dbg_start = dbg_t;
+#endif
         int st = 0;
         double* T64q = T64 + (size_t)q * 16;
         float ra = 0.f, dm = 0.f;
-        if (prm.remove_low_quality && k >= prm.num_min_quality) {
-            for (int i = lane; i < k; i += 32) {
-                float x, y, z;
-                load_ptf(src_pts, cs, k0 + i, x, y, z);
-                sm.A[3 * i] = x; sm.A[3 * i + 1] = y; sm.A[3 * i + 2] = z;
-            }
-            for (int j = lane; j < k; j += 32) {
-                float x, y, z;
-                load_ptf(tgt_pts, ct, k0 + j, x, y, z);
-                sm.Bg[3 * j] = x; sm.Bg[3 * j + 1] = y; sm.Bg[3 * j + 2] = z;
-            }
+        const bool staged = prm.remove_low_quality && k >= prm.num_min_quality;
+        if (staged) {
+            float* arena = reinterpret_cast<float*>(&sm);          // aliases the ICP staging area (filled later)
+            warp_rigidity_stage(arena, src_pts, tgt_pts, cs, ct, k0, k, lane);
             __syncwarp();
             double sum;
             unsigned cnt;
-            warp_rigidity(sm, k, prm.thres_dist_diff, lane, sum, cnt);
+            warp_rigidity(arena, k, prm.thres_dist_diff, lane, sum, cnt);
             const double ne = 0.5 * (double)k * (double)(k - 1);
             dm = (float)(sum / ne);
             ra = (float)((double)(2ull * cnt) / (ne * 2.0));
             if (ra <= prm.thres_inlier_ratio || dm >= prm.thres_dist_diff) st = 1;                   // base.py:3320
             __syncwarp();
         }
+        DBG_T(8)
         if (st == 0 && k < prm.num_min_fine_match) st = 2;                                            // base.py:3338
         if (lane == 0) { ratio_inlier[q] = ra; dist_mean[q] = dm; }
         if (st != 0) {
@@ -206,13 +207,19 @@ k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tg
         }
         // D2: Procrustes (weights None, eps 1e-6)
         double R[9], t[3], Tsvd[16];
-        warp_fit_segment(src_pts, tgt_pts, cs, ct, nullptr, k0, k, 1e-6, 0.f, 0, lane, R, t);
+        __syncwarp();
+        if (lane < 9) sm.Vw[lane] = (lane % 4 == 0) ? 1.0 : 0.0;          // cold start; later fits of this pair start warm
+        __syncwarp();
+        if (staged) warp_fit_arena(reinterpret_cast<const float*>(&sm), k, 1e-6, 0, lane, R, t, sm.Vw);
+        else warp_fit_segment(src_pts, tgt_pts, cs, ct, nullptr, k0, k, 1e-6, 0.f, 0, lane, R, t, sm.Vw);
+        __syncwarp();                  // the arena is dead from here: warp_icp restages over it
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             Tsvd[r * 4 + 0] = R[r * 3 + 0]; Tsvd[r * 4 + 1] = R[r * 3 + 1];
             Tsvd[r * 4 + 2] = R[r * 3 + 2]; Tsvd[r * 4 + 3] = t[r];
         }
         Tsvd[12] = 0; Tsvd[13] = 0; Tsvd[14] = 0; Tsvd[15] = 1;
+        DBG_T(9)
         IcpResult r;
         r.fitness = 0; r.rmse = 0; r.iters = 0;
         if (prm.icp_refine) {
@@ -226,6 +233,9 @@ k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tg
         __syncwarp();
         if (lane < 16) T32[(size_t)q * 16 + lane] = (float)T64q[lane];                                // base.py:3366
         if (lane == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+#ifdef F4L_DEBUG_SCANS
+        if (lane == 0) atomicAdd(&g_dbg[16], (unsigned long long)(clock64() - dbg_start));
+#endif
     }
 }
 
@@ -702,7 +712,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
 
 #ifdef F4L_DEBUG_SCANS
 extern "C" __attribute__((visibility("default"))) void f4l_debug_counters(unsigned long long* h_out, int reset) {
-    cudaMemcpyFromSymbol(h_out, g_dbg, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbg, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(h_out, g_dbg, sizeof(unsigned long long) * 24);
+    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(g_dbg, z, sizeof(z)); }
 }
 #endif

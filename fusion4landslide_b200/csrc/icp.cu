@@ -57,6 +57,9 @@ k_patch_icp_warp(const float* __restrict__ src, const int32_t* __restrict__ src_
         const bool skip = seg_skip && seg_skip[q];
         if (skip || ns < 1 || nt < 1 || ns > WICP_CAP || nt > WICP_CAP) continue;
         __syncwarp();
+        __syncwarp();
+        if (lane < 9) smem[wid].Vw[lane] = (lane % 4 == 0) ? 1.0 : 0.0;     // svd warm-start slot: cold for a new pair
+        __syncwarp();
         IcpResult r = warp_icp(src, src_idx, s0, ns, tgt, tgt_idx, t0, nt, T0 ? T0 + (size_t)q * 16 : nullptr, max_dist,
                                max_iter, rel_fit, rel_rmse, T + (size_t)q * 16, corr, smem[wid], lane);
         if (lane == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }

@@ -16,10 +16,19 @@
 #pragma once
 #include "icp_device.cuh"
 
+#ifndef WICP_CAP
 #define WICP_CAP 224
+#endif
 
 #ifdef F4L_DEBUG_SCANS
-__device__ unsigned long long g_dbg[8];   // 0: point scans, 1: exact-path scans, 2: iterations, 3: points*iters, 4: sum moved (um), 5: keep checks
+__device__ unsigned long long g_dbg[24];   // 0: point scans, 1: exact-path scans, 2: iterations, 3: points*iters, 4: sum moved (um), 5: keep checks
+// phase timers (debug build): DBG_T0 starts, DBG_T(slot) adds the cycles since the last mark to g_dbg[slot]
+// 8 rigidity, 9 procrustes, 10 icp stage, 11 phase1, 12 lane scans, 13 exact scans, 14 phase3, 15 update(svd), 16 total
+#define DBG_T0 long long dbg_t = clock64();
+#define DBG_T(slot) { const long long dbg_n = clock64(); if (lane == 0) atomicAdd(&g_dbg[slot], (unsigned long long)(dbg_n - dbg_t)); dbg_t = dbg_n; }
+#else
+#define DBG_T0
+#define DBG_T(slot)
 #endif
 
 struct WarpIcpSmem {
@@ -30,6 +39,7 @@ struct WarpIcpSmem {
     float d2lb[WICP_CAP];      // lower bound of the distance to the 2nd nearest distinct target
     unsigned short jstar[WICP_CAP];   // current neighbour of each source point
     unsigned short list[WICP_CAP];
+    double Vw[9];              // SVD warm-start basis (common.cuh svd3x3), identical in all lanes
 };
 
 __device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(F4L_FULL, v, o); }
@@ -57,51 +67,73 @@ __device__ __forceinline__ void warp_argmin_f64(double& d, int& j) {
     }
 }
 
+// top-2 merge across the warp in fp64; every lane ends with the global (d1, j1, d2); ties towards the lower index
+__device__ __forceinline__ void warp_top2_f64(double& d1, int& j1, double& d2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od1 = shfl_xor_d(d1, o);
+        const int oj1 = __shfl_xor_sync(F4L_FULL, j1, o);
+        const double od2 = shfl_xor_d(d2, o);
+        const bool other_wins = od1 < d1 || (od1 == d1 && oj1 < j1);
+        const double loser = other_wins ? d1 : od1;
+        d2 = fmin(fmin(d2, od2), loser);
+        if (other_wins) { d1 = od1; j1 = oj1; }
+    }
+}
+
 // Whole-warp scan for ONE query (global fp64 position pg, pivot cB): returns the exact nearest target
 // (first minimal index) and a lower bound of the distance to the second nearest distinct target.
 // f32 error budget: query and targets are rounded to f32 in the pivot-local frame (|coordinate| < 4 m
 // -> <= 1.2e-7 m each), so two candidates are safely ordered when d2 >= 1.004 d1 + 2e-8 (m^2).
+// try_f32 = false: the caller's own f32 scan already failed that test for this query.
 __device__ inline void warp_scan_point(const WarpIcpSmem& sm, int nt, const double pg[3], const double cB[3],
-                                       int lane, int& jbest, float& d2lb) {
-    const float qx = (float)(pg[0] - cB[0]), qy = (float)(pg[1] - cB[1]), qz = (float)(pg[2] - cB[2]);
-    float d1 = INFINITY, d2 = INFINITY;
-    int j1 = 0x7fffffff;
-    for (int j = lane; j < nt; j += 32) {
-        const float4 b = sm.B[j];
-        const float dx = qx - b.x, dy = qy - b.y, dz = qz - b.z;
-        const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (dd < d1) { d2 = d1; d1 = dd; j1 = j; }
-        else if (dd < d2) d2 = dd;
-    }
-    warp_top2_f32(d1, j1, d2);
-    if (d2 >= d1 * 1.004f + 2e-8f) {           // f32 argmin is provably the fp64 argmin
-        jbest = j1;
-        d2lb = fmaxf(sqrtf(d2) * 0.9999f - 2e-6f, 0.f);
-        return;
+                                       int lane, bool try_f32, int& jbest, float& d2lb) {
+    if (try_f32) {
+        const float qx = (float)(pg[0] - cB[0]), qy = (float)(pg[1] - cB[1]), qz = (float)(pg[2] - cB[2]);
+        float d1 = INFINITY, d2 = INFINITY;
+        int j1 = 0x7fffffff;
+        for (int j = lane; j < nt; j += 32) {
+            const float4 b = sm.B[j];
+            const float dx = qx - b.x, dy = qy - b.y, dz = qz - b.z;
+            const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (dd < d1) { d2 = d1; d1 = dd; j1 = j; }
+            else if (dd < d2) d2 = dd;
+        }
+        warp_top2_f32(d1, j1, d2);
+        if (d2 >= d1 * 1.004f + 2e-8f) {           // f32 argmin is provably the fp64 argmin
+            jbest = j1;
+            d2lb = fmaxf(sqrtf(d2) * 0.9999f - 2e-6f, 0.f);
+            return;
+        }
     }
 #ifdef F4L_DEBUG_SCANS
     if (lane == 0) atomicAdd(&g_dbg[1], 1ull);
 #endif
-    // exact path: fp64 argmin with first-index ties, then the nearest target with other coordinates
-    double e1 = INFINITY;
+    // exact path: ONE fp64 pass keeps the two smallest distances (first index on ties).  A duplicate of the
+    // winner has exactly the winner's distance, so e2 > e1 means e2 already is the nearest DISTINCT target;
+    // only e2 == e1 (a duplicate, or an exact tie of different points) needs the pass that skips duplicates.
+    double e1 = INFINITY, e2 = INFINITY;
     int k1 = 0x7fffffff;
     for (int j = lane; j < nt; j += 32) {
         const double dx = pg[0] - (double)sm.Bg[3 * j], dy = pg[1] - (double)sm.Bg[3 * j + 1], dz = pg[2] - (double)sm.Bg[3 * j + 2];
         const double dd = dx * dx + dy * dy + dz * dz;
-        if (dd < e1) { e1 = dd; k1 = j; }
+        if (dd < e1) { e2 = e1; e1 = dd; k1 = j; }
+        else if (dd < e2) e2 = dd;
     }
-    warp_argmin_f64(e1, k1);
-    const float wx = sm.Bg[3 * k1], wy = sm.Bg[3 * k1 + 1], wz = sm.Bg[3 * k1 + 2];
-    double e2 = INFINITY;
-    int k2 = 0;
-    for (int j = lane; j < nt; j += 32) {
-        const float bx = sm.Bg[3 * j], by = sm.Bg[3 * j + 1], bz = sm.Bg[3 * j + 2];
-        if (bx == wx && by == wy && bz == wz) continue;          // duplicate of the winner
-        const double dx = pg[0] - (double)bx, dy = pg[1] - (double)by, dz = pg[2] - (double)bz;
-        const double dd = dx * dx + dy * dy + dz * dz;
-        if (dd < e2) { e2 = dd; k2 = j; }
+    warp_top2_f64(e1, k1, e2);
+    if (e2 == e1 && e1 != INFINITY) {
+        const float wx = sm.Bg[3 * k1], wy = sm.Bg[3 * k1 + 1], wz = sm.Bg[3 * k1 + 2];
+        e2 = INFINITY;
+        int k2 = 0;
+        for (int j = lane; j < nt; j += 32) {
+            const float bx = sm.Bg[3 * j], by = sm.Bg[3 * j + 1], bz = sm.Bg[3 * j + 2];
+            if (bx == wx && by == wy && bz == wz) continue;          // duplicate of the winner
+            const double dx = pg[0] - (double)bx, dy = pg[1] - (double)by, dz = pg[2] - (double)bz;
+            const double dd = dx * dx + dy * dy + dz * dz;
+            if (dd < e2) { e2 = dd; k2 = j; }
+        }
+        warp_argmin_f64(e2, k2);
     }
-    warp_argmin_f64(e2, k2);
     jbest = k1;
     d2lb = (e2 == INFINITY) ? INFINITY : fmaxf((float)(sqrt(e2) * (1.0 - 1e-7)) - 1e-7f, 0.f);
 }
@@ -112,6 +144,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
                                      int t0, int nt, const double* T0, double max_dist, int max_iter,
                                      double rel_fit, double rel_rmse, double* Tout, int32_t* __restrict__ corr,
                                      WarpIcpSmem& sm, int lane) {
+    DBG_T0
     // ---- stage ------------------------------------------------------------------------------
     double cB[3];
     {
@@ -135,6 +168,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
     for (int a = 0; a < 12; ++a) T[a] = T0 ? T0[a] : ((a % 5 == 0) ? 1.0 : 0.0);
     __syncwarp();
 
+    DBG_T(10)
     const double max_d2 = max_dist * max_dist;
     IcpResult out;
     out.fitness = 0; out.rmse = 0; out.iters = 0;
@@ -167,12 +201,14 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
             nres += __popc(m);
         }
         __syncwarp();
+        DBG_T(11)
 #ifdef F4L_DEBUG_SCANS
         if (lane == 0) { atomicAdd(&g_dbg[0], (unsigned long long)nres); atomicAdd(&g_dbg[2], 1ull); atomicAdd(&g_dbg[3], (unsigned long long)ns); }
 #endif
         // ---- phase 2: scans ------------------------------------------------------------------
         int nexact = nres;                 // items [0, nexact) of the list go through the whole-warp exact-capable scan
-        if (nres >= 8) {
+        const bool lane_scanned = nres >= 8;
+        if (lane_scanned) {
             // many points: one LANE per point, every lane walks all targets (broadcast reads), f32 top-2;
             // points whose two best are within the f32 error margin are re-listed for the exact scan
             nexact = 0;
@@ -209,6 +245,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
                 __syncwarp();
             }
         }
+        DBG_T(12)
         for (int r = 0; r < nexact; ++r) {
             const int i = sm.list[r];
             const double fx = sm.A[3 * i], fy = sm.A[3 * i + 1], fz = sm.A[3 * i + 2];
@@ -218,7 +255,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
             pg[2] = T[8] * fx + T[9] * fy + T[10] * fz + T[11];
             int jb;
             float lb;
-            warp_scan_point(sm, nt, pg, cB, lane, jb, lb);
+            warp_scan_point(sm, nt, pg, cB, lane, !lane_scanned, jb, lb);
             if (lane == 0) {
                 sm.jstar[i] = (unsigned short)jb;
                 sm.d2lb[i] = lb;
@@ -226,6 +263,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
             }
         }
         __syncwarp();
+        DBG_T(13)
         // ---- phase 3: accept / accumulate with exact fp64 distances -------------------------
         Moments M;
         moments_zero(M);
@@ -257,6 +295,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
         bool stop = false;
         if (it > 0 && fabs(prev_fit - fit) < rel_fit && fabs(prev_rmse - rmse) < rel_rmse) stop = true;
         if (it >= max_iter) stop = true;
+        DBG_T(14)
         if (stop) {
             out.iters = it;
             break;
@@ -265,7 +304,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
         prev_rmse = rmse;
         // ---- update: U = umeyama(P[corr], tgt[corr]);  T <- U T -------------------------------
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
-        if (cnt > 0) fit_from_moments(M, cB, cB, 0.0, 2, R, t);
+        if (cnt > 0) fit_from_moments(M, cB, cB, 0.0, 2, R, t, sm.Vw);
         double Tn[12];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -274,6 +313,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
                 Tn[r * 4 + c] = R[r * 3 + 0] * T[c] + R[r * 3 + 1] * T[4 + c] + R[r * 3 + 2] * T[8 + c] + (c == 3 ? t[r] : 0.0);
 #pragma unroll
         for (int a = 0; a < 12; ++a) T[a] = Tn[a];
+        DBG_T(15)
     }
 #pragma unroll
     for (int a = 0; a < 12; ++a)
@@ -289,37 +329,166 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
 // GEMM-formulation noise at these coordinates).
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // ftz: one MUFU, no denormal rescaling (d^2 < 1e-38 m^2 -> 0)
     return r;
 }
 
-__device__ __forceinline__ void rigidity_row(const WarpIcpSmem& sm, int i, int n, float thres, float& sum, unsigned& cnt) {
-    const float ax = sm.A[3 * i], ay = sm.A[3 * i + 1], az = sm.A[3 * i + 2];
-    const float bx = sm.Bg[3 * i], by = sm.Bg[3 * i + 1], bz = sm.Bg[3 * i + 2];
-    float rowsum = 0.f;
-#pragma unroll 2
-    for (int j = i + 1; j < n; ++j) {
-        const float ex = ax - sm.A[3 * j], ey = ay - sm.A[3 * j + 1], ez = az - sm.A[3 * j + 2];
-        const float fx = bx - sm.Bg[3 * j], fy = by - sm.Bg[3 * j + 1], fz = bz - sm.Bg[3 * j + 2];
-        const float ds = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-        const float dt = sqrt_approx(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
-        const float diff = fabsf(ds - dt);
-        rowsum += diff;
-        cnt += (diff <= thres) ? 1u : 0u;
-    }
-    sum += rowsum;
+// ---- packed rigidity ----------------------------------------------------------------------------
+// Pair schedule: row i meets the h = (n-1)/2 points that FOLLOW it cyclically (j = i+1 .. i+h mod n), which
+// covers every unordered pair exactly once for odd n and leaves the n/2 "diameters" (i, i+n/2) for even n --
+// every row has the same trip count, so lanes are balanced without the triangular tail.  A lane owns two
+// ADJACENT rows (i, i+1): at offset s they meet points (i+s, i+s+1), at s+1 points (i+s+1, i+s+2) -- a sliding
+// window, one new shared-memory word per coordinate per step -- and the two pairs of a step go through the
+// packed FADD2/FMUL2/FFMA2 pipe (two fp32 lanes per instruction).  The window's halves alternate roles
+// (step A: lo = row i, hi = row i+1; step B: lo = row i+1, hi = row i) so no register moves are needed.
+// The arena holds the six coordinate arrays twice over (cyclic access without a wrap test); it aliases the
+// ICP staging area, which is filled after the check.
+typedef unsigned long long u64p;
+__device__ __forceinline__ u64p pk2(float lo, float hi) { u64p r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64p v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64p sub2(u64p a, u64p b) { u64p r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p mul2(u64p a, u64p b) { u64p r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p fma2(u64p a, u64p b, u64p c) { u64p r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+struct RigRows { u64p ax, ay, az, bx, by, bz; };      // the lane's two rows, packed (lo, hi)
+
+// one step: lo pair = (rows.lo, window.lo), hi pair = (rows.hi, window.hi); (s_lo, c_lo) / (s_hi, c_hi) collect them
+__device__ __forceinline__ void rig_step(const RigRows& r, float x0, float x1, float y0, float y1, float z0, float z1,
+                                         float u0, float u1, float v0, float v1, float w0, float w1, float thres,
+                                         float& s_lo, unsigned& c_lo, float& s_hi, unsigned& c_hi) {
+    const u64p ex = sub2(r.ax, pk2(x0, x1)), ey = sub2(r.ay, pk2(y0, y1)), ez = sub2(r.az, pk2(z0, z1));
+    const u64p fx = sub2(r.bx, pk2(u0, u1)), fy = sub2(r.by, pk2(v0, v1)), fz = sub2(r.bz, pk2(w0, w1));
+    const u64p e2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+    const u64p f2 = fma2(fz, fz, fma2(fy, fy, mul2(fx, fx)));
+    float e_lo, e_hi, f_lo, f_hi;
+    upk2(e2, e_lo, e_hi);
+    upk2(f2, f_lo, f_hi);
+    const float d_lo = fabsf(sqrt_approx(e_lo) - sqrt_approx(f_lo));
+    const float d_hi = fabsf(sqrt_approx(e_hi) - sqrt_approx(f_hi));
+    s_lo += d_lo; c_lo += (d_lo <= thres) ? 1u : 0u;
+    s_hi += d_hi; c_hi += (d_hi <= thres) ? 1u : 0u;
 }
 
-__device__ inline void warp_rigidity(const WarpIcpSmem& sm, int n, float thres, int lane, double& out_sum,
-                                     unsigned& out_cnt) {
+static_assert(6 * (2 * WICP_CAP + 4) * 4 <= (int)offsetof(WarpIcpSmem, Vw), "rigidity arena must fit the warp's slice");
+// floats per coordinate array for n pairs.  Each array holds the extended cyclic sequence j = 0 .. 2n+3
+// (point j mod n; 4 zero pad words) DE-INTERLEAVED: even j in the first half, odd j in the second, so that
+// lanes owning rows 2l, 2l+1 read consecutive words (a plain layout would be a stride-2, two-way bank conflict
+// on every load of the sliding window).
+__device__ __forceinline__ int rig_arena_stride(int n) { return 2 * n + 4; }
+__device__ __forceinline__ int rig_slot(int j, int n) { return (j & 1) * (n + 2) + (j >> 1); }
+
+// Stage the matched pairs (global rows k0 .. k0+n of the correspondence lists) into the arena.
+__device__ inline void warp_rigidity_stage(float* arena, const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
+                                           const int32_t* __restrict__ cs, const int32_t* __restrict__ ct, int k0, int n,
+                                           int lane) {
+    const int L = rig_arena_stride(n);
+    for (int i = lane; i < n; i += 32) {
+        const int s0 = rig_slot(i, n), s1 = rig_slot(i + n, n);
+        float x, y, z;
+        load_ptf(src_pts, cs, k0 + i, x, y, z);
+        arena[s0] = x; arena[s1] = x;
+        arena[L + s0] = y; arena[L + s1] = y;
+        arena[2 * L + s0] = z; arena[2 * L + s1] = z;
+        load_ptf(tgt_pts, ct, k0 + i, x, y, z);
+        arena[3 * L + s0] = x; arena[3 * L + s1] = x;
+        arena[4 * L + s0] = y; arena[4 * L + s1] = y;
+        arena[5 * L + s0] = z; arena[5 * L + s1] = z;
+    }
+    if (lane < 24) arena[(lane >> 2) * L + rig_slot(2 * n + (lane & 3), n)] = 0.f;     // the window may read 3 words past 2n
+}
+
+// Rigidity statistic (base.py:3308-3317) of the staged pairs by one warp: sum of |d_src(i,j) - d_tgt(i,j)| over
+// i < j and the number of pairs with that difference <= thres.  Distances use sqrt.approx.f32 (<= 1 ulp; the
+// reference's own cdist carries ~1e-3 m of GEMM-formulation noise at these coordinates).
+__device__ inline void warp_rigidity(const float* arena, int n, float thres, int lane, double& out_sum, unsigned& out_cnt) {
+    const int L = rig_arena_stride(n);
+    const float* AX = arena; const float* AY = arena + L; const float* AZ = arena + 2 * L;
+    const float* BX = arena + 3 * L; const float* BY = arena + 4 * L; const float* BZ = arena + 5 * L;
+    const int h = (n - 1) >> 1;
     float sum = 0.f;
     unsigned cnt = 0;
-    const int half = n >> 1;                       // row pairs (i, n-1-i), i < half; odd n: middle row alone
-    for (int i = lane; i < half; i += 32) {
-        rigidity_row(sm, i, n, thres, sum, cnt);
-        rigidity_row(sm, n - 1 - i, n, thres, sum, cnt);
+    for (int base = 0; base < n; base += 64) {
+        // a round covers 64 rows; when fewer are left, the offsets 1..h are split over f groups of lanes
+        const int left = n - base;
+        int f = 1;
+        while (f < 16 && left * (2 * f) <= 64) f *= 2;
+        const int per = 32 / f;                          // lanes (row pairs) per group
+        const int grp = lane / per;
+        const int i1 = base + 2 * (lane - grp * per);    // even
+        const int chunk = (h + f - 1) / f;
+        const int sb = 1 + grp * chunk;
+        const int se = min(h, sb + chunk - 1);           // offsets [sb, se]
+        if (i1 < n && sb <= se) {
+            const bool two = i1 + 1 < n;
+            RigRows ra, rb;
+            {
+                const int r1 = rig_slot(i1, n), r2 = rig_slot(i1 + 1, n);
+                const float a1x = AX[r1], a1y = AY[r1], a1z = AZ[r1], b1x = BX[r1], b1y = BY[r1], b1z = BZ[r1];
+                const float a2x = AX[r2], a2y = AY[r2], a2z = AZ[r2], b2x = BX[r2], b2y = BY[r2], b2z = BZ[r2];
+                ra.ax = pk2(a1x, a2x); ra.ay = pk2(a1y, a2y); ra.az = pk2(a1z, a2z);
+                ra.bx = pk2(b1x, b2x); ra.by = pk2(b1y, b2y); ra.bz = pk2(b1z, b2z);
+                rb.ax = pk2(a2x, a1x); rb.ay = pk2(a2y, a1y); rb.az = pk2(a2z, a1z);
+                rb.bx = pk2(b2x, b1x); rb.by = pk2(b2y, b1y); rb.bz = pk2(b2z, b1z);
+            }
+            float s1 = 0.f, s2 = 0.f;
+            unsigned c1 = 0, c2 = 0;
+            // window words: x0 walks the points j, j+2, ... (one parity), x1 the points j+1, j+3, ... (the other)
+            const int j = i1 + sb;
+            int o0 = rig_slot(j, n), o1 = rig_slot(j + 1, n);
+            float x0 = AX[o0], y0 = AY[o0], z0 = AZ[o0], u0 = BX[o0], v0 = BY[o0], w0 = BZ[o0];
+            float x1 = AX[o1], y1 = AY[o1], z1 = AZ[o1], u1 = BX[o1], v1 = BY[o1], w1 = BZ[o1];
+            int s = sb;
+            for (; s < se; s += 2) {
+                rig_step(ra, x0, x1, y0, y1, z0, z1, u0, u1, v0, v1, w0, w1, thres, s1, c1, s2, c2);
+                ++o0;
+                x0 = AX[o0]; y0 = AY[o0]; z0 = AZ[o0]; u0 = BX[o0]; v0 = BY[o0]; w0 = BZ[o0];
+                rig_step(rb, x0, x1, y0, y1, z0, z1, u0, u1, v0, v1, w0, w1, thres, s2, c2, s1, c1);
+                ++o1;
+                x1 = AX[o1]; y1 = AY[o1]; z1 = AZ[o1]; u1 = BX[o1]; v1 = BY[o1]; w1 = BZ[o1];
+            }
+            if (s == se) rig_step(ra, x0, x1, y0, y1, z0, z1, u0, u1, v0, v1, w0, w1, thres, s1, c1, s2, c2);
+            sum += s1;
+            cnt += c1;
+            if (two) { sum += s2; cnt += c2; }
+        }
     }
-    if ((n & 1) && lane == 0) rigidity_row(sm, half, n, thres, sum, cnt);
+    if (!(n & 1)) {
+        // even n: the diameters (i, i + n/2), i < n/2
+        const int hn = n >> 1;
+        for (int i = lane; i < hn; i += 32) {
+            const int p = rig_slot(i, n), q = rig_slot(i + hn, n);
+            const float ex = AX[p] - AX[q], ey = AY[p] - AY[q], ez = AZ[p] - AZ[q];
+            const float fx = BX[p] - BX[q], fy = BY[p] - BY[q], fz = BZ[p] - BZ[q];
+            const float ds = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+            const float dt = sqrt_approx(fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+            const float diff = fabsf(ds - dt);
+            sum += diff;
+            cnt += (diff <= thres) ? 1u : 0u;
+        }
+    }
     out_sum = warp_sum((double)sum);
     out_cnt = (unsigned)warp_sum((int)cnt);
+}
+
+// D1/D2 on the pairs already staged for the rigidity check (unit weights): same values, same pivot, same
+// accumulation order as warp_fit_segment, without gathering the points from global memory a second time.
+__device__ inline bool warp_fit_arena(const float* arena, int n, double eps, int variant, int lane, double R[9],
+                                      double t[3], double* warm) {
+    const int L = rig_arena_stride(n);
+    double ps[3], pt[3];
+    {
+        const int p0 = rig_slot(0, n);
+        ps[0] = arena[p0]; ps[1] = arena[L + p0]; ps[2] = arena[2 * L + p0];
+        pt[0] = arena[3 * L + p0]; pt[1] = arena[4 * L + p0]; pt[2] = arena[5 * L + p0];
+    }
+    Moments M;
+    moments_zero(M);
+    for (int i = lane; i < n; i += 32) {
+        const int p = rig_slot(i, n);
+        const double sx = arena[p], sy = arena[L + p], sz = arena[2 * L + p];
+        const double tx = arena[3 * L + p], ty = arena[4 * L + p], tz = arena[5 * L + p];
+        moments_add(M, 1.0, sx - ps[0], sy - ps[1], sz - ps[2], tx - pt[0], ty - pt[1], tz - pt[2]);
+    }
+    moments_warp_reduce(M);
+    return fit_from_moments(M, ps, pt, eps, variant, R, t, warm);
 }

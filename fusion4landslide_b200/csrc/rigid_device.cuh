@@ -52,7 +52,7 @@ __device__ __forceinline__ void moments_warp_reduce(Moments& M) {
 //   variant 2 (Eigen::umeyama, no scaling):    wn = w/W (true means), S(2) = -1 iff det<0
 // ps, pt: pivots the moments were taken about.  Returns true when the result is not finite.
 __device__ inline bool fit_from_moments(const Moments& M, const double ps[3], const double pt[3],
-                                        double eps, int variant, double R[9], double t[3]) {
+                                        double eps, int variant, double R[9], double t[3], double* warm = nullptr) {
     const double W = M.m[0];
     const double inv = (variant == 2) ? 1.0 / W : 1.0 / (W + eps);
     const double f = W * inv;  // sum of normalised weights
@@ -95,7 +95,7 @@ __device__ inline bool fit_from_moments(const Moments& M, const double ps[3], co
         return true;
     }
     double U[9], S[3], V[9];
-    svd3x3(H, U, S, V);
+    svd3x3(H, U, S, V, warm);
     rotation_from_svd(U, V, variant, R);
     double cs[3], ct[3];
 #pragma unroll
@@ -113,7 +113,7 @@ __device__ inline bool warp_fit_segment(const float* __restrict__ src, const flo
                                         const int32_t* __restrict__ src_idx,
                                         const int32_t* __restrict__ tgt_idx, const float* __restrict__ w,
                                         int s0, int n, double eps, float weight_thresh, int variant,
-                                        int lane, double R[9], double t[3]) {
+                                        int lane, double R[9], double t[3], double* warm = nullptr) {
     if (n <= 0) {
         R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
         t[0] = t[1] = t[2] = 0;
@@ -138,7 +138,7 @@ __device__ inline bool warp_fit_segment(const float* __restrict__ src, const flo
         moments_add(M, wi, sx - ps[0], sy - ps[1], sz - ps[2], tx - pt[0], ty - pt[1], tz - pt[2]);
     }
     moments_warp_reduce(M);
-    return fit_from_moments(M, ps, pt, eps, variant, R, t);
+    return fit_from_moments(M, ps, pt, eps, variant, R, t, warm);
 }
 
 // Block-level rigidity statistic over items [s0, s0+n): sum over pairs i<j of |dS_ij - dT_ij|
