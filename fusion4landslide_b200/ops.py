@@ -6,7 +6,7 @@ computation below happens in libf4l_b200.so kernels.  All tensors must be CUDA +
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr, stream_ptr
+from ._lib import F4LError, check, lib, ptr, stream_ptr
 
 I32 = torch.int32
 F32 = torch.float32
@@ -352,3 +352,36 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
     check(lib().f4l_fine_matching(ctypes.byref(prm), ctypes.byref(bf), ptr(ws), ws.numel(), stream_ptr(dev)),
           "f4l_fine_matching")
     return r
+
+
+class DipsIndex:
+    """Ball-query index of one reference cloud (the counterpart of o3d.geometry.KDTreeFlann(pcd),
+    data_loader.py:26): the cloud binned for queries of `radius`, resident in a workspace tensor."""
+
+    def __init__(self, ref64, radius):
+        if ref64.dtype != F64:
+            raise F4LError("DipsIndex: reference cloud must be float64 (the reference works on Open3D's doubles)")
+        self.ref = ref64.contiguous()
+        self.n_ref = int(ref64.shape[0])
+        self.radius = float(radius)
+        nbytes = lib().f4l_dips_workspace_bytes(self.n_ref)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=ref64.device)
+        check(lib().f4l_dips_build(ptr(self.ref, F64), self.n_ref, self.radius, ptr(self.ws), nbytes,
+                                   stream_ptr(ref64.device)), "f4l_dips_build")
+
+
+def dips_patches(index, query64, num_points=256, ranks=None, seed=0, want_lrf=False, out=None):
+    """K-h.  (n,3,num_points) f32 patches of data_loader.py:37-105 for the rows of query64 (n,3) f64.
+    ranks: optional (n,num_points) i32 distance ranks to keep (the reference's `inds`).
+    Returns patches, count (n) i32 [, lrf (n,9) f64]."""
+    n = int(query64.shape[0])
+    patches = out if out is not None else _empty((n, 3, num_points), F32, query64)
+    count = _empty((n,), I32, query64)
+    lrf = _empty((n, 9), F64, query64) if want_lrf else None
+    check(lib().f4l_dips_patches(ptr(query64, F64), n, index.n_ref, index.radius, int(num_points),
+                                 ptr(ranks, I32, True), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(patches, F32),
+                                 ptr(lrf, F64, True), ptr(count, I32), ptr(index.ws), index.ws.numel(),
+                                 stream_ptr(query64.device)), "f4l_dips_patches")
+    if want_lrf:
+        return patches, count, lrf
+    return patches, count

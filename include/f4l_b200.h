@@ -339,6 +339,32 @@ F4L_API int f4l_peer_close(void* d_ptr);
 F4L_API int f4l_peer_free(void* d_ptr);
 F4L_API int f4l_peer_enable_access(int32_t peer_device);
 
+/* ------------------------------------------------------------------------------------------
+ * 8(f) rank 1 -- DIPs patch front-end.  Replaces src/data_loader.py:16-109
+ * (Preprocess_Dataset.__init__ / extract_patch / __getitem__), called from src/f2s3.py:104-134 and
+ * base.py:1981-2034.
+ *
+ * f4l_dips_build bins the reference cloud ("data_overlap", (n_ref,3) f64) for ball queries of the given
+ * radius into the workspace (the counterpart of o3d.geometry.KDTreeFlann(data_overlap), data_loader.py:26).
+ * f4l_dips_patches then produces, for every query point (the rows of "data", (n_query,3) f64), the
+ * (3, num_points) f32 patch of data_loader.py:37-105: neighbours with d^2 < radius^2 (fp64, nanoflann's
+ * summation order), local reference frame of :46-80 when more than 10 neighbours, coordinates divided by the
+ * radius, zero rows when fewer than num_points neighbours.
+ *   ranks == NULL: slot t holds a uniform random sample without replacement (keyed by seed, query index) --
+ *                  the reference draws np.random.choice from the global generator inside DataLoader workers;
+ *   ranks != NULL: (n_query, num_points) i32, slot t holds the neighbour whose distance rank is ranks[q][t]
+ *                  (ties by original index; a rank >= the neighbour count selects a zero row), i.e. the
+ *                  reference's `ptall[inds]`.
+ * lrf (n_query,9) f64 or NULL: rows xp, yp, zp of the frame (zeros when no frame was estimated);
+ * count (n_query) i32: neighbours found.  More than 2048 neighbours is outside the supported range: the patch
+ * is zero-filled and count reports the size. */
+F4L_API size_t f4l_dips_workspace_bytes(int32_t n_ref);
+F4L_API int f4l_dips_build(const double* ref64, int32_t n_ref, double radius, void* workspace,
+                   size_t workspace_bytes, void* stream);
+F4L_API int f4l_dips_patches(const double* query64, int32_t n_query, int32_t n_ref, double radius,
+                   int32_t num_points, const int32_t* ranks, uint64_t seed, float* patches, double* lrf,
+                   int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@ What gets pinned (reference function -> golden file):
       base.py:2727-2736                                            -> knn_sklearn.npz
   torch.cdist + min call pattern of base.py:2805-2815 / 2966-2986  -> desc_cdist.npz
   torch.cdist rigidity expression of base.py:3310-3317             -> rigidity_cdist.npz
+  src/data_loader.py Preprocess_Dataset.extract_patch, with a cKDTree stand-in for the one Open3D
+      class it uses (KDTreeFlann.search_radius_vector_3d)          -> dips_patches.npz
 Open3D ICP / Octree, hnswlib and faiss cannot be run anywhere here -> no golden, parity unpinned.
 """
 import os
@@ -234,15 +236,69 @@ def make_rigidity():
     np.savez_compressed(os.path.join(GOLD, "rigidity_cdist.npz"), **out)
 
 
+def make_dips():
+    """src/data_loader.py run unmodified: the module-level `o3d` name is pointed at a stand-in whose
+    KDTreeFlann answers radius queries through oracle.dips.radius_search (nanoflann semantics)."""
+    import importlib
+    import types
+    from scipy.spatial import cKDTree
+    from oracle import dips as odips
+    ref_shim.load()
+    dl = importlib.import_module("src.data_loader")
+
+    class _Pcd:
+        def __init__(self, pts):
+            self.points = pts
+
+    class _Tree:
+        def __init__(self, pcd):
+            self.pts = np.asarray(pcd.points)
+            self.tree = cKDTree(self.pts)
+            self.sizes = []
+
+        def search_radius_vector_3d(self, pt, radius):
+            idx, d2 = odips.radius_search(self.tree, self.pts, np.asarray(pt), radius)
+            self.sizes.append(idx.size)
+            return idx.size, idx.tolist(), d2.tolist()
+
+    dl.o3d = types.SimpleNamespace(geometry=types.SimpleNamespace(KDTreeFlann=_Tree))
+    rng = np.random.default_rng(21)
+    n = 7000
+    xy = rng.uniform(0, 8.4, (n, 2))                        # ~100 pts / m^2 like a 0.1 m voxel grid
+    z = 0.8 * np.sin(xy[:, 0] * 0.9) + 0.5 * np.cos(xy[:, 1] * 1.3) + 0.01 * rng.normal(size=n)
+    ref = np.column_stack([xy, z])
+    lonely = np.array([[30.0, 30.0, 1.0]]) + 0.05 * rng.normal(size=(7, 3))      # <= 10 neighbours: no frame
+    wall = np.column_stack([rng.uniform(40, 41.2, 300), np.full(300, 40.0) + 0.005 * rng.normal(size=300),
+                            rng.uniform(0, 1.2, 300)])                          # small vertical patch (< 256 pts)
+    mid = np.array([[60.0, 10.0, 3.0]]) + 0.3 * rng.normal(size=(60, 3))         # 10 < n < 256: frame + zero padding
+    ref = np.vstack([ref, lonely, wall, mid])                # tile-local coordinates
+    radius = float(np.sqrt(3) * 10 * 0.1)                    # f2s3.py:106 with a 0.1 m median resolution: ~940 neighbours
+    pick = np.concatenate([rng.choice(n, 36, replace=False), n + np.arange(7), n + 7 + rng.choice(300, 7, replace=False),
+                           n + 307 + rng.choice(60, 6, replace=False)])
+    data = ref[pick]
+    ds = dl.Preprocess_Dataset(_Pcd(data), _Pcd(ref), points_per_batch=len(pick), feature_radius=radius)
+    np.random.seed(1234)
+    out = ds[0].numpy()                                      # (n_pick, 3, 256) f32
+    sizes = list(ds.pcd_tree.sizes)
+    np.random.seed(1234)
+    inds = np.stack([np.random.choice(max(s_, 256), 256, replace=False) for s_ in sizes]).astype(np.int32)
+    mine, cnt, lrf = odips.patches(data, ref, radius, inds)
+    assert (cnt == np.asarray(sizes)).all()
+    err = np.abs(mine - out).max()
+    print("dips: %d queries, neighbours %d..%d, oracle vs reference max |diff| = %.2e" % (len(pick), min(sizes), max(sizes), err))
+    assert err < 2e-6
+    np.savez_compressed(os.path.join(GOLD, "dips_patches.npz"), ref=ref, pick=pick.astype(np.int32), radius=np.array([radius]),
+                        inds=inds, patches=out, count=np.asarray(sizes, np.int32), lrf=lrf)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)
-    make_rigid()
-    make_f2s3_filter()
-    make_knn()
-    make_desc()
-    make_rigidity()
+    makers = dict(rigid=make_rigid, f2s3_filter=make_f2s3_filter, knn=make_knn, desc=make_desc,
+                  rigidity=make_rigidity, dips=make_dips)
+    for name in (sys.argv[1:] or list(makers)):          # `python -m oracle.make_golden dips` refreshes one file
+        makers[name]()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

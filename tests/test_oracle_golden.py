@@ -98,3 +98,14 @@ def test_rigidity_matches_cdist_expression(golden_dir):
         # torch.cdist switches to the fp32 GEMM formulation above 25 rows: noise ~1e-3 at |p|~40 m
         assert abs(m - z["r%d_mean" % ci][0]) < 5e-3, ci
         assert abs(r - z["r%d_ratio" % ci][0]) < 5e-3, ci
+
+
+def test_dips_oracle_matches_reference_golden(golden_dir):
+    """oracle/dips.py against the reference's own Preprocess_Dataset output (make_golden.make_dips)."""
+    from oracle import dips as odips
+    z = np.load(os.path.join(golden_dir, "dips_patches.npz"))
+    ref, radius = z["ref"], float(z["radius"][0])
+    out, cnt, lrf = odips.patches(ref[z["pick"]], ref, radius, z["inds"])
+    np.testing.assert_array_equal(cnt, z["count"])
+    np.testing.assert_allclose(out, z["patches"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(lrf, z["lrf"], rtol=0, atol=1e-12)
