@@ -7,7 +7,7 @@
 // the tangential parts), the neighbours expressed in that frame and divided by the radius, and `num_points` of
 // them (zero rows when there are fewer) -> (n, 3, num_points) f32.
 //
-// Layout: reference points are binned once per cloud into a uniform grid (cell edge = radius/2, the thin axis of
+// Layout: reference points are binned once per cloud into a uniform grid (cell edge = radius/4, the thin axis of
 // a surface-like cloud is not binned) as double4 {x, y, z, bits(original index)} rows in cell order, so the cells
 // of one grid row that a query's ball overlaps are ONE contiguous range.  One warp owns a query: pass 1 walks the
 // ranges with 32 lanes, keeps the hits as positions in a shared-memory list and accumulates the fp64 moments;
@@ -93,7 +93,7 @@ __global__ void k_dips_params(DipsGrid* g, double radius, int max_cells) {
     for (int c = 0; c < 3; ++c)
         if (c != thin) mid = fmin(mid, ex[c]);
     const bool flat = ex[thin] <= 0.25 * mid;
-    double cell = 0.5 * radius;
+    double cell = 0.25 * radius;
     int nn[3];
     for (int it = 0; it < 64; ++it) {
         for (int c = 0; c < 3; ++c) nn[c] = (flat && c == thin) ? 1 : (int)fmin(floor(ex[c] / cell), 2.0e9) + 1;
@@ -140,9 +140,13 @@ __global__ void __launch_bounds__(256) k_dips_gather(const double* __restrict__ 
 }
 
 // ---- the per-query kernel ------------------------------------------------------------------------
+#define DIPS_ROWCAP (3 * DIPS_MAXP / 2)
 struct DipsWarpSmem {
     unsigned list[DIPS_CAP];        // positions of the hits in `sorted`
-    float out[3 * DIPS_MAXP];       // the patch, staged for coalesced stores
+    union {
+        float out[3 * DIPS_MAXP];   // pass 3: the patch, staged for coalesced stores
+        int rows[2 * DIPS_ROWCAP];  // pass 1: [begin | end) of the candidate range of every grid row the ball touches
+    };
 };
 struct DipsRankSmem {               // ranked mode only
     double d2[DIPS_CAP];
@@ -154,19 +158,17 @@ __device__ __forceinline__ unsigned dips_mix(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
-// keyed bijection of [0, m): 4-round Feistel network on 2*hb bits (2^(2 hb) >= m), cycle walking
+// keyed bijection of [0, m): 3-round Feistel network on 2*hb bits (2^(2 hb) >= m > 2^(2 hb - 2)), cycle walking;
+// round function = high bits of a keyed multiply (one IMAD + shift per round)
 __device__ __forceinline__ unsigned dips_perm(unsigned t, unsigned m, int hb, unsigned key) {
     const unsigned mask = (1u << hb) - 1u;
+    const unsigned k0 = key | 1u, k1 = dips_mix(key) | 1u, k2 = dips_mix(key ^ 0x9e3779b9u) | 1u;
     unsigned v = t;
     do {
         unsigned l = v >> hb, r = v & mask;
-#pragma unroll
-        for (int round = 0; round < 4; ++round) {
-            const unsigned f = dips_mix(r ^ key ^ (0x9e3779b9u * (unsigned)(round + 1))) & mask;
-            const unsigned nl = r;
-            r = l ^ f;
-            l = nl;
-        }
+        l ^= (((r + 1u) * k0) >> 13) & mask;
+        r ^= (((l + 1u) * k1) >> 13) & mask;
+        l ^= (((r + 1u) * k2) >> 13) & mask;
         v = (l << hb) | r;
     } while (v >= m);
     return v;
@@ -175,6 +177,24 @@ __device__ __forceinline__ unsigned dips_perm(unsigned t, unsigned m, int hb, un
 __device__ __forceinline__ double dips_d2(double dx, double dy, double dz) {
     // nanoflann L2_Simple_Adaptor: result += diff * diff per dimension, no contraction
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// sqrt in fp64 from an f32 reciprocal square root and two Newton steps (relative error ~1e-15): the frame weights
+// (radius - dist)^2 need fp64-level accuracy but not the IEEE-rounded root
+__device__ __forceinline__ double dips_sqrt(double x) {
+    if (!(x > 1e-280)) return 0.0;
+    double y = (double)rsqrtf((float)x);
+    y = y * (1.5 - 0.5 * x * y * y);
+    y = y * (1.5 - 0.5 * x * y * y);
+    return x * y;
+}
+
+// distance from v to the interval [a, b] (0 inside); first / last cells are open towards the outside
+__device__ __forceinline__ double dips_slab(double v, double a, double b, bool first, bool last) {
+    double d = 0.0;
+    if (v < a && !first) d = a - v;
+    if (v > b && !last) d = v - b;
+    return d;
 }
 
 template <bool RANKED>
@@ -206,33 +226,81 @@ k_dips_patches(const double* __restrict__ query, int nq, const double4* __restri
         int n = 0;
         double sx = 0, sy = 0, sz = 0, cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
         double best_d2 = INFINITY;
-        long long best_i = 0x7fffffffffffffffll;
-        unsigned best_pos = 0;
-        for (int z = lo[2]; z <= hi[2]; ++z) {
-            for (int y = lo[1]; y <= hi[1]; ++y) {
-                const size_t row = ((size_t)z * g.n[1] + y) * g.n[0];
-                const int b = __ldg(cell_start + row + lo[0]), e = __ldg(cell_start + row + hi[0] + 1);
-                for (int j0 = b; j0 < e; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool hit = false;
-                    if (j < e) {
-                        const double4 p = sorted[j];
-                        const double dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-                        const double d2 = dips_d2(dx, dy, dz);
-                        hit = d2 < r2;                                           // RadiusResultSet::addPoint: dist < radius
-                        if (hit) {
-                            sx += dx; sy += dy; sz += dz;
-                            cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
-                            const long long oi = __double_as_longlong(p.w);
-                            if (d2 < best_d2 || (d2 == best_d2 && oi < best_i)) { best_d2 = d2; best_i = oi; best_pos = (unsigned)j; }
-                        }
+        unsigned best_pos = 0xffffffffu;
+        // one candidate: membership test, moments, nearest (ties between duplicates: any of them, they are equal),
+        // ordered compaction of the hits into the list
+        auto visit = [&](int j, bool valid, const double4& p) {
+            bool hit = false;
+            if (valid) {
+                const double dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                const double d2 = dips_d2(dx, dy, dz);
+                hit = d2 < r2;                                           // RadiusResultSet::addPoint: dist < radius
+                if (hit) {
+                    sx += dx; sy += dy; sz += dz;
+                    cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+                    if (d2 < best_d2) { best_d2 = d2; best_pos = (unsigned)j; }
+                }
+            }
+            const unsigned m = __ballot_sync(F4L_FULL, hit);
+            if (hit) {
+                const int slot = n + __popc(m & ((1u << lane) - 1u));
+                if (slot < DIPS_CAP) sm.list[slot] = (unsigned)j;
+            }
+            n += __popc(m);
+        };
+        const int ny = hi[1] - lo[1] + 1, nrows = ny * (hi[2] - lo[2] + 1);
+        if (nrows <= DIPS_ROWCAP) {
+            // the lanes trim the rows in parallel: a row's cells can only hold hits where the ball is at least as
+            // wide as the row's distance from the query allows
+            __syncwarp();
+            for (int r = lane; r < nrows; r += 32) {
+                const int z = lo[2] + r / ny, y = lo[1] + r % ny;
+                double w2 = r2;
+                if (g.inv[1] != 0.0) {
+                    const double d = dips_slab(qy, g.org[1] + y * g.cell, g.org[1] + (y + 1) * g.cell, y == 0, y == g.n[1] - 1);
+                    w2 -= d * d;
+                }
+                if (g.inv[2] != 0.0) {
+                    const double d = dips_slab(qz, g.org[2] + z * g.cell, g.org[2] + (z + 1) * g.cell, z == 0, z == g.n[2] - 1);
+                    w2 -= d * d;
+                }
+                int b = 0, e = 0;
+                if (w2 > -1e-9 * r2) {
+                    const double w = sqrt(fmax(w2, 0.0)) + 1e-9 * radius;
+                    const int x0 = (int)fmin(fmax(floor((qx - w - g.org[0]) * g.inv[0] - 1e-9), 0.0), (double)(g.n[0] - 1));
+                    const int x1 = (int)fmin(fmax(floor((qx + w - g.org[0]) * g.inv[0] + 1e-9), 0.0), (double)(g.n[0] - 1));
+                    const size_t row = ((size_t)z * g.n[1] + y) * g.n[0];
+                    b = __ldg(cell_start + row + x0);
+                    e = __ldg(cell_start + row + x1 + 1);
+                }
+                sm.rows[r] = b;
+                sm.rows[DIPS_ROWCAP + r] = e;
+            }
+            __syncwarp();
+            for (int r = 0; r < nrows; ++r) {
+                const int b = sm.rows[r], e = sm.rows[DIPS_ROWCAP + r];
+                for (int j0 = b; j0 < e; j0 += 64) {              // two loads in flight per lane
+                    const int j1 = j0 + lane, j2 = j1 + 32;
+                    const bool v1 = j1 < e, v2 = j2 < e;
+                    double4 p1 = make_double4(0, 0, 0, 0), p2 = p1;
+                    if (v1) p1 = sorted[j1];
+                    if (v2) p2 = sorted[j2];
+                    visit(j1, v1, p1);
+                    if (j0 + 32 < e) visit(j2, v2, p2);
+                }
+            }
+            __syncwarp();
+        } else {
+            for (int z = lo[2]; z <= hi[2]; ++z) {
+                for (int y = lo[1]; y <= hi[1]; ++y) {
+                    const size_t row = ((size_t)z * g.n[1] + y) * g.n[0];
+                    const int b = __ldg(cell_start + row + lo[0]), e = __ldg(cell_start + row + hi[0] + 1);
+                    for (int j0 = b; j0 < e; j0 += 32) {
+                        const int j1 = j0 + lane;
+                        double4 p1 = make_double4(0, 0, 0, 0);
+                        if (j1 < e) p1 = sorted[j1];
+                        visit(j1, j1 < e, p1);
                     }
-                    const unsigned m = __ballot_sync(F4L_FULL, hit);
-                    if (hit) {
-                        const int slot = n + __popc(m & ((1u << lane) - 1u));
-                        if (slot < DIPS_CAP) sm.list[slot] = (unsigned)j;
-                    }
-                    n += __popc(m);
                 }
             }
         }
@@ -249,9 +317,8 @@ k_dips_patches(const double* __restrict__ query, int nq, const double4* __restri
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double od = __shfl_xor_sync(F4L_FULL, best_d2, o);
-            const long long oi = __shfl_xor_sync(F4L_FULL, best_i, o);
             const unsigned op = __shfl_xor_sync(F4L_FULL, best_pos, o);
-            if (od < best_d2 || (od == best_d2 && oi < best_i)) { best_d2 = od; best_i = oi; best_pos = op; }
+            if (od < best_d2 || (od == best_d2 && op < best_pos)) { best_d2 = od; best_pos = op; }
         }
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};     // rows: xp, yp, zp (= lRg^T)
         const bool framed = n > 10;                    // data_loader.py:45  ptall.shape[1] > 10
@@ -275,15 +342,22 @@ k_dips_patches(const double* __restrict__ query, int nq, const double4* __restri
             if (!(-(zx * sx + zy * sy + zz * sz) > 0.0)) { zx = -zx; zy = -zy; zz = -zz; }
             // ---- pass 2: x axis = normalised sum of alpha beta v over the neighbours (data_loader.py:60-72) ------
             double ax = 0, ay = 0, az = 0;
-            for (int t = lane; t < n; t += 32) {
-                const unsigned pos = sm.list[t];
-                if (pos == best_pos) continue;
-                const double4 p = sorted[pos];
+            auto axis_term = [&](unsigned pos, const double4& p) {
+                if (pos == best_pos) return;
                 const double dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
                 const double pz = dx * zx + dy * zy + dz * zz;
-                const double a = radius - sqrt(dips_d2(dx, dy, dz));
+                const double a = radius - dips_sqrt(dips_d2(dx, dy, dz));
                 const double w = (a * a) * (pz * pz);
                 ax += w * (dx - pz * zx); ay += w * (dy - pz * zy); az += w * (dz - pz * zz);
+            };
+            for (int t = lane; t < n; t += 64) {                     // two gathers in flight per lane
+                const unsigned pos1 = sm.list[t];
+                const bool v2 = t + 32 < n;
+                const unsigned pos2 = v2 ? sm.list[t + 32] : best_pos;
+                const double4 p1 = sorted[pos1];
+                const double4 p2 = sorted[pos2];
+                axis_term(pos1, p1);
+                axis_term(pos2, p2);
             }
             ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
             const double nrm = sqrt(ax * ax + ay * ay + az * az);
