@@ -32,7 +32,9 @@ __device__ unsigned long long g_dbg[24];   // 0: point scans, 1: exact-path scan
 #endif
 
 struct WarpIcpSmem {
-    float4 B[WICP_CAP];        // target, pivot-local, f32-rounded: ONLY for the f32 scans
+    float Bx[WICP_CAP + 2], By[WICP_CAP + 2], Bz[WICP_CAP + 2];   // target, pivot-local, f32-rounded: ONLY for the f32 scans
+                               // (SoA so that two consecutive targets are one 8-byte word of a packed operand; odd counts are
+                               // padded with a point at 1e18)
     float Bg[WICP_CAP * 3];    // target, as given (f32 global): every exact fp64 computation
     float A[WICP_CAP * 3];     // source, as given (f32 global)
     float pscan[WICP_CAP * 3]; // pivot-local position of each source point at its last scan
@@ -44,19 +46,14 @@ struct WarpIcpSmem {
 
 __device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(F4L_FULL, v, o); }
 
-// top-2 merge across the warp; every lane ends with the global (d1, j1, d2)
-__device__ __forceinline__ void warp_top2_f32(float& d1, int& j1, float& d2) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float od1 = __shfl_xor_sync(F4L_FULL, d1, o);
-        const int oj1 = __shfl_xor_sync(F4L_FULL, j1, o);
-        const float od2 = __shfl_xor_sync(F4L_FULL, d2, o);
-        const bool other_wins = od1 < d1 || (od1 == d1 && oj1 < j1);
-        const float loser = other_wins ? d1 : od1;
-        d2 = fminf(fminf(d2, od2), loser);
-        if (other_wins) { d1 = od1; j1 = oj1; }
-    }
-}
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes of fp32 per instruction)
+typedef unsigned long long u64p;
+__device__ __forceinline__ u64p pk2(float lo, float hi) { u64p r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64p v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64p sub2(u64p a, u64p b) { u64p r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p mul2(u64p a, u64p b) { u64p r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64p fma2(u64p a, u64p b, u64p c) { u64p r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 
 __device__ __forceinline__ void warp_argmin_f64(double& d, int& j) {
 #pragma unroll
@@ -81,31 +78,11 @@ __device__ __forceinline__ void warp_top2_f64(double& d1, int& j1, double& d2) {
     }
 }
 
-// Whole-warp scan for ONE query (global fp64 position pg, pivot cB): returns the exact nearest target
-// (first minimal index) and a lower bound of the distance to the second nearest distinct target.
-// f32 error budget: query and targets are rounded to f32 in the pivot-local frame (|coordinate| < 4 m
-// -> <= 1.2e-7 m each), so two candidates are safely ordered when d2 >= 1.004 d1 + 2e-8 (m^2).
-// try_f32 = false: the caller's own f32 scan already failed that test for this query.
-__device__ inline void warp_scan_point(const WarpIcpSmem& sm, int nt, const double pg[3], const double cB[3],
-                                       int lane, bool try_f32, int& jbest, float& d2lb) {
-    if (try_f32) {
-        const float qx = (float)(pg[0] - cB[0]), qy = (float)(pg[1] - cB[1]), qz = (float)(pg[2] - cB[2]);
-        float d1 = INFINITY, d2 = INFINITY;
-        int j1 = 0x7fffffff;
-        for (int j = lane; j < nt; j += 32) {
-            const float4 b = sm.B[j];
-            const float dx = qx - b.x, dy = qy - b.y, dz = qz - b.z;
-            const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (dd < d1) { d2 = d1; d1 = dd; j1 = j; }
-            else if (dd < d2) d2 = dd;
-        }
-        warp_top2_f32(d1, j1, d2);
-        if (d2 >= d1 * 1.004f + 2e-8f) {           // f32 argmin is provably the fp64 argmin
-            jbest = j1;
-            d2lb = fmaxf(sqrtf(d2) * 0.9999f - 2e-6f, 0.f);
-            return;
-        }
-    }
+// Whole-warp EXACT scan for one query (global fp64 position pg): the nearest target in fp64 (first minimal index)
+// and a lower bound of the distance to the second nearest distinct target.  Only queries whose f32 scan could
+// not separate its two best candidates come here.
+__device__ inline void warp_scan_point(const WarpIcpSmem& sm, int nt, const double pg[3], int lane, int& jbest,
+                                       float& d2lb) {
 #ifdef F4L_DEBUG_SCANS
     if (lane == 0) atomicAdd(&g_dbg[1], 1ull);
 #endif
@@ -161,7 +138,49 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
         float x, y, z;
         load_ptf(tgt, tidx, t0 + j, x, y, z);
         sm.Bg[3 * j] = x; sm.Bg[3 * j + 1] = y; sm.Bg[3 * j + 2] = z;
-        sm.B[j] = make_float4((float)((double)x - cB[0]), (float)((double)y - cB[1]), (float)((double)z - cB[2]), 0.f);
+        sm.Bx[j] = (float)((double)x - cB[0]); sm.By[j] = (float)((double)y - cB[1]); sm.Bz[j] = (float)((double)z - cB[2]);
+    }
+    if (lane == 0 && (nt & 1)) { sm.Bx[nt] = 1e18f; sm.By[nt] = 1e18f; sm.Bz[nt] = 1e18f; }
+    // Several source points are often matched to the SAME target point: a repeated target can never be the
+    // first-index nearest neighbour (its first copy is as close) and must not count as the "second nearest distinct"
+    // one, yet it would send every query near it through the exact scan (d2 == d1).  Repeats are moved out of the
+    // f32 scans' way; the fp64 arrays keep them (correspondence indices and the exact path are unchanged).
+    // (repeats are recognised by their index into the target cloud through a small open-addressing table that
+    // borrows the scan-state arrays, which are not live yet; without an index list nothing is removed)
+    if (tidx) {
+        static_assert(offsetof(WarpIcpSmem, Vw) - offsetof(WarpIcpSmem, pscan) >= 512 * 4 + 512 * 2, "dedup table must fit");
+        int* keys = reinterpret_cast<int*>(sm.pscan);
+        unsigned short* first = reinterpret_cast<unsigned short*>(keys + 512);
+        __syncwarp();
+        for (int h = lane; h < 512; h += 32) { keys[h] = -1; first[h] = 0xffffu; }
+        __syncwarp();
+        for (int j = lane; j < nt; j += 32) {
+            const int key = __ldg(tidx + t0 + j);
+            unsigned h = ((unsigned)key * 2654435761u) >> 23;
+            while (true) {
+                const int prev = atomicCAS(&keys[h], -1, key);
+                if (prev == -1 || prev == key) break;
+                h = (h + 1u) & 511u;
+            }
+            // 16-bit min through the 32-bit word that holds it
+            unsigned* w = reinterpret_cast<unsigned*>(first) + (h >> 1);
+            const unsigned sh = (h & 1u) * 16u;
+            unsigned old = *w;
+            while (((old >> sh) & 0xffffu) > (unsigned)j) {
+                const unsigned want = (old & ~(0xffffu << sh)) | ((unsigned)j << sh);
+                const unsigned got = atomicCAS(w, old, want);
+                if (got == old) break;
+                old = got;
+            }
+        }
+        __syncwarp();
+        for (int j = lane; j < nt; j += 32) {
+            const int key = __ldg(tidx + t0 + j);
+            unsigned h = ((unsigned)key * 2654435761u) >> 23;
+            while (keys[h] != key) h = (h + 1u) & 511u;
+            if (first[h] != (unsigned short)j) { sm.Bx[j] = 1e18f; sm.By[j] = 1e18f; sm.Bz[j] = 1e18f; }
+        }
+        __syncwarp();
     }
     double T[12];
 #pragma unroll
@@ -206,41 +225,58 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
         if (lane == 0) { atomicAdd(&g_dbg[0], (unsigned long long)nres); atomicAdd(&g_dbg[2], 1ull); atomicAdd(&g_dbg[3], (unsigned long long)ns); }
 #endif
         // ---- phase 2: scans ------------------------------------------------------------------
-        int nexact = nres;                 // items [0, nexact) of the list go through the whole-warp exact-capable scan
-        const bool lane_scanned = nres >= 8;
-        if (lane_scanned) {
-            // many points: one LANE per point, every lane walks all targets (broadcast reads), f32 top-2;
-            // points whose two best are within the f32 error margin are re-listed for the exact scan
-            nexact = 0;
-            for (int r0 = 0; r0 < nres; r0 += 32) {
-                const int r = r0 + lane;
+        // f32 scan of the listed points on pivot-local coordinates (targets are stored f32-rounded in that frame,
+        // |coordinate| < 4 m -> <= 1.2e-7 m each, so two candidates are safely ordered when d2 >= 1.004 d1 + 2e-8).
+        // G lanes share a point (G = 1 while >= 17 points are listed, up to 32 for a single one), each walks every
+        // G-th PAIR of targets with packed arithmetic; a candidate is the 32-bit key (bits(d^2) & ~255) | index, so
+        // the two smallest are three integer min/max and ties resolve to the lower index.  The dropped 8 mantissa
+        // bits (2^-15 relative) are covered by testing the truncated values with the factor 1.00404.
+        int nexact = 0;
+        {
+            const int lg = nres > 16 ? 0 : (nres > 8 ? 1 : (nres > 4 ? 2 : (nres > 2 ? 3 : (nres > 1 ? 4 : 5))));
+            const int G = 1 << lg, per_round = 32 >> lg;
+            const int g = lane & (G - 1), slot = lane >> lg;
+            const int npairs = (nt + 1) >> 1;
+            for (int r0 = 0; r0 < nres; r0 += per_round) {
+                const int r = r0 + slot;
                 const bool active = r < nres;
                 const int i = active ? sm.list[r] : sm.list[0];
                 const double fx = sm.A[3 * i], fy = sm.A[3 * i + 1], fz = sm.A[3 * i + 2];
                 const float qx = (float)(T[0] * fx + T[1] * fy + T[2] * fz + T[3] - cB[0]);
                 const float qy = (float)(T[4] * fx + T[5] * fy + T[6] * fz + T[7] - cB[1]);
                 const float qz = (float)(T[8] * fx + T[9] * fy + T[10] * fz + T[11] - cB[2]);
-                float d1 = INFINITY, d2 = INFINITY;
-                int j1 = 0;
+                const u64p qx2 = pk2(qx, qx), qy2 = pk2(qy, qy), qz2 = pk2(qz, qz);
+                unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;
 #pragma unroll 4
-                for (int j = 0; j < nt; ++j) {
-                    const float4 b = sm.B[j];
-                    const float dx = qx - b.x, dy = qy - b.y, dz = qz - b.z;
-                    const float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    const bool better = dd < d1;
-                    d2 = better ? d1 : fminf(d2, dd);
-                    j1 = better ? j : j1;
-                    d1 = better ? dd : d1;
+                for (int p = g; p < npairs; p += G) {
+                    const u64p bx = *reinterpret_cast<const u64p*>(&sm.Bx[2 * p]);
+                    const u64p by = *reinterpret_cast<const u64p*>(&sm.By[2 * p]);
+                    const u64p bz = *reinterpret_cast<const u64p*>(&sm.Bz[2 * p]);
+                    const u64p dx = sub2(qx2, bx), dy = sub2(qy2, by), dz = sub2(qz2, bz);
+                    const u64p dd = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float da, db;
+                    upk2(dd, da, db);
+                    const unsigned ka = (__float_as_uint(da) & 0xffffff00u) | (unsigned)(2 * p);
+                    const unsigned kb = (__float_as_uint(db) & 0xffffff00u) | (unsigned)(2 * p + 1);
+                    k2 = min(k2, max(k1, ka)); k1 = min(k1, ka);
+                    k2 = min(k2, max(k1, kb)); k1 = min(k1, kb);
                 }
-                const bool certain = d2 >= d1 * 1.004f + 2e-8f;
-                if (active && certain) {
-                    sm.jstar[i] = (unsigned short)j1;
-                    sm.d2lb[i] = fmaxf(sqrtf(d2) * 0.9999f - 2e-6f, 0.f);
+                for (int o = 1; o < G; o <<= 1) {
+                    const unsigned o1 = __shfl_xor_sync(F4L_FULL, k1, o), o2 = __shfl_xor_sync(F4L_FULL, k2, o);
+                    k2 = min(min(k2, o2), max(k1, o1));
+                    k1 = min(k1, o1);
+                }
+                const float v1 = __uint_as_float(k1 & 0xffffff00u), v2 = __uint_as_float(k2 & 0xffffff00u);
+                const bool certain = v2 >= v1 * 1.00404f + 2e-8f;
+                const bool writer = active && g == 0;
+                if (writer && certain) {
+                    sm.jstar[i] = (unsigned short)(k1 & 0xffu);
+                    sm.d2lb[i] = fmaxf(sqrtf(v2) * 0.9999f - 2e-6f, 0.f);
                     sm.pscan[3 * i] = qx; sm.pscan[3 * i + 1] = qy; sm.pscan[3 * i + 2] = qz;
                 }
                 __syncwarp();
-                const unsigned m = __ballot_sync(F4L_FULL, active && !certain);
-                if (active && !certain) sm.list[nexact + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;   // in place: nexact <= r0
+                const unsigned m = __ballot_sync(F4L_FULL, writer && !certain);
+                if (writer && !certain) sm.list[nexact + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;   // in place: nexact <= r0
                 nexact += __popc(m);
                 __syncwarp();
             }
@@ -255,7 +291,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
             pg[2] = T[8] * fx + T[9] * fy + T[10] * fz + T[11];
             int jb;
             float lb;
-            warp_scan_point(sm, nt, pg, cB, lane, !lane_scanned, jb, lb);
+            warp_scan_point(sm, nt, pg, lane, jb, lb);
             if (lane == 0) {
                 sm.jstar[i] = (unsigned short)jb;
                 sm.d2lb[i] = lb;
@@ -328,6 +364,9 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
 // balanced; distances use sqrt.approx.f32 (<= 1 ulp; the reference's own cdist carries ~1e-3 m of
 // GEMM-formulation noise at these coordinates).
 __device__ __forceinline__ float sqrt_approx(float x) {
+#ifdef F4L_EXP_NO_SQRT
+    return x;            // timing experiment only
+#endif
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // ftz: one MUFU, no denormal rescaling (d^2 < 1e-38 m^2 -> 0)
     return r;
@@ -343,13 +382,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // (step A: lo = row i, hi = row i+1; step B: lo = row i+1, hi = row i) so no register moves are needed.
 // The arena holds the six coordinate arrays twice over (cyclic access without a wrap test); it aliases the
 // ICP staging area, which is filled after the check.
-typedef unsigned long long u64p;
-__device__ __forceinline__ u64p pk2(float lo, float hi) { u64p r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(u64p v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64p sub2(u64p a, u64p b) { u64p r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64p mul2(u64p a, u64p b) { u64p r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64p fma2(u64p a, u64p b, u64p c) { u64p r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
 struct RigRows { u64p ax, ay, az, bx, by, bz; };      // the lane's two rows, packed (lo, hi)
 
 // one step: lo pair = (rows.lo, window.lo), hi pair = (rows.hi, window.hi); (s_lo, c_lo) / (s_hi, c_hi) collect them
