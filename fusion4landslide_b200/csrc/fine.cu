@@ -184,6 +184,7 @@ k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tg
             float* arena = reinterpret_cast<float*>(&sm);          // aliases the ICP staging area (filled later)
             warp_rigidity_stage(arena, src_pts, tgt_pts, cs, ct, k0, k, lane);
             __syncwarp();
+            DBG_T(17)
             double sum;
             unsigned cnt;
             warp_rigidity(arena, k, prm.thres_dist_diff, lane, sum, cnt);

@@ -46,6 +46,28 @@ struct WarpIcpSmem {
 
 __device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(F4L_FULL, v, o); }
 
+// Gather 4 rounds of 32 points (items base + 32u + lane of the list k0.., u < 4) with every load of the batch in
+// flight before the first use: indices first, then the 12 coordinate words -- the staging loops are pure
+// latency (index -> point, both usually L2 misses) and a round-by-round loop serialises them.
+struct Gather4 {
+    float x[4], y[4], z[4];
+};
+__device__ __forceinline__ void gather4(const float* __restrict__ pts, const int32_t* __restrict__ idx, int k0, int base,
+                                        int n, int lane, Gather4& gq) {
+    size_t row[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        const int k = k0 + (i < n ? i : 0);
+        row[u] = idx ? (size_t)__ldg(idx + k) : (size_t)k;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float* p = pts + row[u] * 3;
+        gq.x[u] = __ldg(p); gq.y[u] = __ldg(p + 1); gq.z[u] = __ldg(p + 2);
+    }
+}
+
 // packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes of fp32 per instruction)
 typedef unsigned long long u64p;
 __device__ __forceinline__ u64p pk2(float lo, float hi) { u64p r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -129,16 +151,27 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
         load_ptf(tgt, tidx, t0, x, y, z);
         cB[0] = x; cB[1] = y; cB[2] = z;
     }
-    for (int i = lane; i < ns; i += 32) {
-        float x, y, z;
-        load_ptf(src, sidx, s0 + i, x, y, z);
-        sm.A[3 * i] = x; sm.A[3 * i + 1] = y; sm.A[3 * i + 2] = z;
+    for (int base = 0; base < ns; base += 128) {
+        Gather4 a;
+        gather4(src, sidx, s0, base, ns, lane, a);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            if (i < ns) { sm.A[3 * i] = a.x[u]; sm.A[3 * i + 1] = a.y[u]; sm.A[3 * i + 2] = a.z[u]; }
+        }
     }
-    for (int j = lane; j < nt; j += 32) {
-        float x, y, z;
-        load_ptf(tgt, tidx, t0 + j, x, y, z);
-        sm.Bg[3 * j] = x; sm.Bg[3 * j + 1] = y; sm.Bg[3 * j + 2] = z;
-        sm.Bx[j] = (float)((double)x - cB[0]); sm.By[j] = (float)((double)y - cB[1]); sm.Bz[j] = (float)((double)z - cB[2]);
+    for (int base = 0; base < nt; base += 128) {
+        Gather4 b;
+        gather4(tgt, tidx, t0, base, nt, lane, b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = base + 32 * u + lane;
+            if (j < nt) {
+                const float x = b.x[u], y = b.y[u], z = b.z[u];
+                sm.Bg[3 * j] = x; sm.Bg[3 * j + 1] = y; sm.Bg[3 * j + 2] = z;
+                sm.Bx[j] = (float)((double)x - cB[0]); sm.By[j] = (float)((double)y - cB[1]); sm.Bz[j] = (float)((double)z - cB[2]);
+            }
+        }
     }
     if (lane == 0 && (nt & 1)) { sm.Bx[nt] = 1e18f; sm.By[nt] = 1e18f; sm.Bz[nt] = 1e18f; }
     // Several source points are often matched to the SAME target point: a repeated target can never be the
@@ -414,17 +447,23 @@ __device__ inline void warp_rigidity_stage(float* arena, const float* __restrict
                                            const int32_t* __restrict__ cs, const int32_t* __restrict__ ct, int k0, int n,
                                            int lane) {
     const int L = rig_arena_stride(n);
-    for (int i = lane; i < n; i += 32) {
-        const int s0 = rig_slot(i, n), s1 = rig_slot(i + n, n);
-        float x, y, z;
-        load_ptf(src_pts, cs, k0 + i, x, y, z);
-        arena[s0] = x; arena[s1] = x;
-        arena[L + s0] = y; arena[L + s1] = y;
-        arena[2 * L + s0] = z; arena[2 * L + s1] = z;
-        load_ptf(tgt_pts, ct, k0 + i, x, y, z);
-        arena[3 * L + s0] = x; arena[3 * L + s1] = x;
-        arena[4 * L + s0] = y; arena[4 * L + s1] = y;
-        arena[5 * L + s0] = z; arena[5 * L + s1] = z;
+    for (int base = 0; base < n; base += 128) {
+        Gather4 a, b;
+        gather4(src_pts, cs, k0, base, n, lane, a);
+        gather4(tgt_pts, ct, k0, base, n, lane, b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            if (i < n) {
+                const int s0 = rig_slot(i, n), s1 = rig_slot(i + n, n);
+                arena[s0] = a.x[u]; arena[s1] = a.x[u];
+                arena[L + s0] = a.y[u]; arena[L + s1] = a.y[u];
+                arena[2 * L + s0] = a.z[u]; arena[2 * L + s1] = a.z[u];
+                arena[3 * L + s0] = b.x[u]; arena[3 * L + s1] = b.x[u];
+                arena[4 * L + s0] = b.y[u]; arena[4 * L + s1] = b.y[u];
+                arena[5 * L + s0] = b.z[u]; arena[5 * L + s1] = b.z[u];
+            }
+        }
     }
     if (lane < 24) arena[(lane >> 2) * L + rig_slot(2 * n + (lane & 3), n)] = 0.f;     // the window may read 3 words past 2n
 }

@@ -22,7 +22,7 @@ if hasattr(L, 'f4l_debug_counters'):
     L.f4l_debug_counters(buf, 1)
     v = list(buf)
     print('scans', v[0], 'exact', v[1], 'iterations(matches)', v[2], 'points*iters', v[3], 'scan frac', v[0] / max(v[3], 1), 'mean moved um', v[4] / max(v[2], 1))
-    names = {8: 'rigidity', 9: 'procrustes', 10: 'icp stage', 11: 'phase1 keep-check', 12: 'lane scans', 13: 'exact scans', 14: 'phase3 moments', 15: 'update svd', 16: 'total'}
+    names = {17: 'rigidity staging', 8: 'rigidity', 9: 'procrustes', 10: 'icp stage', 11: 'phase1 keep-check', 12: 'lane scans', 13: 'exact scans', 14: 'phase3 moments', 15: 'update svd', 16: 'total'}
     tot = max(v[16], 1)
     for k_, n_ in names.items():
         print('  %-20s %8.1f kcycles/patch  %5.1f%%' % (n_, v[k_] / 3136 / 1e3, 100.0 * v[k_] / tot))
