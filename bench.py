@@ -146,6 +146,7 @@ def algorithmic_bytes(name, q):
         # A1 (medres.cu) handles BOTH epochs per launch.  search: every float4 row once as reference and once as
         # query (12N + 12M + 8kN with N = M per epoch, k = 2 -> 40 B/point; the kernel moves 16 + 4)
         "k_a1_search": 40 * (N + M),
+        "k_a1_search_tiled": 40 * (N + M),
         "k_a1_bbox": 12 * (N + M),
         "k_a1_count": 12 * (N + M),
         "k_a1_scatter": (12 + 16) * (N + M),

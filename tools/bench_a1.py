@@ -29,8 +29,9 @@ for n in a.n:
     k = dict(LAST_KERNELS)
     nn = s.shape[0] + tg.shape[0]
     rec = {"ms_total": ms, "points_per_s": nn / ms * 1e3, "kernels_ms": k, "median_resolution": float(ops.median_resolution(s, tg))}
-    if "k_a1_search" in k:
-        rec["search_frac_of_hbm (40 B/pt)"] = 40 * nn / (k["k_a1_search"] * 1e-3) / 1e9 / peak
+    sk = "k_a1_search_tiled" if "k_a1_search_tiled" in k else "k_a1_search"
+    if sk in k:
+        rec["search_frac_of_hbm (40 B/pt)"] = 40 * nn / (k[sk] * 1e-3) / 1e9 / peak
         rec["scatter_frac_of_hbm (28 B/pt)"] = 28 * nn / (k["k_a1_scatter"] * 1e-3) / 1e9 / peak
         rec["pipeline_frac_of_hbm (80 B/pt)"] = 80 * nn / (ms * 1e-3) / 1e9 / peak
     out["sizes"][str(n)] = rec
