@@ -241,7 +241,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
                     const double pz = T[8] * fx + T[9] * fy + T[10] * fz + T[11];
                     const int js = sm.jstar[i];
                     const double dx = px - (double)sm.Bg[3 * js], dy = py - (double)sm.Bg[3 * js + 1], dz = pz - (double)sm.Bg[3 * js + 2];
-                    const float dnow = (float)sqrt(dx * dx + dy * dy + dz * dz) * 1.00001f + 1e-7f;
+                    const float dnow = sqrtf((float)(dx * dx + dy * dy + dz * dz)) * 1.00001f + 1e-7f;   // upper bound: the f32 root's 6e-8 is inside the 1e-5 margin
                     const float mx = (float)(px - cB[0]) - sm.pscan[3 * i], my = (float)(py - cB[1]) - sm.pscan[3 * i + 1],
                                 mz = (float)(pz - cB[2]) - sm.pscan[3 * i + 2];
                     const float moved = sqrtf(mx * mx + my * my + mz * mz) * 1.00001f + 1e-6f;
