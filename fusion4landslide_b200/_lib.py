@@ -47,6 +47,7 @@ class FineBuffers(ctypes.Structure):
         ("ratio_inlier", c_void_p), ("dist_mean", c_void_p),
         ("dense", c_void_p), ("sparse", c_void_p), ("tgt2src", c_void_p), ("counts", c_void_p),
         ("n_peers", c_i32), ("peer_dense", c_void_p * MAX_PEERS),
+        ("sparse_pair_rows", c_void_p),
     ]
 
 
@@ -98,6 +99,7 @@ SIGNATURES = {
     "f4l_dips_patches": (c_int, [P, c_i32, c_i32, c_f64, c_i32, P, ctypes.c_uint64, P, P, P, P, c_size, P]),
     "f4l_fine_matching_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),
     "f4l_fine_matching": (c_int, [ctypes.POINTER(FineParams), ctypes.POINTER(FineBuffers), P, c_size, P]),
+    "f4l_host_expand_sparse": (ctypes.c_longlong, [P, P, c_i32, P, c_i32]),
 }
 
 

@@ -103,3 +103,42 @@ extern "C" void f4l_profile_reset(void) {
     for (auto& m : g_marks) g_pool.push_back(m.ev);
     g_marks.clear();
 }
+
+// ---- host-side helper of the host-buffer API --------------------------------------------------
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+extern "C" long long f4l_host_expand_sparse(const float* h_once, const int32_t* h_pair_rows, int32_t Q, float* h_out,
+                                            int32_t n_threads) {
+    if (!h_once || !h_pair_rows || !h_out || Q <= 0) return 0;
+    std::vector<long long> off((size_t)Q + 1, 0);
+    for (int q = 0; q < Q; ++q) off[q + 1] = off[q] + (h_pair_rows[q] > 0 ? h_pair_rows[q] : 0);
+    const long long total = off[Q];
+    if (total == 0) return 0;
+    int nt = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+    if (total < 4096) nt = 1;
+    auto work = [&](int t) {
+        // pairs are dealt in contiguous blocks of roughly equal row counts
+        const long long lo = total * t / nt, hi = total * (t + 1) / nt;
+        int q = (int)(std::upper_bound(off.begin(), off.end(), lo) - off.begin()) - 1;
+        for (; q < Q && off[q] < hi; ++q) {
+            if (off[q] < lo) continue;                  // the pair belongs to the thread that owns its first row
+            const size_t n = (size_t)(off[q + 1] - off[q]) * 6 * sizeof(float);
+            const float* src = h_once + (size_t)off[q] * 6;
+            float* dst = h_out + (size_t)off[q] * 12;
+            std::memcpy(dst, src, n);
+            std::memcpy(dst + (size_t)(off[q + 1] - off[q]) * 6, src, n);
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    return 2 * total;
+}

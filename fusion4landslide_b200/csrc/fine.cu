@@ -372,7 +372,7 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             R[i * 3] = Tq[i * 4]; R[i * 3 + 1] = Tq[i * 4 + 1]; R[i * 3 + 2] = Tq[i * 4 + 2];
             tv[i] = Tq[i * 4 + 3];
         }
-        const bool assign_nn = prm.assign_type == 1;
+        const bool assign_nn = prm.assign_type >= 1;
         const bool staged = nt <= AA_SMEM_PTS;
         if (tid == 0) { s_cnt = 0; s_maxabs = 0u; }
         if (tid < 6) s_bb[tid] = tid < 3 ? 0xffffffffu : 0u;
@@ -548,7 +548,7 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             kept = warp_sum(kept);
             if ((tid & 31) == 0 && kept) atomicAdd(&s_cnt, kept);
             __syncthreads();
-            if (tid == 0) sparse_cnt[q] = 2 * s_cnt;          // appended twice (q4)
+            if (tid == 0) sparse_cnt[q] = (prm.assign_type == 2 ? 1 : 2) * s_cnt;   // appended twice (q4) unless the host repeats them
         } else if (tid == 0) {
             sparse_cnt[q] = K[q];                              // assign_all_src: the matched points
         }
@@ -569,9 +569,10 @@ k_emit_sparse(const float* __restrict__ src_pts, const float* __restrict__ tgt_p
     const int total = sparse_cnt[q];
     if (total == 0) return;
     const int o0 = sparse_off[q];
-    if (prm.assign_type == 1) {
+    if (prm.assign_type >= 1) {
         const int s0 = sp_ptr[q], ns = sp_ptr[q + 1] - s0, t0 = tp_ptr[q];
-        const int half = total >> 1;
+        const int reps = prm.assign_type == 2 ? 1 : 2;
+        const int half = total / reps;
         int written = 0;
         for (int i0 = 0; i0 < ns; i0 += 32) {
             const int i = i0 + lane;
@@ -583,7 +584,7 @@ k_emit_sparse(const float* __restrict__ src_pts, const float* __restrict__ tgt_p
                 load_ptf(src_pts, sp_idx, s0 + i, x, y, z);
                 load_ptf(tgt_pts, tp_idx, t0 + j, gx, gy, gz);
 #pragma unroll
-                for (int rep = 0; rep < 2; ++rep) {
+                for (int rep = 0; rep < reps; ++rep) {
                     float2* row = reinterpret_cast<float2*>(sparse + (size_t)(o0 + rep * half + r) * 6);
                     row[0] = make_float2(x, y);
                     row[1] = make_float2(z, gx);
@@ -705,6 +706,8 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
                                                         bf->rmse, w.dense_off, w.t2s_off, Q, *prm,
                                                         bf->d_median_resolution, bf->dense, bf->tgt2src, w.nn,
                                                         w.sparse_cnt, bf->n_peers, peers);
+    if (bf->sparse_pair_rows)
+        cudaMemcpyAsync(bf->sparse_pair_rows, w.sparse_cnt, (size_t)Q * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     f4l_mark("k_sparse_offsets", st);
     k_sparse_offsets<<<1, 1024, 0, st>>>(w.sparse_cnt, Q, w.sparse_off, bf->counts);
     f4l_mark("k_emit_sparse", st);

@@ -281,7 +281,7 @@ def piecewise_icp(src64, tgt64, smax, number_points_min, internal_min_points=250
 class FineResult:
     """Outputs of the fused fine-matching stage (device tensors; row counts in `counts`)."""
     __slots__ = ("T", "T64", "status", "K", "fitness", "rmse", "iters", "ratio_inlier", "dist_mean",
-                 "dense", "sparse", "tgt2src", "counts")
+                 "dense", "sparse", "tgt2src", "counts", "sparse_pair_rows")
 
     def rows(self):
         """Host sync: slice the row buffers to their true lengths (dense, sparse, tgt2src)."""
@@ -291,7 +291,7 @@ class FineResult:
 
 
 _MODES = {"only_3d": 0, "only_2d": 1, "fusion": 2}
-_ASSIGN = {"assign_all_src": 0, "assign_then_nn": 1}
+_ASSIGN = {"assign_all_src": 0, "assign_then_nn": 1, "assign_then_nn_once": 2}
 
 
 def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_point, pair_tgt_patch,
@@ -326,6 +326,7 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
         r.sparse = torch.empty((2 * n_src_items, 6), dtype=F32, device=dev)
         r.tgt2src = torch.empty((n_tgt_items, 6), dtype=F32, device=dev) if output_tgt2src else None
         r.counts = torch.empty((4,), dtype=I32, device=dev)
+        r.sparse_pair_rows = torch.empty((Q,), dtype=I32, device=dev) if assign_type == "assign_then_nn_once" else None
     prm = _lib.FineParams(_MODES[mode], int(remove_low_quality_patch_matches), int(num_min_matches_for_quality_check),
                           float(thres_dist_diff), float(thres_inlier_ratio), int(num_min_fine_match), int(icp_refine),
                           _ASSIGN[assign_type], int(output_tgt2src), float(icp_threshold),
@@ -340,6 +341,9 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
         ptr(r.T), ptr(r.T64), ptr(r.status), ptr(r.K), ptr(r.fitness), ptr(r.rmse), ptr(r.iters),
         ptr(r.ratio_inlier), ptr(r.dist_mean), ptr(r.dense), ptr(r.sparse),
         ptr(r.tgt2src, F32, True), ptr(r.counts))
+    spr = getattr(r, "sparse_pair_rows", None)
+    if spr is not None:
+        bf.sparse_pair_rows = ptr(spr, I32)
     if peer_dense:
         if len(peer_dense) > _lib.MAX_PEERS:
             raise _lib.F4LError("at most %d peers" % _lib.MAX_PEERS)
@@ -385,3 +389,12 @@ def dips_patches(index, query64, num_points=256, ranks=None, seed=0, want_lrf=Fa
     if want_lrf:
         return patches, count, lrf
     return patches, count
+
+
+def host_expand_sparse(once, pair_rows, out, n_threads=4):
+    """HOST tensors: restore the reference's per-pair doubled sparse layout (base.py:3430,3436) from rows emitted
+    once (assign_type "assign_then_nn_once").  once (R,6) f32, pair_rows (Q) i32, out (>= 2R,6) f32.  Returns rows."""
+    if once.is_cuda or pair_rows.is_cuda or out.is_cuda:
+        raise F4LError("host_expand_sparse works on host tensors")
+    return int(lib().f4l_host_expand_sparse(once.data_ptr(), pair_rows.data_ptr(), int(pair_rows.numel()),
+                                            out.data_ptr(), int(n_threads)))

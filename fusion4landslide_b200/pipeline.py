@@ -173,9 +173,20 @@ class HostPipeline:
     copies of one tile overlapping the kernels of the others (one side stream per slot).  Row counts are read
     back per tile (a stream-local synchronisation) so that only the rows that exist cross PCIe."""
 
-    def __init__(self, host_tiles, cfg=None, device="cuda:0", n_streams=4, want_sparse=True):
+    def __init__(self, host_tiles, cfg=None, device="cuda:0", n_streams=4, want_sparse=True, sparse_once=False,
+                 expand_threads=8):
+        """sparse_once: the reference appends every pair's sparse rows twice (base.py:3430,3436); with this option
+        the kernels emit them once and host threads restore the doubled layout while later tiles are in flight
+        (same bytes in the returned tensors, a third less device->host traffic).  OFF by default: measured on the
+        B200 box the DMA engines move the second copy at 56 GB/s while host threads rebuild it at ~14 GB/s
+        (tools/exp_e2e.py: 25.2 ms vs 22.6 ms per 16 tiles) -- it only pays on hosts with a slow PCIe link."""
         self.host_tiles = host_tiles
         self.cfg = cfg or FineConfig()
+        self.sparse_once = bool(sparse_once and want_sparse and self.cfg.fine_kwargs().get("assign_type") == "assign_then_nn")
+        self.pool = None
+        if self.sparse_once:
+            import concurrent.futures
+            self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, int(expand_threads)))
         self.dev = torch.device(device)
         self.streams = make_streams(n_streams, self.dev)
         self.want_sparse = want_sparse
@@ -189,6 +200,9 @@ class HostPipeline:
                  "median_resolution": torch.empty((1,), dtype=torch.float32).pin_memory()}
             if want_sparse:
                 o["sparse"] = torch.empty((2 * n_s, 6), dtype=torch.float32).pin_memory()
+            if self.sparse_once:
+                o["sparse_once"] = torch.empty((n_s, 6), dtype=torch.float32).pin_memory()
+                o["pair_rows"] = torch.empty((q,), dtype=torch.int32).pin_memory()
             self.out.append(o)
 
     def run(self):
@@ -198,6 +212,11 @@ class HostPipeline:
             s.wait_stream(cur)
         h2d = d2h = 0
         pending = []
+        self._expanding = []
+        self._futures = []
+        kw = dict(self.cfg.fine_kwargs())
+        if self.sparse_once:
+            kw["assign_type"] = "assign_then_nn_once"
         for i, ht in enumerate(self.host_tiles):
             st = self.streams[i % len(self.streams)]
             with torch.cuda.stream(st):
@@ -208,9 +227,14 @@ class HostPipeline:
                     setattr(t, k, v.to(self.dev, non_blocking=True))
                     h2d += v.numel() * v.element_size()
                 t.n_src_items, t.n_tgt_items, t.n_pairs = ht.meta
-                r, med = displacement_field(t, self.cfg)
+                med = ops.median_resolution(t.src, t.tgt)
+                r = ops.fine_matching(t.src, t.tgt, t.sp_idx, t.sp_ptr, t.tp_idx, t.tp_ptr, t.tgt_patch_of_point,
+                                      t.pair_tgt_patch, corr3d=t.corr3d, corr2d=t.corr2d, d_median_resolution=med,
+                                      n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items, **kw)
                 o = self.out[i]
                 o["counts"].copy_(r.counts, non_blocking=True)
+                if self.sparse_once:
+                    o["pair_rows"].copy_(r.sparse_pair_rows, non_blocking=True)
                 o["median_resolution"].copy_(med, non_blocking=True)
                 o["T"].copy_(r.T, non_blocking=True)
                 o["status"].copy_(r.status, non_blocking=True)
@@ -225,14 +249,24 @@ class HostPipeline:
         for s in self.streams:
             cur.wait_stream(s)
         cur.synchronize()
+        for item in self._expanding:                       # tiles whose sparse copy was still in flight
+            self._expand(*item)
+        if self.pool is not None:
+            for f in self._futures:
+                f.result()
         res = []
         for o in self.out:
             c = o["counts"].tolist()
             v = {"dense": o["dense"][:c[0]], "T": o["T"], "status": o["status"], "median_resolution": o["median_resolution"]}
             if self.want_sparse:
-                v["sparse"] = o["sparse"][:c[1]]
+                v["sparse"] = o["sparse"][:(2 * c[1] if self.sparse_once else c[1])]
             res.append(v)
         return res, h2d, d2h
+
+    def _expand(self, i, ev, rows):
+        ev.synchronize()
+        o = self.out[i]
+        self._futures.append(self.pool.submit(ops.host_expand_sparse, o["sparse_once"][:rows], o["pair_rows"], o["sparse"], 2))
 
     def _drain(self, item):
         i, st, ev, r, t = item
@@ -240,10 +274,19 @@ class HostPipeline:
         o = self.out[i]
         c = o["counts"].tolist()
         n = 4 * 4 + 4 + o["T"].numel() * 4 + o["status"].numel()
+        # the previous tile's sparse rows have landed by now: hand them to the host threads
+        while self._expanding and self._expanding[0][1].query():
+            self._expand(*self._expanding.pop(0))
         with torch.cuda.stream(st):
             o["dense"][:c[0]].copy_(r.dense[:c[0]], non_blocking=True)
             n += c[0] * 24
-            if self.want_sparse:
+            if self.sparse_once:
+                o["sparse_once"][:c[1]].copy_(r.sparse[:c[1]], non_blocking=True)
+                n += c[1] * 24 + o["pair_rows"].numel() * 4
+                ev2 = torch.cuda.Event()
+                ev2.record(st)
+                self._expanding.append((i, ev2, c[1]))
+            elif self.want_sparse:
                 o["sparse"][:c[1]].copy_(r.sparse[:c[1]], non_blocking=True)
                 n += c[1] * 24
             # keep the device tensors alive until the copies are done

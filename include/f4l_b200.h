@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define F4L_ABI_VERSION 2
+#define F4L_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define F4L_API __attribute__((visibility("default")))
@@ -180,7 +180,8 @@ typedef struct f4l_fine_params {
     float thres_inlier_ratio;     /* method.thres_inlier_ratio */
     int32_t num_min_fine_match;   /* method.num_min_fine_match */
     int32_t icp_refine;           /* method.icp_refine */
-    int32_t assign_type;          /* 0 assign_all_src, 1 assign_then_nn */
+    int32_t assign_type;          /* 0 assign_all_src, 1 assign_then_nn, 2 assign_then_nn with every kept row
+                                     emitted ONCE (the host layer repeats them, f4l_host_expand_sparse) */
     int32_t output_tgt2src;       /* method.output_tgt2src */
     double icp_threshold;         /* parameter_setting.icp_threshold */
     double median_max_resolution; /* para.median_max_resolution (base.py:2751) */
@@ -219,12 +220,21 @@ typedef struct f4l_fine_buffers {
        NVLink, tile by tile.  n_peers == 0: no exchange. */
     int32_t n_peers;
     float* peer_dense[F4L_MAX_PEERS];
+    int32_t* sparse_pair_rows;   /* (Q) or NULL: sparse rows emitted per pair (what f4l_host_expand_sparse needs) */
 } f4l_fine_buffers;
 
 F4L_API size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t n_tgt_items, int32_t Q,
                                          int32_t mode);
 F4L_API int f4l_fine_matching(const f4l_fine_params* h_params, const f4l_fine_buffers* h_buffers,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* HOST function (host pointers, no CUDA): the reference appends the sparse rows of a pair twice
+ * (base.py:3430,3436).  A caller that moves results over PCIe runs the path with
+ * assign_type 2 -- every kept row once, h_pair_rows[q] rows for pair q, pairs back to back -- and restores the
+ * reference layout on the host: out = [rows of pair 0][rows of pair 0][rows of pair 1][rows of pair 1]...
+ * h_out holds 2 * sum(h_pair_rows) rows of 6 floats.  Uses up to n_threads host threads.  Returns the rows written. */
+F4L_API long long f4l_host_expand_sparse(const float* h_once, const int32_t* h_pair_rows, int32_t Q, float* h_out,
+                                 int32_t n_threads);
 
 /* ------------------------------------------------------------------------------------------
  * (b) exact descriptor-space nearest neighbour, D in {32, 64}, on tensor cores.      kernel K-b

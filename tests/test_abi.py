@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert not untyped, untyped
     extra = [n for n in _lib.SIGNATURES if n not in names]
     assert not extra, extra
-    assert L.f4l_abi_version() == 2
+    assert L.f4l_abi_version() == 3
     assert L.f4l_launch_count() >= 0
 
 
@@ -58,3 +58,29 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_host_expand_sparse_restores_doubled_layout():
+    """f4l_host_expand_sparse is a HOST function (no GPU): rows emitted once per pair -> the reference's
+    [pair rows][pair rows] layout (base.py:3430,3436), any thread count, empty pairs included."""
+    import numpy as np
+    from fusion4landslide_b200 import ops
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 40, 500).astype(np.int32)
+    counts[[0, 7, 499]] = 0
+    total = int(counts.sum())
+    once = rng.normal(size=(total, 6)).astype(np.float32)
+    want = []
+    off = 0
+    for c in counts:
+        blk = once[off:off + c]
+        want += [blk, blk]
+        off += c
+    want = np.concatenate(want)
+    for nt in (1, 3, 16):
+        out = torch.zeros((2 * total + 5, 6))
+        n = ops.host_expand_sparse(torch.from_numpy(once), torch.from_numpy(counts), out, n_threads=nt)
+        assert n == 2 * total
+        np.testing.assert_array_equal(out[:n].numpy(), want)
+        assert not out[n:].any()
+    assert ops.host_expand_sparse(torch.zeros((0, 6)), torch.zeros(4, dtype=torch.int32), torch.zeros((0, 6))) == 0

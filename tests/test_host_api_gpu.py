@@ -257,3 +257,21 @@ def test_piecewise_icp_entry_point(cuda, tmp_path):
     np.testing.assert_allclose(dvfs, o["dvfs"], atol=1e-9)
     np.testing.assert_allclose(dvfms, o["dvfms"], atol=1e-9)
     assert vis[0, 3] == 0 and vis[1, 3] == 5 and np.allclose(vis[2:], o["dvfms"][2:], atol=1e-9)
+
+
+def test_host_pipeline_sparse_once_equals_doubled(cuda):
+    """HostPipeline with the sparse rows crossing PCIe once (+ host expansion) returns the same tensors as the
+    path that moves both copies."""
+    from fusion4landslide_b200 import pipeline, synth
+    tiles = []
+    for s in range(3):
+        d = synth.make_tile(30_000 + 5000 * s, seed=40 + s, device=cuda, patch_pts=200)
+        tiles.append(pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"]))
+    hts = [pipeline.HostTile(t) for t in tiles]
+    a, _, da = pipeline.HostPipeline(hts, None, cuda, n_streams=2, sparse_once=False).run()
+    b, _, db = pipeline.HostPipeline(hts, None, cuda, n_streams=2, sparse_once=True, expand_threads=3).run()
+    assert db < da
+    for x, y in zip(a, b):
+        assert x["sparse"].shape == y["sparse"].shape and x["sparse"].shape[0] > 0
+        for k in ("dense", "sparse", "T", "status", "median_resolution"):
+            assert torch.equal(x[k], y[k]), k
