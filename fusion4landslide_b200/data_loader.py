@@ -12,7 +12,7 @@ import torch
 from . import ops
 from ._lib import F4LError
 
-DIPS_CAP = 2048
+DIPS_CAP = 1408
 
 
 def _cloud(x, device):

@@ -366,7 +366,7 @@ F4L_API int f4l_peer_enable_access(int32_t peer_device);
  *                  (ties by original index; a rank >= the neighbour count selects a zero row), i.e. the
  *                  reference's `ptall[inds]`.
  * lrf (n_query,9) f64 or NULL: rows xp, yp, zp of the frame (zeros when no frame was estimated);
- * count (n_query) i32: neighbours found.  More than 2048 neighbours is outside the supported range: the patch
+ * count (n_query) i32: neighbours found.  More than 1408 neighbours is outside the supported range: the patch
  * is zero-filled and count reports the size. */
 F4L_API size_t f4l_dips_workspace_bytes(int32_t n_ref);
 F4L_API int f4l_dips_build(const double* ref64, int32_t n_ref, double radius, void* workspace,
