@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(256) k_a1_scatter(A1Args a) {
 }
 
 // ---- stage 4: 2nd-neighbour distance of every point + level-1 histogram ------------------------
-__global__ void __launch_bounds__(128) k_a1_search(A1Args a) {
+#ifndef A1S_MIN_BLOCKS
+#define A1S_MIN_BLOCKS 10     // 48 registers, 40 warps per SM: ~5 % on the search (long-scoreboard bound)
+#endif
+__global__ void __launch_bounds__(128, A1S_MIN_BLOCKS) k_a1_search(A1Args a) {
     __shared__ int sh[A1_BINS];
     const int e = blockIdx.y;
     const int n = e ? a.n1 : a.n0;
