@@ -324,12 +324,16 @@ k_sparse_offsets(const int32_t* __restrict__ sparse_cnt, int Q, int32_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------
-#define AA_THREADS 256
+#ifndef AA_THREADS
+#define AA_THREADS 128     // a pair has ~250 source points: 2 per thread; small CTAs interleave better across pairs
+#endif
 #ifndef AA_MIN_BLOCKS
-#define AA_MIN_BLOCKS 4      // 64 registers: 4 CTAs per SM (measured +2.8 % on the step; 5 spills too much)
+#define AA_MIN_BLOCKS 8      // 64 registers, 8 CTAs of 128 threads per SM (measured +4 % on the step over 4 x 256)
 #endif
 struct PeerDense { float* p[F4L_MAX_PEERS]; };
-#define AA_SMEM_PTS 2048
+#ifndef AA_SMEM_PTS
+#define AA_SMEM_PTS 1024    // staged target patch (16 KB); larger patches are scanned from global memory
+#endif
 
 // D5 + A4.  CTA per pair.  The target patch is staged in shared memory as pivot-local float4 (|coordinate|
 // of a patch is metres, so f32 keeps ~1e-7 m), binned on a small uniform grid (patch_grid.cuh: counting sort
@@ -436,7 +440,11 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             const float bmx[3] = {ord2f(s_bb[3]), ord2f(s_bb[4]), ord2f(s_bb[5])};
             grid = make_patch_grid(bmn, bmx, nt, 16);
             const int ncells = grid.ncu * grid.ncv;
-            s_fill[tid] = 0;
+            // the grid has at most 256 cells; a thread owns AA_CPT consecutive ones
+            constexpr int AA_CPT = 256 / AA_THREADS;
+            static_assert(AA_CPT * AA_THREADS == 256 && AA_CPT >= 1, "AA_THREADS must divide 256");
+#pragma unroll
+            for (int u = 0; u < AA_CPT; ++u) s_fill[tid * AA_CPT + u] = 0;
             __syncthreads();
             for (int j = tid; j < nt; j += AA_THREADS) {
                 float x, y, z;
@@ -444,7 +452,9 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
                 atomicAdd(&s_fill[pg_cell(grid, (float)((double)x - cB[0]), (float)((double)y - cB[1]), (float)((double)z - cB[2]))], 1);
             }
             __syncthreads();
-            const int cnt = s_fill[tid];
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < AA_CPT; ++u) cnt += s_fill[tid * AA_CPT + u];
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -456,9 +466,14 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             int before = 0;
 #pragma unroll
             for (int w = 0; w < AA_THREADS / 32; ++w) before += (w < (tid >> 5)) ? s_wsum[w] : 0;
-            const int excl = before + inc - cnt;
-            s_start[tid] = excl;
-            s_fill[tid] = excl;
+            int run = before + inc - cnt;
+#pragma unroll
+            for (int u = 0; u < AA_CPT; ++u) {
+                const int c = s_fill[tid * AA_CPT + u];
+                s_start[tid * AA_CPT + u] = run;
+                s_fill[tid * AA_CPT + u] = run;
+                run += c;
+            }
             if (tid == 0) s_start[256] = nt;
             __syncthreads();
             for (int j = tid; j < nt; j += AA_THREADS) {

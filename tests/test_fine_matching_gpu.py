@@ -41,10 +41,13 @@ def _ulp(x):
     return np.spacing(np.abs(x).astype(np.float32)).astype(np.float64)
 
 
-@pytest.mark.parametrize("assign,tgt2src", [("assign_then_nn", True), ("assign_all_src", False)])
-def test_fine_matching_vs_oracle(cuda, assign, tgt2src):
+# patch_pts 1400: more matched pairs than the warp kernel takes (CTA fit kernel) and target patches larger than
+# the shared-memory staging area of the assign kernel (global-memory path)
+@pytest.mark.parametrize("assign,tgt2src,patch_pts", [("assign_then_nn", True, 200), ("assign_all_src", False, 200),
+                                                      ("assign_then_nn", True, 1400)])
+def test_fine_matching_vs_oracle(cuda, assign, tgt2src, patch_pts):
     from fusion4landslide_b200 import ops
-    d, spt_src, spt_tgt, g = _setup(80_000, 31, 200, cuda)
+    d, spt_src, spt_tgt, g = _setup(80_000, 31, patch_pts, cuda)
     med = oknn.median_resolution(d["src"].numpy(), d["tgt"].numpy())
     prm = ofm.FineParams(mode="only_3d", assign_type=assign, output_tgt2src=tgt2src, median_max_resolution=med)
     o = ofm.fine_matching(d["src"].numpy(), d["tgt"].numpy(), d["corr3d"].numpy(), None, spt_src, spt_tgt, prm)
