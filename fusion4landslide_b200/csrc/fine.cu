@@ -153,9 +153,11 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
 // ------------------------------------------------------------------------------------------
 // Small pairs (K <= WICP_CAP matched points): the whole fit by ONE warp -- stage the matched pairs
 // in the warp's shared-memory slice, rigidity check, Procrustes, ICP loop (icp_warp.cuh).
+#ifndef FITW_WARPS
 #define FITW_WARPS 4
+#endif
 #ifndef FITW_MIN_BLOCKS
-#define FITW_MIN_BLOCKS 4
+#define FITW_MIN_BLOCKS (16 / FITW_WARPS)
 #endif
 __global__ void __launch_bounds__(FITW_WARPS * 32, FITW_MIN_BLOCKS)
 k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
@@ -701,7 +703,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
     k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
                                                    bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
                                                    prm->mode, w.cs, w.ct, w.kstart, bf->K);
-    const int grid_w = f4l_div_up(Q, FITW_WARPS) < 148 * 8 ? f4l_div_up(Q, FITW_WARPS) : 148 * 8;
+    const int grid_w = f4l_div_up(Q, FITW_WARPS) < 148 * 32 / FITW_WARPS ? f4l_div_up(Q, FITW_WARPS) : 148 * 32 / FITW_WARPS;
     f4l_mark("k_patch_fit_warp", st);
     k_patch_fit_warp<<<grid_w, FITW_WARPS * 32, FITW_WARPS * sizeof(WarpIcpSmem), st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q, *prm,
                                                         bf->T, bf->T64, bf->status, bf->fitness, bf->rmse, bf->iters,
