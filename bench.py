@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="side streams for tile-level concurrency (1 = serial)")
+    ap.add_argument("--a1-overlap", type=int, default=1, help="1: A1 of a tile runs on a side stream next to its rigid fits")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the exchange (N > 1)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -251,9 +252,10 @@ def run_b200(a):
         gathered_counts = torch.empty((world * n_tiles_max * 4,), dtype=torch.int32, device=dev)
 
     streams = pipeline.make_streams(a.streams, dev) if a.streams > 1 else None
+    sides = pipeline.make_streams(a.streams, dev) if (a.streams > 1 and a.a1_overlap) else None
 
     def step_tiles(par=0):
-        pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par])
+        pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par], side_streams=sides)
 
     # The per-tile launch sequence is static (all buffers preallocated, no host round trip inside the path):
     # capture one step -- all tiles, all side streams -- into a CUDA graph and replay it (one graph per
@@ -458,7 +460,7 @@ def run_b200(a):
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
                              (sum(t.nbytes() for t in tiles) * world / 1e9),
                        "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type, "streams": a.streams,
-                       "cuda_graph": graph is not None},
+                       "cuda_graph": graph is not None, "a1_side_stream": bool(sides)},
             "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline,
             "kernels": kernel_table, "cpu_baseline": cpu, "breakdown": breakdown,
         }

@@ -47,7 +47,7 @@ class FineBuffers(ctypes.Structure):
         ("ratio_inlier", c_void_p), ("dist_mean", c_void_p),
         ("dense", c_void_p), ("sparse", c_void_p), ("tgt2src", c_void_p), ("counts", c_void_p),
         ("n_peers", c_i32), ("peer_dense", c_void_p * MAX_PEERS),
-        ("sparse_pair_rows", c_void_p),
+        ("sparse_pair_rows", c_void_p), ("median_ready_event", c_void_p),
     ]
 
 

@@ -717,6 +717,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
     k_row_offsets<<<1, 1024, 0, st>>>(bf->status, bf->sp_ptr, bf->tp_ptr, Q, prm->icp_refine ? 1 : 0, w.dense_off,
                                       w.t2s_off, bf->counts);
     const int grid_aa = Q < 148 * 8 ? Q : 148 * 8;
+    if (bf->median_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)bf->median_ready_event, 0);
     f4l_mark("k_apply_assign", st);
     k_apply_assign<<<grid_aa, AA_THREADS, smem_aa, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
                                                         bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T,

@@ -300,7 +300,7 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
                   num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
                   output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
                   d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None,
-                  peer_dense=None):
+                  peer_dense=None, median_event=None):
     """Fused fine-matching stage of one tile (f4l_fine_matching).  n_*_items = sp_ptr[-1], tp_ptr[-1]
     (pass them to avoid a device->host read).  peer_dense: device pointers (ints) of the slot of `out.dense`
     in every peer GPU's exchange buffer (exchange.PeerExchange); the D5 kernel stores each dense row there too."""
@@ -341,6 +341,8 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
         ptr(r.T), ptr(r.T64), ptr(r.status), ptr(r.K), ptr(r.fitness), ptr(r.rmse), ptr(r.iters),
         ptr(r.ratio_inlier), ptr(r.dist_mean), ptr(r.dense), ptr(r.sparse),
         ptr(r.tgt2src, F32, True), ptr(r.counts))
+    if median_event is not None:
+        bf.median_ready_event = int(median_event.cuda_event)      # d_median_resolution comes from another stream
     spr = getattr(r, "sparse_pair_rows", None)
     if spr is not None:
         bf.sparse_pair_rows = ptr(spr, I32)

@@ -62,15 +62,29 @@ def prepare_tile(src, tgt, label_src, label_tgt, corr3d, corr2d=None, min_pts=10
     return t
 
 
-def displacement_field(tile, cfg=None, out=None, med_out=None, peer_dense=None):
+def displacement_field(tile, cfg=None, out=None, med_out=None, peer_dense=None, side_stream=None):
     """The hot path on one tile, device -> device, no host synchronisation.
-    Returns (FineResult, median_resolution device scalar).  peer_dense: see ops.fine_matching."""
+    Returns (FineResult, median_resolution device scalar).  peer_dense: see ops.fine_matching.
+    side_stream: run A1 there, concurrently with correspondence selection and the rigid fits of the same tile
+    (only the assign step needs the resolution; the library waits for it in-stream)."""
     cfg = cfg or FineConfig()
-    med = ops.median_resolution(tile.src, tile.tgt, out=med_out)                          # A1
+    ev = None
+    if side_stream is None:
+        med = ops.median_resolution(tile.src, tile.tgt, out=med_out)                      # A1
+    else:
+        cur = torch.cuda.current_stream(tile.src.device)
+        if med_out is None:
+            med_out = torch.empty((1,), dtype=torch.float32, device=tile.src.device)
+        side_stream.wait_stream(cur)
+        with torch.cuda.stream(side_stream):
+            med = ops.median_resolution(tile.src, tile.tgt, out=med_out)
+            ev = torch.cuda.Event()
+            ev.record(side_stream)
     r = ops.fine_matching(tile.src, tile.tgt, tile.sp_idx, tile.sp_ptr, tile.tp_idx, tile.tp_ptr,
                           tile.tgt_patch_of_point, tile.pair_tgt_patch, corr3d=tile.corr3d,
                           corr2d=tile.corr2d, d_median_resolution=med, n_src_items=tile.n_src_items,
-                          n_tgt_items=tile.n_tgt_items, out=out, peer_dense=peer_dense, **cfg.fine_kwargs())
+                          n_tgt_items=tile.n_tgt_items, out=out, peer_dense=peer_dense, median_event=ev,
+                          **cfg.fine_kwargs())
     return r, med
 
 
@@ -80,7 +94,7 @@ def make_streams(n, device):
     return [torch.cuda.Stream(device=device) for _ in range(max(1, int(n)))]
 
 
-def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None):
+def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None, side_streams=None):
     """The hot path over many tiles.  With `streams`, tile i runs on streams[i % n]: the small kernels and the
     tail of one tile's patch loop overlap with the next tile's work.  The caller's current stream waits for all
     of them at the end, so events recorded around this call time the whole batch.  `peers[i]`: peer pointers
@@ -116,7 +130,8 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
             with torch.cuda.stream(streams[i % len(streams)]):
                 res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
                                               med_out=None if meds is None else meds[i:i + 1],
-                                              peer_dense=None if peers is None else peers[i]))
+                                              peer_dense=None if peers is None else peers[i],
+                                              side_stream=None if not side_streams else side_streams[i % len(side_streams)]))
     for s in streams:
         cur.wait_stream(s)
     return res

@@ -221,6 +221,9 @@ typedef struct f4l_fine_buffers {
     int32_t n_peers;
     float* peer_dense[F4L_MAX_PEERS];
     int32_t* sparse_pair_rows;   /* (Q) or NULL: sparse rows emitted per pair (what f4l_host_expand_sparse needs) */
+    void* median_ready_event;    /* cudaEvent_t or NULL: d_median_resolution is produced on ANOTHER stream (A1 is
+                                    independent of correspondence selection and the rigid fits); the library makes
+                                    `stream` wait for this event right before the first kernel that reads it */
 } f4l_fine_buffers;
 
 F4L_API size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t n_tgt_items, int32_t Q,
