@@ -66,6 +66,33 @@ def compute_median_resolution(src_pts, tgt_pts):
     return ops.median_resolution(_dev_f32(src_pts), _dev_f32(tgt_pts))
 
 
+def voxel_down_sample(pts, voxel_size):
+    """Open3D `pcd.voxel_down_sample(voxel_size)` (base.py:1024-1025) for an (n,3) array / tensor / Open3D cloud:
+    fp64 voxel means, rows in ascending voxel order (Open3D's order is its hash map's; same rows)."""
+    import numpy as np
+    if hasattr(pts, "points"):
+        pts = np.asarray(pts.points)
+    if isinstance(pts, np.ndarray):
+        pts = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
+    dev = pts.device if pts.is_cuda else torch.device("cuda:0")
+    return ops.voxel_downsample(pts.to(device=dev, dtype=torch.float64).contiguous(), voxel_size)
+
+
+def voxel_subsampling(src_pts, tgt_pts):
+    """`Coarse2Fine_Base._voxel_subsampling` (base.py:1012-1057) on tensors: adaptive voxel size = median resolution,
+    voxel means of both epochs, nearest raw point of every voxel and the inverse maps.  Returns a dict with the
+    reference's field names."""
+    voxel = float(compute_median_resolution(src_pts, tgt_pts).item())
+    out = {"voxel_size": voxel}
+    for name, p in (("src", src_pts), ("tgt", tgt_pts)):
+        sub = voxel_down_sample(p, voxel).float()
+        v2p, p2v = voxel_subsampling_maps(sub, p)
+        out[name + "_pts_sub"] = sub
+        out["idx_voxel2pts_" + name] = v2p
+        out["idx_pts2voxel_" + name] = p2v
+    return out
+
+
 def voxel_subsampling_maps(pts_sub, pts_raw):
     """idx_voxel2pts (N_sub,) = nearest raw point of every voxel centroid, idx_pts2voxel (N,) = inverse map with
     -1 default (base.py:1038-1057; duplicate targets: the largest voxel index wins, like a sequential scatter)."""

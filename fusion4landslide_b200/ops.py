@@ -400,3 +400,23 @@ def host_expand_sparse(once, pair_rows, out, n_threads=4):
         raise F4LError("host_expand_sparse works on host tensors")
     return int(lib().f4l_host_expand_sparse(once.data_ptr(), pair_rows.data_ptr(), int(pair_rows.numel()),
                                             out.data_ptr(), int(n_threads)))
+
+
+def voxel_downsample(pts64, voxel_size, want_map=False):
+    """Open3D voxel_down_sample (base.py:1024-1025) on the GPU: (n,3) f64 -> centroids (V,3) f64 in ascending voxel
+    order [, voxel_of_point (n) i32].  One host read (the voxel count sizes the returned view)."""
+    if pts64.dtype != F64:
+        raise F4LError("voxel_downsample: points must be float64 (Open3D works on doubles)")
+    n = int(pts64.shape[0])
+    cent = _empty((max(n, 1), 3), F64, pts64)
+    vop = _empty((n,), I32, pts64) if want_map else None
+    counts = _empty((1,), I32, pts64)
+    nbytes = lib().f4l_voxel_downsample_workspace_bytes(n)
+    ws = _workspace(nbytes, pts64.device)
+    check(lib().f4l_voxel_downsample(ptr(pts64, F64) if n else None, n, float(voxel_size), ptr(cent, F64),
+                                     ptr(vop, I32, True), ptr(counts, I32), ptr(ws), ws.numel(),
+                                     stream_ptr(pts64.device)), "f4l_voxel_downsample")
+    v = int(counts.item())
+    if v < 0:
+        raise F4LError("voxel_downsample: the cloud spans more than 2^21 voxels along an axis")
+    return (cent[:v], vop) if want_map else cent[:v]

@@ -378,6 +378,18 @@ F4L_API int f4l_dips_patches(const double* query64, int32_t n_query, int32_t n_r
                    int32_t num_points, const int32_t* ranks, uint64_t seed, float* patches, double* lrf,
                    int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 8(f) rank 3 -- voxel subsampling.  Replaces Open3D PointCloud.voxel_down_sample as called at
+ * base.py:1024-1025 (_voxel_subsampling) and :906-907: voxel_min_bound = min_bound - voxel_size/2, voxel index
+ * floor((p - voxel_min_bound)/voxel_size), output = fp64 mean of the points of every occupied voxel (summed in point
+ * order).  pts64 (n,3) f64 -> centroids (>= number of voxels, 3) f64 in ascending (ix,iy,iz) voxel order (Open3D:
+ * unordered_map order, i.e. the same rows permuted), voxel_of_point (n) i32 or NULL = output row of every input
+ * point, counts[0] (device) = number of voxels, or -1 when the cloud spans more than 2^21 voxels along an axis. */
+F4L_API size_t f4l_voxel_downsample_workspace_bytes(int32_t n);
+F4L_API int f4l_voxel_downsample(const double* pts64, int32_t n, double voxel_size, double* centroids,
+                         int32_t* voxel_of_point, int32_t* counts, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,7 +90,12 @@ def main():
         rec("f4l_knn_grid cross k=1 N=M=%d (bin + search)" % n, ms, 12 * n + 12 * n + 8 * n, {"queries_per_s": n / ms * 1e3})
         ms = timed(lambda: ops.median_resolution(s, tg), a.reps, flush)
         rec("f4l_median_resolution N=M=%d" % n, ms, 2 * (24 * n + 16 * n), {"points_per_s": 2 * n / ms * 1e3})
-        del d
+        s64 = s.double().contiguous()
+        nv = ops.voxel_downsample(s64, 0.1).shape[0]
+        ms = timed(lambda: ops.voxel_downsample(s64, 0.1, want_map=True), a.reps, flush)
+        # 24 B per point in, 4 B map out, 24 B per voxel out (the sort passes are extra traffic on top)
+        rec("f4l_voxel_downsample N=%d (%d voxels of 0.1 m)" % (n, nv), ms, 28 * n + 24 * nv, {"points_per_s": n / ms * 1e3})
+        del d, s64
     print(json.dumps({"hbm_peak_gbs": peak, "kernels": out}, indent=1))
 
 
