@@ -66,6 +66,43 @@ def compute_median_resolution(src_pts, tgt_pts):
     return ops.median_resolution(_dev_f32(src_pts), _dev_f32(tgt_pts))
 
 
+def _pixels_xyz0(p, device):
+    """(n,2) pixel coordinates -> (n,3) f32 device points with z = 0 (the grid kNN does not bin a flat axis)."""
+    import numpy as np
+    if isinstance(p, np.ndarray):
+        p = torch.from_numpy(np.ascontiguousarray(p))
+    p = p.to(device=device, dtype=torch.float32)
+    return torch.cat([p[:, :2], torch.zeros((p.shape[0], 1), dtype=torch.float32, device=device)], 1).contiguous()
+
+
+def map_corr_2d_to_3d(corres_2d, src_pixel, tgt_pixel, pixel_thres, reverse=False):
+    """`map_corr_2d_to_3d` (base.py:387-427; rgb_guided.py:590-639): lift image matches to projected 3D points.
+    Every projected source point takes its nearest match in the source image (2-D), follows it to the target image
+    and takes the nearest projected target point there; both hops must be shorter than `pixel_thres` pixels.
+    corres_2d (K,4) [u_src, v_src, u_tgt, v_tgt]; src_pixel (N,2), tgt_pixel (M,2).  Returns device tensors
+    (index into tgt_pixel (N,) i64, mask (N,) bool, matched rows of corres_2d (N,4) f64).  Two exact grid-kNN
+    launches replace the two cKDTree builds + queries; pixel coordinates are compared in f32.
+    reverse=True is `map_corr_2d_to_3d_tgt2src` (base.py:431-472)."""
+    import numpy as np
+    dev = src_pixel.device if (torch.is_tensor(src_pixel) and src_pixel.is_cuda) else torch.device("cuda:0")
+    c = torch.from_numpy(np.ascontiguousarray(corres_2d, dtype=np.float64)) if isinstance(corres_2d, np.ndarray) else corres_2d
+    c = c.to(device=dev, dtype=torch.float64)
+    a, b = (tgt_pixel, src_pixel) if reverse else (src_pixel, tgt_pixel)
+    ca, cb = (c[:, 2:4], c[:, :2]) if reverse else (c[:, :2], c[:, 2:4])
+    i1, d1 = ops.knn_grid(_pixels_xyz0(a, dev), _pixels_xyz0(ca, dev), 1)
+    rows = c[i1[:, 0].long()]
+    hop = (rows[:, :2] if reverse else rows[:, 2:4])
+    i2, d2 = ops.knn_grid(_pixels_xyz0(hop, dev), _pixels_xyz0(b, dev), 1)
+    thr2 = float(pixel_thres) ** 2
+    mask = (d1[:, 0] < thr2) & (d2[:, 0] < thr2)
+    return i2[:, 0].long(), mask, rows
+
+
+def map_corr_2d_to_3d_tgt2src(corres_2d, src_pixel, tgt_pixel, pixel_thres):
+    """base.py:431-472: the same lifting from the target image to the source image."""
+    return map_corr_2d_to_3d(corres_2d, src_pixel, tgt_pixel, pixel_thres, reverse=True)
+
+
 def voxel_down_sample(pts, voxel_size):
     """Open3D `pcd.voxel_down_sample(voxel_size)` (base.py:1024-1025) for an (n,3) array / tensor / Open3D cloud:
     fp64 voxel means, rows in ascending voxel order (Open3D's order is its hash map's; same rows)."""

@@ -18,6 +18,8 @@ What gets pinned (reference function -> golden file):
   torch.cdist rigidity expression of base.py:3310-3317             -> rigidity_cdist.npz
   src/data_loader.py Preprocess_Dataset.extract_patch, with a cKDTree stand-in for the one Open3D
       class it uses (KDTreeFlann.search_radius_vector_3d)          -> dips_patches.npz
+  src/coarse_to_fine_matching_base.py map_corr_2d_to_3d, map_corr_2d_to_3d_tgt2src
+      (scipy cKDTree, present here)                                -> map_corr_2d.npz
 Open3D ICP / Octree, hnswlib and faiss cannot be run anywhere here -> no golden, parity unpinned.
 """
 import os
@@ -291,12 +293,38 @@ def make_dips():
                         inds=inds, patches=out, count=np.asarray(sizes, np.int32), lrf=lrf)
 
 
+def make_lifting():
+    """src/coarse_to_fine_matching_base.py map_corr_2d_to_3d / map_corr_2d_to_3d_tgt2src, unmodified."""
+    base = ref_shim.ref_base()
+    from oracle import lifting as olift
+    rng = np.random.default_rng(33)
+    W, H = 640.0, 800.0                                   # a crop: keeps the fixture small at realistic densities
+    n_match, n_src, n_tgt = 4000, 3000, 8000
+    m_src = rng.uniform(0, [W, H], (n_match, 2))
+    m_tgt = m_src + rng.normal(0, 6.0, (n_match, 2)) + np.array([12.0, -7.0])
+    corres_2d = np.round(np.hstack([m_src, m_tgt]), 3)                       # np.loadtxt of "%.3f" files
+    src_pixel = torch.from_numpy(rng.uniform(0, [W, H], (n_src, 2)).astype(np.float32))
+    tgt_pixel = torch.from_numpy((rng.uniform(0, [W, H], (n_tgt, 2))).astype(np.float32))
+    thres = 5.0
+    i_f, m_f, r_f = base.map_corr_2d_to_3d(corres_2d, src_pixel, tgt_pixel, thres)
+    i_r, m_r, r_r = base.map_corr_2d_to_3d_tgt2src(corres_2d, src_pixel, tgt_pixel, thres)
+    oi, om, orow = olift.map_corr_2d_to_3d(corres_2d, src_pixel.numpy(), tgt_pixel.numpy(), thres)
+    assert np.array_equal(oi, i_f) and np.array_equal(om, m_f) and np.array_equal(orow, r_f)
+    oi, om, orow = olift.map_corr_2d_to_3d(corres_2d, src_pixel.numpy(), tgt_pixel.numpy(), thres, reverse=True)
+    assert np.array_equal(oi, i_r) and np.array_equal(om, m_r) and np.array_equal(orow, r_r)
+    print("lifting: %d / %d source points and %d / %d target points lifted; oracle == reference" %
+          (int(m_f.sum()), n_src, int(m_r.sum()), n_tgt))
+    np.savez_compressed(os.path.join(GOLD, "map_corr_2d.npz"), corres_2d=corres_2d, src_pixel=src_pixel.numpy(),
+                        tgt_pixel=tgt_pixel.numpy(), thres=np.array([thres]), idx_fwd=i_f.astype(np.int64), mask_fwd=m_f,
+                        rows_fwd=r_f, idx_rev=i_r.astype(np.int64), mask_rev=m_r, rows_rev=r_r)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)
     makers = dict(rigid=make_rigid, f2s3_filter=make_f2s3_filter, knn=make_knn, desc=make_desc,
-                  rigidity=make_rigidity, dips=make_dips)
+                  rigidity=make_rigidity, dips=make_dips, lifting=make_lifting)
     for name in (sys.argv[1:] or list(makers)):          # `python -m oracle.make_golden dips` refreshes one file
         makers[name]()
     for f in sorted(os.listdir(GOLD)):

@@ -42,6 +42,28 @@ class _Anything(types.ModuleType):
         return _Anything(self.__name__ + "()")
 
 
+class _StubFinder:
+    """Last-resort import hook: any submodule of a package that is absent from this image (Open3D, the
+    superpoint_transformer submodule, image matchers ...) resolves to a permissive stand-in, so that
+    src/coarse_to_fine_matching_base.py can be imported for its module-level functions."""
+    roots = ("superpoint_transformer", "open3d", "cpp_core", "matplotlib", "romatch", "hydra", "omegaconf", "kornia",
+             "cv2", "pycolmap", "pyproj", "laspy", "plyfile", "hnswlib", "faiss", "easydict", "coloredlogs", "colorhash")
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        if name.split(".")[0] in self.roots:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _Anything(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
 
@@ -50,6 +72,8 @@ def load():
     """Make `import src.functions`, `import scripts.weighted_svd` ... resolve to the reference."""
     if not available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.append(_StubFinder())          # before the loop: stubbed packages must be PACKAGES
     for name in _STUBS:
         if name not in sys.modules:
             try:
@@ -63,6 +87,12 @@ def load():
         sys.modules["easydict"].EasyDict = EasyDict
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+
+
+def ref_base():
+    """src/coarse_to_fine_matching_base.py (module-level functions: map_corr_2d_to_3d, ...)."""
+    load()
+    return importlib.import_module("src.coarse_to_fine_matching_base")
 
 
 def ref_functions():

@@ -109,3 +109,15 @@ def test_dips_oracle_matches_reference_golden(golden_dir):
     np.testing.assert_array_equal(cnt, z["count"])
     np.testing.assert_allclose(out, z["patches"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(lrf, z["lrf"], rtol=0, atol=1e-12)
+
+
+def test_lifting_oracle_matches_reference_golden(golden_dir):
+    """oracle/lifting.py against the reference's own map_corr_2d_to_3d / _tgt2src (make_golden.make_lifting)."""
+    from oracle import lifting as olift
+    z = np.load(os.path.join(golden_dir, "map_corr_2d.npz"))
+    for rev, tag in ((False, "fwd"), (True, "rev")):
+        i, m, rows = olift.map_corr_2d_to_3d(z["corres_2d"], z["src_pixel"], z["tgt_pixel"], float(z["thres"][0]), reverse=rev)
+        np.testing.assert_array_equal(i, z["idx_" + tag])
+        np.testing.assert_array_equal(m, z["mask_" + tag])
+        np.testing.assert_array_equal(rows, z["rows_" + tag])
+        assert 0 < m.sum() < m.size
