@@ -131,6 +131,23 @@ def ncu_traffic(kernel):
     return best
 
 
+def ncu_metrics(kernel, names):
+    """Selected metrics of `kernel` from the newest committed ncu --set full summary under profiles/ (context for a
+    kernel that is not memory-bound: issue-slot and pipe utilisation), {} when there is none."""
+    import glob
+    import re
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_%s.txt" % kernel))):
+        found = {}
+        for line in open(path):
+            m = re.match(r"\s*(\S+)\s+([0-9.]+)\s*(\S*)", line)
+            if m and m.group(1) in names and m.group(1) not in found:
+                found[m.group(1)] = float(m.group(2))
+        if found:
+            out = dict(found, source=os.path.basename(path))
+    return out
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -435,6 +452,15 @@ def run_b200(a):
                     "note": "kernel durations from in-stream CUDA events in a separate profiled (single-stream) pass of the "
                             "same step; this kernel is FP/issue-bound (K^2 rigidity + the on-chip ICP loop: ncu DRAM < 1 % of "
                             "peak, issue slots ~50 %), so its HBM fraction is small by construction -- see DESIGN.md section 4"}
+        ctx = ncu_metrics(top, ("smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+                                "sm__warps_active.avg.pct_of_peak_sustained_active",
+                                "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                                "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                                "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+                                "smsp__inst_executed.sum"))
+        if ctx:
+            roofline["ncu_context"] = ctx          # from the committed capture, not measured in this run
         # also report the two kernels the north star names (kNN search, Kabsch/ICP reduction)
         for name in ("k_a1_search", "k_a1_scatter", "k_a1_count", "k_a1_bbox", "k_patch_fit_warp", "k_patch_fit",
                      "k_apply_assign"):
