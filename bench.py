@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="side streams for tile-level concurrency (1 = serial)")
+    ap.add_argument("--workload", default="c5", choices=["c5", "dips"],
+                    help="c5: the headline hot path (default).  dips: the DIPs patch front-end of SURVEY 8(f) rank 1 "
+                         "(one 625 k-point tile-epoch per step) with its own metric and CPU leg")
+    ap.add_argument("--dips-pts", type=int, default=625_000)
+    ap.add_argument("--dips-cpu-queries", type=int, default=300)
     ap.add_argument("--a1-overlap", type=int, default=1, help="1: A1 of a tile runs on a side stream next to its rigid fits")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the exchange (N > 1)")
@@ -528,6 +533,84 @@ def cpu_arm_sample(a, tile, cfg, target_seconds=15.0, workers=None, pairs=None):
             "seconds": secs}
 
 
+def run_dips(a):
+    """--workload dips: DIPs patch front-end (src/data_loader.py:16-109) at tile scale, single GPU.
+    One step = index build + (n,3,256) patches of every point of one C3-shaped tile-epoch (625 k points at 0.1 m
+    spacing, feature radius sqrt(3)*10*resolution, ~850 neighbours per point).  cpu_baseline: oracle/dips.py (numpy +
+    cKDTree, one core -- the reference's own per-point loop shape) on a bounded sample of the same queries."""
+    import numpy as np
+    import torch
+    from fusion4landslide_b200 import _lib, ops, synth
+    dev = torch.device("cuda:0")
+    peak, peak_src = load_peaks()
+    n = a.dips_pts
+    batch = 125_000
+    d = synth.make_tile(n, seed=3, device=dev)
+    ref = d["src"].double().contiguous()
+    radius = float(np.sqrt(3) * 10 * 0.1)
+    L = _lib.lib()
+    out = torch.empty((batch, 3, 256), dtype=torch.float32, device=dev)
+
+    def step():
+        index = ops.DipsIndex(ref, radius)
+        cnt = []
+        for off in range(0, n, batch):
+            q = ref[off:off + batch]
+            cnt.append(ops.dips_patches(index, q, 256, seed=off, out=out[:q.shape[0]])[1])
+        return torch.cat(cnt)
+
+    for _ in range(max(a.warmup, 1)):
+        cnt = step()
+    torch.cuda.synchronize()
+    L.f4l_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = int(L.f4l_launch_count())
+    ms = e0.elapsed_time(e1) / a.steps
+    L.f4l_profile_reset(); L.f4l_profile_enable(1)
+    step()
+    torch.cuda.synchronize()
+    L.f4l_profile_enable(0)
+    kern = {k: {"ms_total": round(v[0], 4), "launches": v[1]} for k, v in _lib.profile_table().items()}
+    kms = kern.get("k_dips_patches", {}).get("ms_total", ms)
+    alg = n * (24 + 3 * 256 * 4)
+    line = {"metric": "dips_patches_per_sec", "value": n / (ms * 1e-3), "unit": "patches/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (f32 out)", "data": "synthetic",
+            "config": {"workload": "DIPs front-end: 1 tile-epoch of %d points (cloud = queries), radius %.3f m, 256-point patches"
+                                   % (n, radius), "neighbours_mean": float(cnt.float().mean()), "neighbours_max": int(cnt.max()),
+                       "l2": "3 KB written per point (1.9 GB per step) exceeds the L2"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": "k_dips_patches", "bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": (ncu_traffic("k_dips_patches") or [None])[0],
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "note": "24 B in + 3*256*4 B out per point; the kernel is FP64 / latency-bound today"},
+            "kernels": kern}
+    if not a.no_cpu_baseline:
+        import time
+        from scipy.spatial import cKDTree
+        from oracle import dips as odips
+        refn = ref.cpu().numpy()
+        rng = np.random.default_rng(0)
+        pick = rng.choice(n, a.dips_cpu_queries, replace=False)
+        tree = cKDTree(refn)
+        t0 = time.perf_counter()
+        for q in refn[pick]:
+            pa, _, _ = odips.extract_all(q, tree, refn, radius)
+            odips.sample(pa, rng.permutation(max(pa.shape[0], 256))[:256])
+        t_q = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": a.dips_cpu_queries / t_q, "unit": "patches/s", "cores": 1, "kind": "port",
+                                "sample": "%d queries of the same tile (oracle/dips.py: numpy + cKDTree, tree build excluded)" % a.dips_cpu_queries}
+    print(json.dumps(line))
+
+
 def run_reference(a):
     """--impl reference: the CPU arm alone, on this box's host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -562,5 +645,7 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "dips":
+        run_dips(args)
     else:
         run_b200(args)
