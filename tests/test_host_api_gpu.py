@@ -302,3 +302,23 @@ def test_map_corr_2d_to_3d_golden(cuda, golden_dir):
         assert ((idx == z["idx_" + tag]) | tie).all()
         assert ((mask == z["mask_" + tag]) | tie | edge).all()
         assert tie.mean() < 1e-3 and edge.mean() < 1e-3
+
+
+def test_displacement_field_side_stream_equals_serial(cuda):
+    """A1 on a side stream (median_ready_event in the C ABI: the library waits in-stream before the assign kernel)
+    gives bit-identical results to the serial order, also with many tiles over several streams."""
+    from fusion4landslide_b200 import pipeline, synth
+    tiles = []
+    for s in range(4):
+        d = synth.make_tile(40_000, seed=60 + s, device=cuda, patch_pts=220)
+        tiles.append(pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"]))
+    base = [pipeline.displacement_field(t) for t in tiles]
+    torch.cuda.synchronize()
+    streams, sides = pipeline.make_streams(2, cuda), pipeline.make_streams(2, cuda)
+    got = pipeline.displacement_field_tiles(tiles, streams=streams, side_streams=sides)
+    torch.cuda.synchronize()
+    for (r0, m0), (r1, m1) in zip(base, got):
+        assert m0.item() == m1.item()
+        d0, s0, _ = r0.rows()
+        d1, s1, _ = r1.rows()
+        assert torch.equal(d0, d1) and torch.equal(s0, s1) and torch.equal(r0.T64, r1.T64)
