@@ -256,10 +256,11 @@ def run_b200(a):
                 r.dist_mean = torch.empty((Q,), dtype=torch.float32, device=dev)
                 r.sparse = torch.empty((2 * t.n_src_items, 6), dtype=torch.float32, device=dev)
                 r.tgt2src = None
+                r.sparse_pair_rows = None
                 r.counts = counts_arena[i]
             else:                                           # parity 1 differs only in the dense arena
                 for k in FineResult.__slots__:
-                    setattr(r, k, getattr(outs_par[0][i], k))
+                    setattr(r, k, getattr(outs_par[0][i], k, None))
             r.dense = arena[ro:ro + t.n_src_items]
             outs.append(r)
             peers.append(ex.peer_ptrs(par, ro) if fused else None)
