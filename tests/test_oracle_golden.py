@@ -121,3 +121,27 @@ def test_lifting_oracle_matches_reference_golden(golden_dir):
         np.testing.assert_array_equal(m, z["mask_" + tag])
         np.testing.assert_array_equal(rows, z["rows_" + tag])
         assert 0 < m.sum() < m.size
+
+
+def test_voxel_oracle_equals_sequential_hash_map_loop():
+    """oracle/voxel.py (vectorised) against a literal transcription of Open3D's VoxelDownSample loop: a hash map from
+    the integer voxel index to (sum, count), filled point by point; bit-equal means, same membership."""
+    import math
+    from oracle import voxel as ovox
+    rng = np.random.default_rng(4)
+    pts = np.vstack([rng.uniform(-3, 7, (4000, 3)), np.round(rng.uniform(-3, 7, (500, 3)) / 0.25) * 0.25])
+    for voxel in (0.25, 0.4, 3.0):
+        cent, inv = ovox.voxel_down_sample(pts, voxel)
+        vmb = pts.min(0) - voxel * 0.5
+        acc = {}
+        for p in pts:
+            key = tuple(int(math.floor((p[c] - vmb[c]) / voxel)) for c in range(3))
+            s_, n_ = acc.get(key, (np.zeros(3), 0))
+            acc[key] = (s_ + p, n_ + 1)
+        keys = sorted(acc)
+        assert len(keys) == cent.shape[0]
+        want = np.array([acc[k][0] / acc[k][1] for k in keys])
+        np.testing.assert_array_equal(cent, want)
+        row_of = {k: i for i, k in enumerate(keys)}
+        got_rows = [row_of[tuple(int(math.floor((p[c] - vmb[c]) / voxel)) for c in range(3))] for p in pts]
+        np.testing.assert_array_equal(inv, np.array(got_rows))
