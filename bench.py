@@ -539,6 +539,8 @@ def run_dips(a):
     One step = index build + (n,3,256) patches of every point of one C3-shaped tile-epoch (625 k points at 0.1 m
     spacing, feature radius sqrt(3)*10*resolution, ~850 neighbours per point).  cpu_baseline: oracle/dips.py (numpy +
     cKDTree, one core -- the reference's own per-point loop shape) on a bounded sample of the same queries."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                      # single-GPU workload: under torchrun only rank 0 runs it
     import numpy as np
     import torch
     from fusion4landslide_b200 import _lib, ops, synth
