@@ -397,9 +397,6 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
 // balanced; distances use sqrt.approx.f32 (<= 1 ulp; the reference's own cdist carries ~1e-3 m of
 // GEMM-formulation noise at these coordinates).
 __device__ __forceinline__ float sqrt_approx(float x) {
-#ifdef F4L_EXP_NO_SQRT
-    return x;            // timing experiment only
-#endif
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // ftz: one MUFU, no denormal rescaling (d^2 < 1e-38 m^2 -> 0)
     return r;

@@ -53,7 +53,5 @@ extern "C" int ubench_main() {
     run<1>("MUFU.RSQ ftz", out);
     run<2>("FFMA2", out);
     run<3>("FFMA", out);
-    run<4>("LDS stride-2 (+FADD)", out);
-    run<5>("LDS stride-1 (+FADD)", out);
     return 0;
 }
