@@ -420,3 +420,42 @@ def voxel_downsample(pts64, voxel_size, want_map=False):
     if v < 0:
         raise F4LError("voxel_downsample: the cloud spans more than 2^21 voxels along an axis")
     return (cent[:v], vop) if want_map else cent[:v]
+
+
+# ---- 8(f) rank 2: per-segment parts of the filtering network / superpoint attention pooling -------------------
+def segment_scale_maxabs(x, seg_ptr):
+    """rows (K,C) of every segment divided by the segment's max |value| (src/f2s3.py:343)."""
+    if x.dtype not in (F32, F64):
+        raise F4LError("segment_scale_maxabs: float32 or float64 rows")
+    out = torch.empty(x.shape, dtype=F32, device=x.device)
+    Q = seg_ptr.numel() - 1
+    check(lib().f4l_segment_scale_maxabs(ptr(x), int(x.dtype == F64), ptr(seg_ptr, I32), Q, x.shape[1], ptr(out),
+                                         stream_ptr(x.device)), "f4l_segment_scale_maxabs")
+    return out
+
+
+def segment_norm2_relu(y, seg_ptr, eps=1e-3, residual=None):
+    """InstanceNorm2d -> BatchNorm2d(batch stats) -> ReLU [-> + residual] per segment and channel (PointCN)."""
+    y = y.contiguous()
+    out = torch.empty_like(y)
+    Q = seg_ptr.numel() - 1
+    check(lib().f4l_segment_norm2_relu(ptr(y, F32), ptr(seg_ptr, I32), Q, y.shape[1], float(eps),
+                                       ptr(residual, F32, True), ptr(out), stream_ptr(y.device)), "f4l_segment_norm2_relu")
+    return out
+
+
+def segment_attention_pool(Qm, Km, Vm, seg_ptr, scale):
+    """(P,hidden): mean over the rows of each segment of softmax(Q K^T * scale) V."""
+    Pn = seg_ptr.numel() - 1
+    out = _empty((Pn, Qm.shape[1]), F32, Qm)
+    check(lib().f4l_segment_attention_pool(ptr(Qm, F32), ptr(Km, F32), ptr(Vm, F32), ptr(seg_ptr, I32), Pn, Qm.shape[1],
+                                           float(scale), ptr(out), stream_ptr(Qm.device)), "f4l_segment_attention_pool")
+    return out
+
+
+def segment_mean(x, seg_ptr):
+    Pn = seg_ptr.numel() - 1
+    out = _empty((Pn, x.shape[1]), F32, x)
+    check(lib().f4l_segment_mean(ptr(x, F32), ptr(seg_ptr, I32), Pn, x.shape[1], ptr(out), stream_ptr(x.device)),
+          "f4l_segment_mean")
+    return out

@@ -205,3 +205,185 @@ def prepare_tile_host(src, tgt, label_src, label_tgt, corr3d, corr2d, min_pts, p
     t.n_src_items = int(t.sp_ptr[-1]) if t.n_pairs else 0
     t.n_tgt_items = int(t.tp_ptr[-1]) if t.n_pairs else 0
     return t
+
+
+# ---------------------------------------------------------------------------------------------
+# Scene generator v2 -- SURVEY 8(d) as written: epoch 2 is an INDEPENDENT resample of the surface (no 1:1
+# counterpart), a nested 3-level superpoint-like hierarchy (~64 / 192 / 576 points), ~2 % of the points in
+# patches of <= 10 points, descriptors tied to the nearest physical counterpart, 2D-lifted matches.
+# ---------------------------------------------------------------------------------------------
+def _grid_candidates_nn(q, r, cell, per_cell=4):
+    """For every row of q (n,>=2) the nearest row of r (m,>=2) among the first `per_cell` points of each of the
+    3x3 xy grid cells around it (pure torch; with ~1 point per cell this is the true nearest neighbour for all but
+    a fraction of a percent of the queries).  Distances use all columns.  Returns (idx (n) i64 or -1, d2 (n))."""
+    dev = q.device
+    m = r.shape[0]
+    nx = int(max(float(q[:, 0].max()), float(r[:, 0].max()), float(q[:, 1].max()), float(r[:, 1].max())) / cell) + 3
+
+    def cid(p, dx=0, dy=0):
+        ix = ((p[:, 0] / cell).floor().long() + 1 + dx).clamp(0, nx - 1)
+        iy = ((p[:, 1] / cell).floor().long() + 1 + dy).clamp(0, nx - 1)
+        return ix * nx + iy
+
+    cr = cid(r)
+    order = torch.argsort(cr, stable=True)
+    sc = cr[order]
+    best_d = torch.full((q.shape[0],), float("inf"), dtype=q.dtype, device=dev)
+    best_i = torch.full((q.shape[0],), -1, dtype=torch.int64, device=dev)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            c = cid(q, dx, dy)
+            start = torch.searchsorted(sc, c)
+            for k in range(per_cell):
+                pos = (start + k).clamp(max=m - 1)
+                ok = sc[pos] == c
+                j = order[pos]
+                d = ((r[j] - q) ** 2).sum(1)
+                d = torch.where(ok, d, torch.full_like(d, float("inf")))
+                upd = (d < best_d) | ((d == best_d) & (j < best_i))
+                best_d = torch.where(upd, d, best_d)
+                best_i = torch.where(upd, j, best_i)
+    return best_i, best_d
+
+
+def hierarchy_labels(x, y, spacing, L, seed=0, small_frac=0.02):
+    """Patch labels of a point set from its (pre-motion) xy position, int64 (4, n):
+        row 0  supervoxel-like patches of ~256 points           (2 x 2 level-1 cells)
+        row 1  superpoint level 1, ~64 points                   (warped 0.8 m grid at 0.1 m spacing)
+        row 2  superpoint level 2, ~192 points                  (3 level-1 cells along the first axis)
+        row 3  superpoint level 3, ~576 points                  (3 x 3 level-1 cells) -- the hierarchy is nested
+    ~small_frac of the points sit in patches of <= 10 points (0.2 m cells picked by a hash of the cell id; they keep
+    their tiny label on every row), which exercises the size gates (base.py:1309-1316, f2s3.py:222-225)."""
+    s1 = spacing * 8.0
+    u = x + 0.25 * s1 * torch.sin(2 * math.pi * y / (7.3 * s1))
+    v = y + 0.25 * s1 * torch.sin(2 * math.pi * x / (5.9 * s1))
+    n1 = int(math.ceil(L / s1)) + 4
+    i = (u / s1).floor().long().clamp(-1, n1 - 3) + 1
+    j = (v / s1).floor().long().clamp(-1, n1 - 3) + 1
+    rows = [(i // 2) * n1 + (j // 2), i * n1 + j, (i // 3) * n1 + j, (i // 3) * n1 + (j // 3)]
+    sf = 2.0 * spacing
+    nf = int(math.ceil(L / sf)) + 2
+    fid = (x / sf).floor().long().clamp(0, nf - 1) * nf + (y / sf).floor().long().clamp(0, nf - 1)
+    h = (fid * 2654435761 + (seed + 1) * 40503) % 4294967296
+    h = (h * 2246822519 + 3266489917) % 4294967296
+    small = h < int(small_frac * 4294967296)
+    off = n1 * n1
+    return torch.stack([torch.where(small, off + fid, r) for r in rows], 0)
+
+
+def make_scene(n_pts, seed=0, device="cpu", spacing=0.1, block=10.0, noise=0.005, desc_dim=0,
+               desc_noise=0.15, desc_outliers=0.10, wrong_frac=0.05, frac_2d=0.0, outliers_2d=0.05,
+               small_frac=0.02, origin=(0.0, 0.0)):
+    """One synthetic tile, SURVEY 8(d).  Both epochs sample the same rough surface INDEPENDENTLY (n_pts points each);
+    epoch 2 then moves block-wise (10 m checkerboard, half of the blocks rotate by U(0,2) degrees about a random axis
+    through the block centre and shift by 0.05-0.5 m) and receives N(0,(5 mm)^2) noise.
+
+    Returns a dict of tensors on `device`:
+      src, tgt (n,3) f32; labels_src, labels_tgt (4,n) i64 (see hierarchy_labels; label_src/label_tgt = row 0);
+      counterpart_of_tgt (n) i64: the source point nearest to the pre-motion position of each target point (-1: none
+      within 1.5 spacings); corr3d (n,2) i64: what an exact descriptor matcher + magnitude gate delivers (target whose
+      counterpart is the source point; `wrong_frac` of those point to the match of another point of the same patch);
+      corr2d (n,2) i64 when frac_2d > 0: 2D-lifted matches of a frac_2d sample of the source points
+      (nearest target of the same ground, `outliers_2d` wrong); src_feat/tgt_feat (n,D) unit rows when desc_dim > 0
+      (target = normalize(feat[counterpart] + desc_noise * N(0,I)), `desc_outliers` replaced by random rows);
+      block_of_src, R_gt (B,3,3), t_gt (B,3), moving (B) -- the known block motion."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    L = spacing * math.sqrt(n_pts)
+    dev = device
+
+    def U(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=g, device=dev, dtype=f64) * (hi - lo) + lo
+
+    def Nrm(*shape, dtype=f64):
+        return torch.randn(*shape, generator=g, device=dev, dtype=dtype)
+
+    J = 6
+    amps = 5.0 * 0.5 ** torch.arange(1, J + 1, device=dev, dtype=f64)
+    wl = 40.0 * 0.6 ** torch.arange(J, device=dev, dtype=f64)
+    th = U(J, hi=2 * math.pi)
+    kx = 2 * math.pi / wl * torch.cos(th)
+    ky = 2 * math.pi / wl * torch.sin(th)
+    ph = U(J, hi=2 * math.pi)
+
+    x, y = U(n_pts, hi=L), U(n_pts, hi=L)
+    src = torch.stack([x, y, _terrain(x, y, ph, amps, kx, ky)], 1)
+    x2, y2 = U(n_pts, hi=L), U(n_pts, hi=L)                    # independent resample of the same surface
+    tgt0 = torch.stack([x2, y2, _terrain(x2, y2, ph, amps, kx, ky)], 1)
+
+    nb = int(math.ceil(L / block))
+    ar = torch.arange(nb * nb, device=dev)
+
+    def blk_of(px, py):
+        return torch.clamp((px / block).long(), max=nb - 1) * nb + torch.clamp((py / block).long(), max=nb - 1)
+
+    B = nb * nb
+    moving = ((ar // nb + ar % nb) % 2 == 1)
+    ang = U(B, hi=math.radians(2.0)) * moving
+    axis = Nrm(B, 3)
+    tn = U(B, lo=0.05, hi=0.5) * moving
+    tdir = Nrm(B, 3)
+    tdir = tdir / tdir.norm(dim=1, keepdim=True)
+    Rb = _axis_angle(axis, ang)
+    cb = torch.stack([(ar // nb + 0.5) * block, (ar % nb + 0.5) * block, torch.zeros(B, device=dev, dtype=f64)], 1).to(f64)
+    tb = cb + tdir * tn[:, None] - torch.einsum("bij,bj->bi", Rb, cb)
+    blk_t = blk_of(x2, y2)
+    tgt = torch.einsum("nij,nj->ni", Rb[blk_t], tgt0) + tb[blk_t] + noise * Nrm(n_pts, 3)
+
+    labels_src = hierarchy_labels(x, y, spacing, L, seed, small_frac)
+    labels_tgt = hierarchy_labels(x2, y2, spacing, L, seed, small_frac)     # same ground <=> same id
+
+    # physical counterpart of every target point (pre-motion position) among the source points, and the reverse
+    cp, cp_d2 = _grid_candidates_nn(tgt0, src, spacing)
+    cp = torch.where(cp_d2 < (1.5 * spacing) ** 2, cp, torch.full_like(cp, -1))
+    ar_n = torch.arange(n_pts, device=dev)
+    first_tgt = torch.full((n_pts,), n_pts, dtype=torch.int64, device=dev)
+    okc = cp >= 0
+    first_tgt.scatter_reduce_(0, cp[okc], ar_n[okc], reduce="amin", include_self=True)
+    has = first_tgt < n_pts                                                  # a target point claims this source point
+
+    # correspondences as an exact descriptor matcher would deliver them
+    corr = torch.full((n_pts, 2), -1, dtype=torch.int64, device=dev)
+    corr[:, 0] = ar_n
+    good = has & (torch.rand(n_pts, generator=g, device=dev) >= desc_outliers)
+    wrong = good & (torch.rand(n_pts, generator=g, device=dev) < wrong_frac)
+    lab = labels_src[0]
+    order = torch.argsort(lab, stable=True)
+    _, counts = torch.unique_consecutive(lab[order], return_counts=True)
+    starts = torch.cumsum(counts, 0) - counts
+    seg_sorted = torch.repeat_interleave(torch.arange(counts.numel(), device=dev), counts)
+    seg = torch.empty(n_pts, dtype=torch.int64, device=dev)
+    seg[order] = seg_sorted
+    rnd = (torch.rand(n_pts, generator=g, device=dev) * counts[seg].to(f64)).long()
+    other = order[starts[seg] + torch.minimum(rnd, counts[seg] - 1)]
+    tgt_of = torch.where(wrong & has[other], first_tgt[other], first_tgt)
+    corr[:, 1] = torch.where(good, tgt_of, torch.full_like(tgt_of, -1))
+
+    ox, oy = origin
+    off = torch.tensor([ox, oy, 0.0], dtype=f64, device=dev)
+    out = dict(src=(src + off).float().contiguous(), tgt=(tgt + off).float().contiguous(),
+               labels_src=labels_src, labels_tgt=labels_tgt, label_src=labels_src[0], label_tgt=labels_tgt[0],
+               counterpart_of_tgt=cp, corr3d=corr, block_of_src=blk_of(x, y), R_gt=Rb,
+               t_gt=tb + off - torch.einsum("bij,j->bi", Rb, off), moving=moving, L=L)
+    if frac_2d > 0:
+        c2 = torch.full((n_pts, 2), -1, dtype=torch.int64, device=dev)
+        c2[:, 0] = ar_n
+        nn_t, nn_d2 = _grid_candidates_nn(src, tgt0, spacing)               # nearest target of the same ground
+        pick = (torch.rand(n_pts, generator=g, device=dev) < frac_2d) & (nn_d2 < (1.5 * spacing) ** 2)
+        bad2 = pick & (torch.rand(n_pts, generator=g, device=dev) < outliers_2d)
+        rnd2 = (torch.rand(n_pts, generator=g, device=dev) * counts[seg].to(f64)).long()
+        other2 = order[starts[seg] + torch.minimum(rnd2, counts[seg] - 1)]
+        t2 = torch.where(bad2, nn_t[other2], nn_t)
+        c2[:, 1] = torch.where(pick & (t2 >= 0), t2, torch.full_like(t2, -1))
+        out["corr2d"] = c2
+    if desc_dim > 0:
+        fs = torch.randn(n_pts, desc_dim, generator=g, device=dev)
+        fs = fs / fs.norm(dim=1, keepdim=True)
+        rndv = torch.randn(n_pts, desc_dim, generator=g, device=dev)
+        ft = fs[cp.clamp(min=0)] + desc_noise * torch.randn(n_pts, desc_dim, generator=g, device=dev)
+        bad = (cp < 0) | (torch.rand(n_pts, generator=g, device=dev) < desc_outliers)
+        ft = torch.where(bad[:, None], rndv, ft)
+        out["src_feat"] = fs.contiguous()
+        out["tgt_feat"] = (ft / ft.norm(dim=1, keepdim=True)).contiguous()
+    return out

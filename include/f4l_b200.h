@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define F4L_ABI_VERSION 3
+#define F4L_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define F4L_API __attribute__((visibility("default")))
@@ -389,6 +389,28 @@ F4L_API size_t f4l_voxel_downsample_workspace_bytes(int32_t n);
 F4L_API int f4l_voxel_downsample(const double* pts64, int32_t n, double voxel_size, double* centroids,
                          int32_t* voxel_of_point, int32_t* counts, void* workspace, size_t workspace_bytes,
                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 8(f) rank 2 -- the per-segment parts of the two small networks inside the reference's per-patch loops,
+ * for all segments (CSR seg_ptr (Q+1) int32 over rows) of a tile at once.  The per-point dense products in
+ * between (1x1 convolutions, linear layers) are ordinary GEMMs and stay with the caller's BLAS.
+ *   f4l_segment_scale_maxabs    src/f2s3.py:343: rows (K,C) f32 or f64 (x_is_f64) of every supervoxel divided by its
+ *                               max |value| in the input precision, stored as f32 (:346)
+ *   f4l_segment_norm2_relu      src/models/outlier_classifier.py:15-23,29-33 (PointCN): InstanceNorm2d(eps) ->
+ *                               BatchNorm2d(eps, batch statistics of the single-sample batch) -> ReLU
+ *                               [-> + residual] per segment and channel; y, residual, out (K,C) f32
+ *   f4l_segment_attention_pool  src/feature_aggregation/cluster_feature_net_self_attention.py:18-33,:91:
+ *                               out[p] = mean_i sum_j softmax_j(Q_i.K_j * scale) V_j over the rows of segment p;
+ *                               Q,K,V (rows,hidden) f32, hidden in {32,64}; out (P,hidden).  Empty segment -> NaN
+ *                               (torch.mean of an empty tensor)
+ *   f4l_segment_mean            :97 per-segment mean of x (rows,C) f32 (fp64 accumulation) -> (P,C) */
+F4L_API int f4l_segment_scale_maxabs(const void* x, int32_t x_is_f64, const int32_t* seg_ptr, int32_t Q, int32_t C,
+                             float* out, void* stream);
+F4L_API int f4l_segment_norm2_relu(const float* y, const int32_t* seg_ptr, int32_t Q, int32_t C, float eps,
+                           const float* residual, float* out, void* stream);
+F4L_API int f4l_segment_attention_pool(const float* Qm, const float* Km, const float* Vm, const int32_t* seg_ptr,
+                               int32_t P, int32_t hidden, float scale, float* out, void* stream);
+F4L_API int f4l_segment_mean(const float* x, const int32_t* seg_ptr, int32_t P, int32_t C, float* out, void* stream);
 
 #ifdef __cplusplus
 }
