@@ -30,6 +30,27 @@ int f4l_finish(const char* what, void* stream);   // closing mark + launch error
 
 static inline int f4l_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-device one-time setup (cudaFuncSetAttribute and memory-pool attributes belong to the CURRENT device, so a
+// process-wide flag would skip them on the second GPU a process touches).  Usage:
+//     static F4lPerDevice once;  if (!once.done()) { if (f4l_optin_smem(k, bytes) ...) once.mark(); }
+struct F4lPerDevice {
+    unsigned long long mask[2] = {0ull, 0ull};      // 128 devices; benign race: the setup is idempotent
+    static int dev() { int d = 0; cudaGetDevice(&d); return d & 127; }
+    bool done() const { const int d = dev(); return (__atomic_load_n(&mask[d >> 6], __ATOMIC_ACQUIRE) >> (d & 63)) & 1ull; }
+    void mark() { const int d = dev(); __atomic_fetch_or(&mask[d >> 6], 1ull << (d & 63), __ATOMIC_RELEASE); }
+};
+// opt-in to `bytes` of dynamic shared memory for kernel `fn` on the current device; false (+ error text) on failure
+template <class F>
+static inline bool f4l_optin_smem(F* fn, size_t bytes, const char* name) {
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        f4l_set_error("cudaFuncSetAttribute(%s, %zu B dynamic shared memory): %s", name, bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
 // ---- warp reductions ----------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -525,10 +525,10 @@ extern "C" int f4l_dips_patches(const double* query64, int32_t n_query, int32_t 
     const int grid = min(f4l_div_up(n_query, DIPS_WARPS), 148 * 16);
     if (ranks) {
         const size_t smem = DIPS_WARPS * (sizeof(DipsWarpSmem) + sizeof(DipsRankSmem));
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_dips_patches<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_done = true;
+        static F4lPerDevice once;
+        if (!once.done()) {
+            if (!f4l_optin_smem(k_dips_patches<true>, smem, "k_dips_patches<ranked>")) return F4L_E_CUDA;
+            once.mark();
         }
         f4l_mark("k_dips_patches_ranked", st);
         k_dips_patches<true><<<grid, DIPS_WARPS * 32, smem, st>>>(query64, n_query, w.sorted, w.table, w.grid, radius,

@@ -689,15 +689,15 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
         f4l_set_error("f4l_fine_matching: workspace too small (%zu < %zu)", workspace_bytes, w.total);
         return F4L_E_WORKSPACE;
     }
-    static bool attr_set = false;
+    static F4lPerDevice once;
     const size_t smem_fit = (size_t)ICP_SMEM_PTS * 3 * sizeof(float);
     const size_t smem_aa = (size_t)AA_SMEM_PTS * sizeof(float4);
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_patch_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
-        cudaFuncSetAttribute(k_apply_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_aa);
-        cudaFuncSetAttribute(k_patch_fit_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(FITW_WARPS * sizeof(WarpIcpSmem)));
-        attr_set = true;
+    if (!once.done()) {
+        if (!f4l_optin_smem(k_patch_fit, smem_fit, "k_patch_fit") ||
+            !f4l_optin_smem(k_apply_assign, smem_aa, "k_apply_assign") ||
+            !f4l_optin_smem(k_patch_fit_warp, FITW_WARPS * sizeof(WarpIcpSmem), "k_patch_fit_warp"))
+            return F4L_E_CUDA;
+        once.mark();
     }
     f4l_mark("k_select_corr", st);
     k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,

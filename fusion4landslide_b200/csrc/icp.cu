@@ -78,12 +78,12 @@ extern "C" int f4l_patch_icp(const float* src, const int32_t* src_idx, const int
     F4L_REQUIRE(max_corr_dist > 0.0, "max_correspondence_distance must be > 0 (Open3D raises too)");
     F4L_REQUIRE(max_iter >= 0, "max_iter < 0");
     const size_t smem = (size_t)ICP_SMEM_PTS * 3 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_patch_icp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(ICPW_WARPS * sizeof(WarpIcpSmem)));
-        cudaFuncSetAttribute(k_patch_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    static F4lPerDevice once;
+    if (!once.done()) {
+        if (!f4l_optin_smem(k_patch_icp_warp, ICPW_WARPS * sizeof(WarpIcpSmem), "k_patch_icp_warp") ||
+            !f4l_optin_smem(k_patch_icp, smem, "k_patch_icp"))
+            return F4L_E_CUDA;
+        once.mark();
     }
     const int grid_w = f4l_div_up(Q, ICPW_WARPS) < 148 * 8 ? f4l_div_up(Q, ICPW_WARPS) : 148 * 8;
     f4l_mark("k_patch_icp_warp", (cudaStream_t)stream);
@@ -169,10 +169,10 @@ extern "C" int f4l_segmented_nn(const float* qpts, const int32_t* qidx, const in
     if (Q == 0) return F4L_OK;
     F4L_REQUIRE(qpts && rpts && q_start && r_start && nn, "null pointer");
     const size_t smem = (size_t)SNN_SMEM_PTS * 3 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_segmented_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    static F4lPerDevice once;
+    if (!once.done()) {
+        if (!f4l_optin_smem(k_segmented_nn, smem, "k_segmented_nn")) return F4L_E_CUDA;
+        once.mark();
     }
     const int grid = Q < 148 * 8 ? Q : 148 * 8;
     f4l_mark("k_segmented_nn", (cudaStream_t)stream);

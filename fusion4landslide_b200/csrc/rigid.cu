@@ -186,8 +186,8 @@ extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const in
     cudaStream_t st = (cudaStream_t)stream;
     // 128 B of scratch per segment (raw moments, then the fp64 fit), stream-ordered pool allocation
     double* mom = nullptr;
-    static bool pool_ready = false;
-    if (!pool_ready) {
+    static F4lPerDevice pool_ready;
+    if (!pool_ready.done()) {
         // keep freed blocks in the default pool instead of returning them to the OS at every synchronisation
         int dev = 0;
         cudaMemPool_t pool;
@@ -195,7 +195,7 @@ extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const in
             unsigned long long keep = 1ull << 30;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        pool_ready = true;
+        pool_ready.mark();
     }
     if (cudaMallocAsync((void**)&mom, (size_t)Q * 16 * sizeof(double), st) != cudaSuccess) {
         f4l_set_error("f4l_segmented_kabsch: cudaMallocAsync of %zu bytes failed", (size_t)Q * 128);
@@ -333,10 +333,10 @@ extern "C" int f4l_rigidity_check(const float* src, const float* tgt, const int3
     if (Q == 0) return F4L_OK;
     F4L_REQUIRE(src && tgt && seg_start && ratio_inlier && dist_mean, "null pointer");
     size_t smem = (size_t)RIG_MAX_SMEM_PTS * 6 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_rigidity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    static F4lPerDevice once;
+    if (!once.done()) {
+        if (!f4l_optin_smem(k_rigidity, smem, "k_rigidity")) return F4L_E_CUDA;
+        once.mark();
     }
     f4l_mark("k_rigidity", (cudaStream_t)stream);
     k_rigidity<<<Q, 256, smem, (cudaStream_t)stream>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count, Q,

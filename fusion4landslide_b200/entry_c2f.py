@@ -64,10 +64,24 @@ def _points_of(pcd_or_tensor):
 
 
 class _Cloud:
-    """Stand-in for an Open3D PointCloud where only `.points` is consumed downstream (data_loader.py:25-26)."""
+    """Stand-in for an Open3D PointCloud where only `.points` is consumed downstream (data_loader.py:25-26).
+    Built from a numpy array or from a device tensor; the host copy of a device tensor is made on first use."""
 
     def __init__(self, points64):
-        self.points = points64
+        self._dev = points64 if torch.is_tensor(points64) else None
+        self._host = None if torch.is_tensor(points64) else points64
+
+    @property
+    def points(self):
+        if self._host is None:
+            self._host = self._dev.detach().cpu().numpy().astype(np.float64)
+        return self._host
+
+    def device_points(self, dev):
+        """float64 (n,3) tensor on `dev` without a host round trip when the cloud already lives there."""
+        if self._dev is not None and self._dev.device == dev:
+            return self._dev.to(torch.float64)
+        return torch.from_numpy(np.ascontiguousarray(self.points, dtype=np.float64)).to(dev)
 
 
 def _list_key(lst):
@@ -122,10 +136,17 @@ class HotPathMixin:
         di.tgt_pts_sub = _dev_f32(d3.tgt_pts, dev)
         self.method.voxel_size = self._compute_median_resolution() # :1023
         for name in ("src", "tgt"):
-            raw64 = torch.from_numpy(_points_of(d3.get(name + "_pcd", None) if d3.get(name + "_pcd", None) is not None
-                                                else d3[name + "_pts"])).to(dev)
+            pcd = d3.get(name + "_pcd", None)
+            if isinstance(pcd, _Cloud):
+                raw64 = pcd.device_points(dev)
+            elif pcd is not None:
+                raw64 = torch.from_numpy(_points_of(pcd)).to(dev)
+            elif torch.is_tensor(d3[name + "_pts"]) and d3[name + "_pts"].device == dev:
+                raw64 = d3[name + "_pts"].to(torch.float64)
+            else:
+                raw64 = torch.from_numpy(_points_of(d3[name + "_pts"])).to(dev)
             sub64 = ops.voxel_downsample(raw64.contiguous(), self.method.voxel_size)          # :1024-1025
-            di[name + "_pcd_sub"] = _Cloud(sub64.cpu().numpy())
+            di[name + "_pcd_sub"] = _Cloud(sub64)
             sub = sub64.float().contiguous()                       # pcd2tensor -> float32 (o3d_tools.py:251)
             di[name + "_pts_sub"] = sub
             v2p, p2v = c2f.voxel_subsampling_maps(sub, _dev_f32(d3[name + "_pts"], dev))      # :1038-1057
@@ -469,6 +490,13 @@ class StandaloneBase:
         self.device = config.get("device", "cuda")
         self.debugging = config.get("debugging", edict(use_debugging=False))
         self.write_interim_files = config.get("write_interim_files", True)
+        # in-memory tile (tests, benchmarks, callers that already hold the tile): config.tile_tensors = dict with
+        #   src_pts, tgt_pts (n,3); partition_src, partition_tgt: (n,) labels or a list of them (one per level);
+        #   feat_src, feat_tgt (n_sub,D) descriptors of the sub-sampled clouds, OR feat_raw_src, feat_raw_tgt (n,D)
+        #   per raw point (gathered through idx_voxel2pts_*); optionally corres_3d_from_2d_idx (n,2) int64
+        self.tile_tensors = config.get("tile_tensors", None)
+        if config.get("feat_aggregate_model", None) is not None:
+            self.feat_aggregate_model = config.feat_aggregate_model
         self._initialize()
         self._read_data()
 
@@ -485,13 +513,23 @@ class StandaloneBase:
     def _read_data(self):                                          # base.py:890-916 (3D part)
         from .piecewise_icp import _read_xyz
         dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
-        if self.data.multiple_case:
+        if self.tile_tensors is not None:
+            self.src_pcd_path = self.tgt_pcd_path = None
+        elif self.data.multiple_case:
             self.src_pcd_path, self.tgt_pcd_path = self.config.src_tile_overlap_path, self.config.tgt_tile_overlap_path
         else:
             self.src_pcd_path = osp.join(self.input_root, 'raw_pcd', self.data.src_pcd)
             self.tgt_pcd_path = osp.join(self.input_root, 'raw_pcd', self.data.tgt_pcd)
         d3 = self.data_input_3d
+        tt = self.tile_tensors
         for name, path in (("src", self.src_pcd_path), ("tgt", self.tgt_pcd_path)):
+            if tt is not None:
+                p = tt[name + "_pts"]
+                p = p if torch.is_tensor(p) else torch.from_numpy(np.asarray(p))
+                p = p.to(dev, non_blocking=True)
+                d3[name + "_pcd"] = _Cloud(p)
+                d3[name + "_pts"] = p.float().contiguous()
+                continue
             pts64 = _read_xyz(path)
             d3[name + "_pcd"] = _Cloud(pts64)
             d3[name + "_pts"] = torch.from_numpy(pts64).float().to(dev)       # pcd2tensor: float32
@@ -499,6 +537,8 @@ class StandaloneBase:
         d3.idx_initial_tgt = torch.arange(d3.tgt_pts.shape[0], device=dev)
         if not (self.method.coarse_matching_only_3d and self.method.fine_matching_only_3d):
             c = self.config.get("corres_3d_from_2d_idx", None)
+            if c is None and tt is not None:
+                c = tt.get("corres_3d_from_2d_idx", None)
             if c is None:
                 raise NotImplementedError("2D matching / 2D->3D lifting run in the reference (image networks); hand the "
                                           "lifted matches in as config.corres_3d_from_2d_idx (N,2) int64")
@@ -517,6 +557,19 @@ class StandaloneBase:
 
     def load_partition(self):                                      # base.py:1237-1299
         m_ = self.method
+        if self.tile_tensors is not None and "partition_src" in self.tile_tensors:
+            dev = self.data_input_3d.src_pts.device
+            di = self.data_interim
+            get = lambda a: [torch.as_tensor(x).to(dev, I64) for x in a] if isinstance(a, (list, tuple)) else torch.as_tensor(a).to(dev, I64)
+            ps, pt = get(self.tile_tensors["partition_src"]), get(self.tile_tensors["partition_tgt"])
+            if m_.partition_type == 'superpoint' and isinstance(m_.level_of_superpoint, list):
+                di.idx_pts2spt_src_multiple = [ps[lv - 1] for lv in m_.level_of_superpoint] if isinstance(ps, list) else [ps]
+                di.idx_pts2spt_tgt_multiple = [pt[lv - 1] for lv in m_.level_of_superpoint] if isinstance(pt, list) else [pt]
+            elif m_.partition_type == 'superpoint' and isinstance(ps, list):
+                di.idx_pts2spt_src, di.idx_pts2spt_tgt = ps[m_.level_of_superpoint - 1], pt[m_.level_of_superpoint - 1]
+            else:
+                di.idx_pts2spt_src, di.idx_pts2spt_tgt = ps, pt
+            return
         folder = f'{m_.partition_type}_partition'
         pdir = osp.join(self.output_root, folder)
         if not os.path.isdir(pdir) or not os.listdir(pdir):
@@ -544,6 +597,15 @@ class StandaloneBase:
     def compute_point_feat(self):                                  # base.py:1965-2072
         di = self.data_interim
         dev = self.data_input_3d.src_pts.device
+        tt = self.tile_tensors
+        if tt is not None and ("feat_src" in tt or "feat_raw_src" in tt):
+            for name in ("src", "tgt"):
+                if "feat_" + name in tt:
+                    f = torch.as_tensor(tt["feat_" + name]).to(dev)
+                else:                                              # descriptor of a voxel = descriptor of its raw point
+                    f = torch.as_tensor(tt["feat_raw_" + name]).to(dev)[torch.as_tensor(di["idx_voxel2pts_" + name]).to(dev).long()]
+                di["tile_pts_sub_feat_" + name] = f.float().contiguous()
+            return
         if not self.method.point_feat_compute:
             if not osp.exists(self._feat_path):
                 raise FileNotFoundError(f"The feature path '{self._feat_path}' is not found")

@@ -192,8 +192,15 @@ class StandaloneBase(object):
         self.device = config.get("device", "cuda")
         self.batch_size = config.get("batch_size", 1)
         self.num_workers = config.get("num_workers", 0)
-        self.src_tile_overlap_pcd = _Cloud(_read_xyz(src_tile_overlap_path))
-        self.tgt_tile_overlap_pcd = _Cloud(_read_xyz(tgt_tile_overlap_path))
+        # in-memory tile: config.tile_tensors = dict(src_pts, tgt_pts (n,3) float64 numpy / tensors, src_feat, tgt_feat
+        # (n,D), svl_idx (n,) supervoxel label per source point); the two path arguments are then unused
+        self.tile_tensors = config.get("tile_tensors", None)
+        if self.tile_tensors is not None:
+            self.src_tile_overlap_pcd = _Cloud(self.tile_tensors["src_pts"])
+            self.tgt_tile_overlap_pcd = _Cloud(self.tile_tensors["tgt_pts"])
+        else:
+            self.src_tile_overlap_pcd = _Cloud(_read_xyz(src_tile_overlap_path))
+            self.tgt_tile_overlap_pcd = _Cloud(_read_xyz(tgt_tile_overlap_path))
         self.src_tile_non_overlap_path, self.tgt_tile_non_overlap_path = src_tile_overlap_path, tgt_tile_overlap_path
         self.src_tile_non_overlap_pcd, self.tgt_tile_non_overlap_pcd = self.src_tile_overlap_pcd, self.tgt_tile_overlap_pcd
         self.tile_id = config.tile_id
@@ -234,6 +241,10 @@ class StandaloneBase(object):
 
     def compute_features(self):                                        # src/f2s3.py:91-164
         dev = _dev(self)
+        if self.tile_tensors is not None and "src_feat" in self.tile_tensors:
+            self.src_tile_feat = torch.as_tensor(self.tile_tensors["src_feat"]).to(dev)
+            self.tgt_tile_feat = torch.as_tensor(self.tile_tensors["tgt_feat"]).to(dev)
+            return None
         if not self.config.feat_compute:
             if not osp.exists(self._feat_path):
                 raise FileNotFoundError(f"The feature path '{self._feat_path}' is not found")
@@ -258,6 +269,11 @@ class StandaloneBase(object):
         return None
 
     def implement_segmentation(self):                                  # src/f2s3.py:166-238
+        if self.tile_tensors is not None and "svl_idx" in self.tile_tensors:
+            lab = self.tile_tensors["svl_idx"]
+            lab = lab.cpu().numpy() if torch.is_tensor(lab) else np.asarray(lab)
+            self.svl_type = supervoxel_lists(lab, 10 if self.small_patch_removal else 1, _dev(self))
+            return
         if self.pcd_segment:
             raise NotImplementedError("the native supervoxel / superpoint segmentation stays in the reference; "
                                       "set pcd_segment: False to load its result file")

@@ -308,3 +308,50 @@ class HostPipeline:
             r.dense.record_stream(st)
             r.sparse.record_stream(st)
         return n
+
+
+def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_ptr, svl_idx, weights=None, filter_net=None, coeff=1.0,
+              refine_results=False, max_disp_magnitude=0.0, mutual=False, want_median=True):
+    """The F2S3 hot path on one tile, device -> device (BASELINE config C2; src/f2s3.py:248-441 without the files):
+    A1 median resolution (the descriptor radius of compute_features, f2s3.py:106) -> B1 exact descriptor 1-NN on the
+    tensor cores -> rows [src | tgt[label]] in supervoxel order (CSR svl_ptr / svl_idx over source points) -> weights
+    (filter_net.compute_weights_segments, or `weights` (n,) handed in) -> per supervoxel weighted Kabsch -> residual
+    median filter -> refit (D3 F4) -> keep mask -> magnitude gate (F1).
+    mutual: both search directions; rows whose target's nearest source is another point get weight 0.
+    Returns a dict of device tensors; `rows` / `mag` are the kept correspondences (one host sync for their count)."""
+    from . import f2s3 as hot
+    out = {}
+    if want_median:
+        out["median_resolution"] = ops.median_resolution(src, tgt)
+    if mutual:
+        ri, _, ci, _ = ops.desc_nn(feat_src, feat_tgt, both_dirs=True)
+    else:
+        ri, _ = ops.desc_nn(feat_src, feat_tgt)
+        ci = None
+    out["labels"] = ri
+    sel = svl_idx.long()
+    lab_sel = ri[sel].long()
+    X = torch.cat([src[sel], tgt[lab_sel]], dim=1).contiguous()                      # f2s3.py:284-285, :366
+    ptr = svl_ptr.to(src.device, torch.int32).contiguous()
+    if filter_net is not None:
+        with torch.no_grad():
+            scores = filter_net.compute_weights_segments(X, ptr, scale=True)
+    else:
+        scores = weights.to(torch.float32)[sel]
+    if mutual:
+        scores = torch.where(ci[lab_sel] == svl_idx.to(ci.dtype), scores, torch.zeros_like(scores))
+    scores = scores.contiguous()
+    R, t, robust, res = hot.filter_input_tail(X, scores, ptr, coeff)
+    keep = scores > 0.99999
+    if refine_results:
+        seg = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=src.device), (ptr[1:] - ptr[:-1]).long())
+        keep = keep | robust[seg]
+    rows = X[keep].contiguous()
+    if max_disp_magnitude > 0 and rows.shape[0] > 0:
+        mask, mag = ops.magnitude_mask(rows, max_mag=max_disp_magnitude)
+        m = mask.bool()
+        rows, mag = rows[m], mag[m]
+    else:
+        mag = torch.linalg.norm(rows[:, 3:6] - rows[:, :3], dim=1)
+    out.update(rows=rows, mag=mag, keep=keep, scores=scores, R=R, t=t, robust=robust, residuals=res, corr=X)
+    return out

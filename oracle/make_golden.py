@@ -20,7 +20,13 @@ What gets pinned (reference function -> golden file):
       class it uses (KDTreeFlann.search_radius_vector_3d)          -> dips_patches.npz
   src/coarse_to_fine_matching_base.py map_corr_2d_to_3d, map_corr_2d_to_3d_tgt2src
       (scipy cKDTree, present here)                                -> map_corr_2d.npz
-Open3D ICP / Octree, hnswlib and faiss cannot be run anywhere here -> no golden, parity unpinned.
+  src/coarse_to_fine_matching_base.py Coarse2Fine_Base.coarse_matching_with_different_types, the method body
+      itself on a stand-in `self` (2D vote, mutual 3D, pair order)  -> coarse_method.npz
+  src/coarse_to_fine_matching.py merge_correspondences_by_priority_with_distance_threshold with an EXACT
+      stand-in for the faiss HNSW index                            -> merge_levels.npz
+  FilteringNetwork.compute_weights / ClusterFeatureNetWithAttention.aggregation with the shipped weights
+      (per-patch loops of f2s3.py:340-347, base.py:2561-2656)      -> nets_shipped.npz
+Open3D ICP / Octree, hnswlib and faiss' HNSW cannot be run anywhere here -> no golden, parity unpinned.
 """
 import os
 import sys
@@ -319,12 +325,231 @@ def make_lifting():
                         rows_fwd=r_f, idx_rev=i_r.astype(np.int64), mask_rev=m_r, rows_rev=r_r)
 
 
+class _Log:
+    def info(self, *a, **k):
+        pass
+
+
+def make_coarse():
+    """B3 + B4 + the pair ordering: the reference's OWN method body `Coarse2Fine_Base.coarse_matching_with_different_types`
+    (base.py:2925-3157) executed unmodified on a stand-in `self` (fusion mode: 2D-vote pairs followed by mutual 3D
+    pairs; the learned superpoint features are handed in, so `_compute_spt_feat_and_coord_with_fused_feats` is a no-op).
+    Source patches whose best vote count is shared by several target labels are recorded (`tie`): torch.argsort's order
+    of equal counts is unspecified, the golden holds what torch-CPU returned."""
+    base = ref_shim.ref_base()
+    ED = sys.modules["easydict"].EasyDict
+    rng = np.random.default_rng(11)
+    n_s, n_t, P = 6000, 6400, 60
+    # patch labels: contiguous blocks with gaps in the label space, a few patches below the size gate (removed)
+    lab_s = np.sort(rng.integers(0, P, n_s)) * 3 + 5
+    lab_t = np.sort(rng.integers(0, P, n_t)) * 3 + 5
+    lab_t[lab_t == 5 + 3 * 7] = 5 + 3 * 8                       # one target label never occurs
+    perm_s, perm_t = rng.permutation(n_s), rng.permutation(n_t)
+    lab_s, lab_t = lab_s[perm_s], lab_t[perm_t]
+
+    def lists(lab, min_pts):
+        u, c = np.unique(lab, return_counts=True)
+        keep = u[c > min_pts]
+        return keep, [torch.from_numpy(np.nonzero(lab == k)[0]) for k in keep]
+
+    idx_spt_src, spt2pts_src = lists(lab_s, 40)
+    idx_spt_tgt, spt2pts_tgt = lists(lab_t, 40)
+    # 2D-lifted matches: 30 % of the source points, most into the "same" patch id, some elsewhere, some ties by design
+    corr2d = -np.ones((n_s, 2), np.int64)
+    corr2d[:, 0] = np.arange(n_s)
+    pts_of_t = {int(k): np.nonzero(lab_t == k)[0] for k in np.unique(lab_t)}
+    keys_t = np.array(sorted(pts_of_t))
+    for i in np.nonzero(rng.random(n_s) < 0.3)[0]:
+        k = int(lab_s[i])
+        if rng.random() < 0.35 or k not in pts_of_t:
+            k = int(keys_t[rng.integers(0, keys_t.size)])
+        corr2d[i, 1] = rng.choice(pts_of_t[k])
+    # force exact ties in three source patches: two matches each into two target patches
+    for m in (3, 11, 20):
+        pts = spt2pts_src[m].numpy()
+        corr2d[pts, 1] = -1
+        ka, kb = int(keys_t[2 * m]), int(keys_t[2 * m + 1])
+        corr2d[pts[0], 1], corr2d[pts[1], 1] = pts_of_t[ka][0], pts_of_t[ka][1]
+        corr2d[pts[2], 1], corr2d[pts[3], 1] = pts_of_t[kb][0], pts_of_t[kb][1]
+    # superpoint coordinates / features for the 3D branch
+    S, T, D = len(spt2pts_src), len(spt2pts_tgt), 64
+    cs = rng.uniform(0, 60, size=(S, 3)).astype(np.float32)
+    ct = (cs[rng.integers(0, S, T)] + rng.normal(size=(T, 3)) * 0.4).astype(np.float32)
+    fs = rng.normal(size=(S, D)).astype(np.float32)
+    fs /= np.linalg.norm(fs, axis=1, keepdims=True)
+    ft = (fs[rng.integers(0, S, T)] + 0.4 * rng.normal(size=(T, D))).astype(np.float32)
+    ft /= np.linalg.norm(ft, axis=1, keepdims=True)
+    out = dict(lab_s=lab_s, lab_t=lab_t, corr2d=corr2d, cs=cs, ct=ct, fs=fs, ft=ft, min_pts=np.array([40]),
+               max_mag=np.array([5.0]))
+
+    for mode in ("fusion", "only_2d", "only_3d"):
+        class Fake:
+            pass
+        me = Fake()
+        me.verbose, me.logging, me.device = False, _Log(), "cpu"
+        me.method = ED(coarse_matching_fusion=mode == "fusion", coarse_matching_only_3d=mode == "only_3d",
+                       coarse_matching_only_2d=mode == "only_2d", fine_matching_only_2d=False,
+                       feat_aggregate_type="learning_based", use_img_patch_enhanced_3d_aggregation=False,
+                       use_img_pixel_enhanced_3d_aggregation=False, use_normal_3d_aggregation=True,
+                       coarse_refinement_3d_type="nn_mutual")
+        me.para = ED(max_magnitude=5.0)
+        me.visualize = ED(visualize_patch=False)
+        me.data_interim = ED()
+        di = me.data_interim
+        di.idx_spt2pts_src, di.idx_spt2pts_tgt = list(spt2pts_src), list(spt2pts_tgt)
+        di.idx_spt_src, di.idx_spt_tgt = torch.from_numpy(idx_spt_src), torch.from_numpy(idx_spt_tgt)
+        di.idx_pts2spt_src, di.idx_pts2spt_tgt = torch.from_numpy(lab_s), torch.from_numpy(lab_t)
+        di.corres_3d_from_2d_idx = torch.from_numpy(corr2d)
+        di.spt_coord_src, di.spt_coord_tgt = torch.from_numpy(cs), torch.from_numpy(ct)
+        di.spt_feat_src, di.spt_feat_tgt = torch.from_numpy(fs), torch.from_numpy(ft)
+        me.data_output = ED()
+        me._compute_spt_feat_and_coord_with_fused_feats = lambda: None
+        base.Coarse2Fine_Base.coarse_matching_with_different_types(me)
+        # identify every returned list by its first point index -> patch position
+        first_s = {int(x[0]): k for k, x in enumerate(spt2pts_src)}
+        first_t = {int(x[0]): k for k, x in enumerate(spt2pts_tgt)}
+        m = np.array([first_s[int(x[0])] for x in me.data_output.spt_corres_src], np.int64)
+        j = np.array([first_t[int(x[0])] for x in me.data_output.spt_corres_tgt], np.int64)
+        out[mode + "_m"], out[mode + "_j"] = m, j
+        out[mode + "_spt_length"] = np.array(me.spt_length, np.int64)
+    # which source patches have a tied top count (independent of the reference: plain counting)
+    tie = np.zeros(S, bool)
+    for m, pts in enumerate(spt2pts_src):
+        t = corr2d[pts.numpy(), 1]
+        t = t[t >= 0]
+        if t.size:
+            _, c = np.unique(lab_t[t], return_counts=True)
+            tie[m] = (c == c.max()).sum() > 1
+    out["tie"] = tie
+    np.savez_compressed(os.path.join(GOLD, "coarse_method.npz"), **out)
+
+
+def make_merge():
+    """M1: the reference's OWN `merge_correspondences_by_priority_with_distance_threshold`
+    (src/coarse_to_fine_matching.py:40-118, default search_type='faiss') executed unmodified, with `faiss` replaced by an
+    EXACT stand-in index (brute force, float32 squared L2 like faiss' fvec_L2sqr): the result is what the function
+    returns when its HNSW index (approximate, absent here) answers every query correctly.  The function's 'cdist' and
+    'kdtree' branches are broken in the reference (torch.cat over numpy arrays / inverted mask) and cannot be run."""
+    ref_shim.load()
+    import types
+
+    class _Hnsw:
+        efConstruction = 0
+        efSearch = 0
+
+    class IndexHNSWFlat:
+        def __init__(self, dim, m):
+            self.dim, self.hnsw, self.x = dim, _Hnsw(), np.zeros((0, dim), np.float32)
+
+        def add(self, x):
+            self.x = np.concatenate([self.x, np.asarray(x, np.float32).reshape(-1, self.dim)], 0)
+
+        def search(self, q, k):
+            assert k == 1
+            q = np.asarray(q, np.float32)
+            D = np.full((q.shape[0], 1), np.float32(np.inf), np.float32)
+            I = np.full((q.shape[0], 1), -1, np.int64)
+            for s in range(0, q.shape[0], 512):
+                d = ((q[s:s + 512, None, :] - self.x[None, :, :]) ** 2).sum(-1, dtype=np.float32)
+                if d.shape[1]:
+                    I[s:s + 512, 0] = d.argmin(1)
+                    D[s:s + 512, 0] = d.min(1)
+            return D, I
+
+    fake = types.ModuleType("faiss")
+    fake.IndexHNSWFlat = IndexHNSWFlat
+    sys.modules["faiss"] = fake
+    import importlib
+    mod = importlib.import_module("src.coarse_to_fine_matching")
+    mod.faiss = fake
+    rng = np.random.default_rng(12)
+    src = rng.uniform(0, 40, size=(5000, 3)).astype(np.float32)
+    out = {}
+    levels = []
+    for lv, frac in enumerate((0.5, 0.6, 0.7)):
+        pick = np.nonzero(rng.random(src.shape[0]) < frac)[0]
+        rows = np.concatenate([src[pick], src[pick] + rng.normal(size=(pick.size, 3)).astype(np.float32) * 0.1], 1)
+        if lv == 2:                                   # near-duplicates on both sides of the 1e-3 threshold
+            rows[:50, 0] += np.float32(5e-4)
+            rows[50:100, 0] += np.float32(2e-3)
+        levels.append(rows.astype(np.float32))
+        out["level%d" % lv] = levels[-1]
+    merged = mod.merge_correspondences_by_priority_with_distance_threshold([torch.from_numpy(x) for x in levels])
+    out["merged"] = merged.numpy()
+    levels_e = [levels[0][:0], levels[1], levels[2]]     # empty first level
+    out["merged_empty0"] = mod.merge_correspondences_by_priority_with_distance_threshold(
+        [torch.from_numpy(x) for x in levels_e]).numpy()
+    np.savez_compressed(os.path.join(GOLD, "merge_levels.npz"), **out)
+
+
+def make_nets():
+    """8(f)-2: the reference's two small learned models with the SHIPPED weights, executed unmodified per patch:
+      FilteringNetwork.compute_weights (src/models/outlier_classifier.py:52-63) per supervoxel, scaled as f2s3.py:343-346
+      ClusterFeatureNetWithAttention.aggregation, mode 'test' (cluster_feature_net_self_attention.py:72-103)
+    The weights travel with the golden (float32 arrays keyed by state_dict key) so the GPU test runs the batched
+    kernels with the same parameters."""
+    ref_shim.load()
+    import importlib
+    ED = sys.modules["easydict"].EasyDict
+    rng = np.random.default_rng(13)
+    out = {}
+    oc = ref_shim.ref_outlier_classifier()
+    net = oc.FilteringNetwork()
+    sd = torch.load(os.path.join(ref_shim.REFERENCE_ROOT, "weights", "outlier_classifier_best.pt"), map_location="cpu",
+                    weights_only=False)
+    sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+    net.load_state_dict(sd)
+    net.eval()
+    for k, v in net.state_dict().items():
+        out["filter/" + k] = v.numpy()
+    sizes = [11, 12, 37, 150, 33, 400, 64, 1200, 15]
+    rows, scores = [], []
+    with torch.no_grad():
+        for ci, n in enumerate(sizes):
+            s, t = _patch(rng, n, rng.uniform(-30, 30, size=3), outliers=0.25 if ci % 2 else 0.05)
+            svl = torch.from_numpy(np.concatenate([s, t], 1).astype(np.float64))
+            scaled = torch.divide(svl, torch.max(torch.abs(svl)))                       # f2s3.py:343
+            w = net.compute_weights(scaled.unsqueeze(0).unsqueeze(0).float())            # :346
+            rows.append(svl.numpy())
+            scores.append(w.reshape(-1).numpy())
+    out["filter_corr"] = np.concatenate(rows, 0)
+    out["filter_ptr"] = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    out["filter_scores"] = np.concatenate(scores, 0)
+
+    cf = importlib.import_module("src.feature_aggregation.cluster_feature_net_self_attention")
+    model = cf.ClusterFeatureNetWithAttention(ED(input_feat_dim=64, hidden_feat_dim=64, output_feat_dim=64, mode="test"))
+    st = torch.load(os.path.join(ref_shim.REFERENCE_ROOT, "weights", "feat_aggregation_3d.pth"), map_location="cpu",
+                    weights_only=False)
+    model.load_state_dict(st["state_dict"] if "state_dict" in st else st)
+    model.eval()
+    for k, v in model.state_dict().items():
+        out["agg/" + k] = v.numpy()
+    V, n_pts = 3000, 3600
+    feats = rng.normal(size=(V, 64)).astype(np.float32)
+    feats /= np.linalg.norm(feats, axis=1, keepdims=True)
+    coords = rng.uniform(0, 50, size=(V, 3)).astype(np.float32)
+    p2v = rng.integers(0, V, n_pts)
+    p2v[rng.random(n_pts) < 0.1] = -1                                                    # points without a voxel
+    psz = [1, 2, 13, 64, 200, 7, 576, 31, 900]
+    order = rng.permutation(n_pts)
+    spt, o = [], 0
+    for n in psz:
+        spt.append(torch.from_numpy(np.sort(order[o:o + n])))
+        o += n
+    with torch.no_grad():
+        f, c = model.aggregation(spt, torch.from_numpy(feats)[None], torch.from_numpy(coords)[None], torch.from_numpy(p2v))
+    out.update(agg_feats=feats, agg_coords=coords, agg_p2v=p2v, agg_spt_ptr=np.concatenate([[0], np.cumsum(psz)]).astype(np.int32),
+               agg_spt_idx=np.concatenate([x.numpy() for x in spt]), agg_out_feat=f.numpy(), agg_out_coord=c.numpy())
+    np.savez_compressed(os.path.join(GOLD, "nets_shipped.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)
     makers = dict(rigid=make_rigid, f2s3_filter=make_f2s3_filter, knn=make_knn, desc=make_desc,
-                  rigidity=make_rigidity, dips=make_dips, lifting=make_lifting)
+                  rigidity=make_rigidity, dips=make_dips, lifting=make_lifting,
+                  coarse=make_coarse, merge=make_merge, nets=make_nets)
     for name in (sys.argv[1:] or list(makers)):          # `python -m oracle.make_golden dips` refreshes one file
         makers[name]()
     for f in sorted(os.listdir(GOLD)):

@@ -1,0 +1,184 @@
+"""GPU parity of the CLASS-LEVEL entry points the reference's mains call, on in-memory synthetic tiles (SURVEY 8(d)
+scenes: independent epochs, 3-level hierarchy, small patches), against the whole-tile oracle compositions:
+
+  Coarse2Fine(cfg).implement_c2f_matching()                 main_fusion.py:147-148   vs oracle.paths.c2f_tile
+  Deformation_Analyze(cfg, ..).correspondence_searching() /
+      .correspondence_pruning()                              main_f2s3.py:72-81       vs oracle.paths.f2s3_tile
+  pipeline.f2s3_tile (the same path device -> device)                                  vs oracle.paths.f2s3_tile
+
+Integer decisions (labels, pairs, status, K, kept rows) exact; displacement rows within 1e-5 m for the pairs whose
+ICP took the same number of iterations in both implementations (count asserted >= 99 %)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fine_matching as ofm
+from oracle import knn as oknn
+from oracle import paths as opaths
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _agg_model(golden_dir, dev):
+    from fusion4landslide_b200 import nets
+    z = np.load(os.path.join(golden_dir, "nets_shipped.npz"))
+    m = nets.ClusterFeatureNetWithAttention()
+    m.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("agg/")})
+    w = {k[4:]: z[k] for k in z.files if k.startswith("agg/")}
+    return m.to(dev).eval(), w
+
+
+def _filter_net(golden_dir, dev):
+    from fusion4landslide_b200 import nets
+    z = np.load(os.path.join(golden_dir, "nets_shipped.npz"))
+    m = nets.FilteringNetwork()
+    m.load_state_dict({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("filter/")})
+    return m.to(dev).eval()
+
+
+def _check_level(r, o, tag):
+    """FineResult of one level vs the oracle's fine-matching dict."""
+    np.testing.assert_array_equal(r.K.cpu().numpy(), o["K"], err_msg=tag)
+    np.testing.assert_array_equal(r.status.cpu().numpy(), o["status"], err_msg=tag)
+    same = r.iters.cpu().numpy() == o["iters"]
+    assert same.mean() > 0.99, (tag, same.mean())
+    return same
+
+
+@pytest.mark.parametrize("mode", ["only_3d", "fusion"])
+def test_coarse2fine_class_vs_oracle(cuda, golden_dir, mode):
+    from fusion4landslide_b200 import configs, synth
+    from fusion4landslide_b200.entry_c2f import Coarse2Fine
+    d = synth.make_scene(36_000, seed=5, desc_dim=64, frac_2d=0.06 if mode == "fusion" else 0.0)
+    model, w = _agg_model(golden_dir, cuda)
+    levels_s = [d["labels_src"][k] for k in (1, 2, 3)]
+    levels_t = [d["labels_tgt"][k] for k in (1, 2, 3)]
+    tt = dict(src_pts=d["src"], tgt_pts=d["tgt"], partition_src=levels_s, partition_tgt=levels_t,
+              feat_raw_src=d["src_feat"], feat_raw_tgt=d["tgt_feat"])
+    if mode == "fusion":
+        tt["corres_3d_from_2d_idx"] = d["corr2d"]
+    cfg = configs.fusion_config(tt, mode=mode, levels=[1, 2, 3], feat_aggregate_model=model)
+    c = Coarse2Fine(cfg)
+    c.implement_c2f_matching()
+    torch.cuda.synchronize()
+    voxel = float(c.method.voxel_size)
+    med_raw = oknn.median_resolution(d["src"].numpy(), d["tgt"].numpy())
+    assert abs(voxel - med_raw) < 1e-5 * med_raw
+    med2 = float(c.para.median_max_resolution)
+    o = opaths.c2f_tile(d["src"].numpy(), d["tgt"].numpy(), [x.numpy() for x in levels_s], [x.numpy() for x in levels_t],
+                        d["src_feat"].numpy(), d["tgt_feat"].numpy(), w, voxel_size=voxel,
+                        corr2d=d["corr2d"].numpy() if mode == "fusion" else None, coarse=mode, fine=mode,
+                        median_max_resolution=float(np.float32(med2)))
+    di, do = c.data_interim, c.data_output
+    # voxel subsampling + maps, descriptor matches
+    np.testing.assert_array_equal(di.src_pts_sub.cpu().numpy(), o["src_pts_sub"])
+    np.testing.assert_array_equal(di.idx_voxel2pts_src.cpu().numpy(), o["idx_voxel2pts_src"])
+    np.testing.assert_array_equal(di.idx_pts2voxel_tgt.cpu().numpy(), o["idx_pts2voxel_tgt"])
+    med_sub = oknn.median_resolution(o["src_pts_sub"], o["tgt_pts_sub"])
+    assert abs(med2 - med_sub) < 1e-5 * med_sub
+    np.testing.assert_array_equal(di.labels_from_3d.cpu().numpy(), o["labels"])
+    np.testing.assert_array_equal(di.corres_3d_voxel_from_3d_idx.cpu().numpy(), o["corr3d"])
+    assert (o["corr3d"][:, 1] >= 0).mean() > 0.3
+    # per level: pairs, status / K, dense rows
+    assert len(do.spt_corres_src_multiple) == 3
+    for lv in range(3):
+        ol = o["levels"][lv]
+        firsts = [int(x[0]) for x in do.spt_corres_src_multiple[lv]]
+        _, spt_s = opaths.patch_lists(levels_s[lv].numpy(), 10)
+        assert firsts == [int(spt_s[a][0]) for a in ol["m"]], "level %d source pairs" % lv
+        _, spt_t = opaths.patch_lists(levels_t[lv].numpy(), 10)
+        assert [int(x[0]) for x in do.spt_corres_tgt_multiple[lv]] == [int(spt_t[b][0]) for b in ol["j"]]
+        assert len(firsts) > 20
+        dn = do.corres_3d_refine_apply_icp_multiple[lv].cpu().numpy()
+        od = ofm.stack(ol["fine"]["dense"])
+        assert dn.shape == od.shape and dn.shape[0] > 1000, (lv, dn.shape, od.shape)
+        np.testing.assert_array_equal(dn[:, :3], od[:, :3])
+        close = np.abs(dn - od).max(1) < TOL + 2 * np.spacing(np.float32(np.abs(od).max()))
+        assert close.mean() > 0.99, (lv, close.mean())
+    # merged result: level-1 rows first and complete, later levels only add new source points
+    merged = do.corres_3d_refine_apply_icp.cpu().numpy()
+    om = o["dense"]
+    assert merged.shape == om.shape
+    np.testing.assert_array_equal(merged[:, :3], om[:, :3])
+    n1 = do.corres_3d_refine_apply_icp_multiple[0].shape[0]
+    assert merged.shape[0] > n1
+    assert np.unique(merged[:, :3], axis=0).shape[0] == merged.shape[0]
+    assert do.corres_3d_magnitude_refine_apply_icp.shape[0] == merged.shape[0]      # save_process_dvf ran
+    sp = do.corres_3d_refine_apply_icp_discrete.cpu().numpy()
+    assert abs(sp.shape[0] - o["sparse"].shape[0]) <= 0.005 * o["sparse"].shape[0] + 2
+
+
+def _supervoxel_csr(labels, dev):
+    from fusion4landslide_b200 import ops
+    _, ptr, idx, _ = ops.labels_to_csr(labels.to(dev, torch.int64).contiguous(), 10)
+    return ptr, idx
+
+
+@pytest.mark.parametrize("D,mutual", [(32, False), (64, True)])
+def test_f2s3_tile_vs_oracle(cuda, D, mutual):
+    from fusion4landslide_b200 import pipeline, synth
+    d = synth.make_scene(30_000, seed=9, desc_dim=D)
+    g = torch.Generator().manual_seed(1)
+    w = torch.rand(30_000, generator=g)
+    w = torch.where(torch.rand(30_000, generator=g) < 0.5, torch.ones_like(w), w)   # half of the rows pass the 0.99999 gate
+    ptr, idx = _supervoxel_csr(d["label_src"], cuda)
+    r = pipeline.f2s3_tile(d["src"].to(cuda), d["tgt"].to(cuda), d["src_feat"].to(cuda), d["tgt_feat"].to(cuda), ptr, idx,
+                           weights=w.to(cuda), coeff=1.0, refine_results=True, max_disp_magnitude=5.0, mutual=mutual)
+    torch.cuda.synchronize()
+    o = opaths.f2s3_tile(d["src"].numpy(), d["tgt"].numpy(), d["src_feat"].numpy(), d["tgt_feat"].numpy(),
+                         d["label_src"].numpy(), w.numpy(), coeff=1.0, refine_results=True, max_disp_magnitude=5.0,
+                         mutual=mutual)
+    np.testing.assert_array_equal(r["labels"].cpu().numpy(), o["labels"])
+    np.testing.assert_array_equal(r["robust"].cpu().numpy(), o["robust"])
+    assert 0 < o["robust"].sum() < o["robust"].size or o["robust"].all()
+    rows = r["rows"].cpu().numpy()
+    assert rows.shape == o["rows"].shape and rows.shape[0] > 3000
+    np.testing.assert_allclose(rows, o["rows"].astype(np.float32), rtol=0, atol=0)
+    # transforms by their action on the supervoxel's points
+    R, t = r["R"].cpu().numpy().astype(np.float64), r["t"].cpu().numpy().astype(np.float64)
+    corr = r["corr"].cpu().numpy().astype(np.float64)
+    p = ptr.cpu().numpy()
+    worst = 0.0
+    for q in range(0, p.size - 1, 7):
+        X = corr[p[q]:p[q + 1], :3]
+        worst = max(worst, np.abs((X @ R[q].T + t[q]) - (X @ o["R"][q].T + o["t"][q].reshape(3))).max())
+    assert worst < 5e-5, worst
+    med = oknn.median_resolution(d["src"].numpy(), d["tgt"].numpy())
+    assert abs(r["median_resolution"].item() - med) < 1e-5 * med
+
+
+def test_deformation_analyze_class_vs_oracle(cuda, golden_dir):
+    """main_f2s3.py:72-81 on an in-memory tile, the filtering network with the SHIPPED weights evaluated for all
+    supervoxels at once; the oracle receives the network's scores (their parity is test_pinned_gpu's job)."""
+    from fusion4landslide_b200 import configs, synth
+    from fusion4landslide_b200.entry_f2s3 import Deformation_Analyze
+    n = 24_000
+    d = synth.make_scene(n, seed=2, desc_dim=32)
+    net = _filter_net(golden_dir, cuda)
+    tt = dict(src_pts=d["src"].double().numpy(), tgt_pts=d["tgt"].double().numpy(), src_feat=d["src_feat"],
+              tgt_feat=d["tgt_feat"], svl_idx=d["label_src"])
+    cfg = configs.f2s3_config(tt, net, max_disp_magnitude=5.0, filter_median_magnitude=True, refine_results=True)
+    a = Deformation_Analyze(cfg, None, None)
+    a.compute_features()
+    a.implement_segmentation()
+    a.correspondence_searching()
+    a.correspondence_pruning()
+    assert a.correspondences.shape == (n, 6) and a.correspondences.dtype == np.float64
+    lists = a.svl_type
+    order = np.concatenate(lists)
+    scores = np.zeros(n, np.float32)
+    scores[order] = a.scores.cpu().numpy()
+    o = opaths.f2s3_tile(tt["src_pts"], tt["tgt_pts"], d["src_feat"].numpy(), d["tgt_feat"].numpy(), d["label_src"].numpy(),
+                         scores, coeff=1.0, refine_results=True, max_disp_magnitude=5.0)
+    np.testing.assert_array_equal(a.labels.cpu().numpy(), o["labels"])
+    np.testing.assert_array_equal(a.robust_estimate.cpu().numpy(), o["robust"])
+    assert a.final_results.shape[0] == o["rows"].shape[0] > 100
+    np.testing.assert_array_equal(a.final_results[:, :6], o["rows"])
+    np.testing.assert_allclose(a.final_results[:, 6], o["mag"], rtol=1e-12)
+    # the 30 x median gate (f2s3.py:427-431) on the strictly gated rows
+    mag = o["mag"][o["mag"] < 5.0]
+    keep = mag < 30 * np.median(mag)
+    assert a.filtered_results.shape[0] == int(keep.sum())

@@ -145,3 +145,51 @@ def test_voxel_oracle_equals_sequential_hash_map_loop():
         row_of = {k: i for i, k in enumerate(keys)}
         got_rows = [row_of[tuple(int(math.floor((p[c] - vmb[c]) / voxel)) for c in range(3))] for p in pts]
         np.testing.assert_array_equal(inv, np.array(got_rows))
+
+
+def _lists_from_labels(lab, min_pts):
+    u, c = np.unique(lab, return_counts=True)
+    keep = u[c > min_pts]
+    return keep, [np.nonzero(lab == k)[0] for k in keep]
+
+
+def test_coarse_vote_and_mutual_match_reference_method_body(golden_dir):
+    """B4 + B3 + pair order: oracle/desc_nn.py against `Coarse2Fine_Base.coarse_matching_with_different_types` itself
+    (make_golden.make_coarse ran the unmodified method on a stand-in self).  Source patches with a tied top vote are
+    exempt (torch.argsort leaves their order unspecified): 3 forced + whatever the draw produced."""
+    z = np.load(os.path.join(golden_dir, "coarse_method.npz"))
+    lab_s, lab_t, corr2d = z["lab_s"], z["lab_t"], z["corr2d"]
+    idx_spt_src, spt_s = _lists_from_labels(lab_s, int(z["min_pts"][0]))
+    idx_spt_tgt, spt_t = _lists_from_labels(lab_t, int(z["min_pts"][0]))
+    m2, j2, tie2 = desc_nn.coarse_matching_2d_vote(corr2d, lab_t, spt_s, idx_spt_tgt)
+    m3, j3 = desc_nn.coarse_matching_3d(z["cs"], z["fs"], z["ct"], z["ft"], float(z["max_mag"][0]), "nn_mutual")
+    tie = z["tie"]
+    assert tie.sum() >= 3 and tie2.sum() >= 1
+    np.testing.assert_array_equal(tie[m2], tie2)
+    n2 = int(z["fusion_spt_length"][0])
+    assert z["fusion_spt_length"].tolist() == [n2, int(z["only_3d_spt_length"][0])]
+    # 3D pairs: exact, and appended AFTER the 2D pairs in fusion mode
+    np.testing.assert_array_equal(z["only_3d_m"], m3)
+    np.testing.assert_array_equal(z["only_3d_j"], j3)
+    np.testing.assert_array_equal(z["fusion_m"][n2:], m3)
+    np.testing.assert_array_equal(z["fusion_j"][n2:], j3)
+    np.testing.assert_array_equal(z["fusion_m"][:n2], z["only_2d_m"])
+    # 2D pairs: identical on every source patch without a tie
+    ref = dict(zip(z["only_2d_m"].tolist(), z["only_2d_j"].tolist()))
+    mine = dict(zip(m2.tolist(), j2.tolist()))
+    for m in range(len(spt_s)):
+        if not tie[m]:
+            assert ref.get(m, -1) == mine.get(m, -1), m
+    order_ref = [m for m in z["only_2d_m"].tolist() if not tie[m]]
+    assert order_ref == [m for m in m2.tolist() if not tie[m]]            # ascending source patch order
+
+
+def test_merge_matches_reference_function(golden_dir):
+    """M1: oracle merge against the reference's own function run with an exact index (make_golden.make_merge)."""
+    z = np.load(os.path.join(golden_dir, "merge_levels.npz"))
+    levels = [z["level0"], z["level1"], z["level2"]]
+    merged, masks = desc_nn.merge_by_priority(levels)
+    np.testing.assert_array_equal(merged, z["merged"])
+    assert 0 < (~masks[2]).sum() < masks[2].size
+    merged0, _ = desc_nn.merge_by_priority([levels[0][:0], levels[1], levels[2]])
+    np.testing.assert_array_equal(merged0, z["merged_empty0"])
