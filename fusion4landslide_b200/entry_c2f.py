@@ -599,6 +599,8 @@ class StandaloneBase:
         dev = self.data_input_3d.src_pts.device
         tt = self.tile_tensors
         if tt is not None and ("feat_src" in tt or "feat_raw_src" in tt):
+            if "feat_raw_src" in tt:                               # stands in for the descriptor network: like :1982 the
+                self._compute_median_resolution()                  # patch radius is taken from the sub-sampled clouds
             for name in ("src", "tgt"):
                 if "feat_" + name in tt:
                     f = torch.as_tensor(tt["feat_" + name]).to(dev)

@@ -31,14 +31,20 @@ def patch_lists(labels, min_pts):
     return u[keep], [order[s:s + c] for s, c in zip(start[keep], cnt[keep])]
 
 
-def voxel_subsampling(src, tgt, voxel_size):
-    """base.py:1012-1057 for a given voxel size (= the median resolution of the raw tile, :1023)."""
+def voxel_subsampling(src, tgt, voxel_size, v2p_given=None):
+    """base.py:1012-1057 for a given voxel size (= the median resolution of the raw tile, :1023).
+    v2p_given: {'src': idx, 'tgt': idx} replaces the kd-tree answer (a voxel of two points has its centroid
+    equidistant from both up to f32 rounding: the caller checks those rows as ties and injects one choice so that
+    everything downstream is compared on identical maps)."""
     out = {}
     for name, p in (("src", src), ("tgt", tgt)):
         sub64, _ = ovox.voxel_down_sample(np.asarray(p, np.float64), voxel_size)     # :1024-1025
         sub = sub64.astype(np.float32)                                               # pcd2tensor
         raw = np.asarray(p, np.float32)
         _, v2p = cKDTree(raw.astype(np.float64)).query(sub.astype(np.float64), k=1)  # :1038-1042
+        out["idx_voxel2pts_kdtree_" + name] = v2p
+        if v2p_given is not None:
+            v2p = np.asarray(v2p_given[name], np.int64)
         p2v = np.full(raw.shape[0], -1, np.int64)                                    # :1049-1056
         p2v[v2p] = np.arange(sub.shape[0])                # sequential assignment: the last (largest) voxel wins
         out[name + "_pts_sub"], out["idx_voxel2pts_" + name], out["idx_pts2voxel_" + name] = sub, v2p, p2v
@@ -75,7 +81,7 @@ def attention_pool(w, feats, coords, lists, p2v):
 
 def c2f_tile(src, tgt, labels_src, labels_tgt, feat_raw_src, feat_raw_tgt, agg_weights, voxel_size, corr2d=None,
              coarse="only_3d", fine="only_3d", max_magnitude=5.0, min_pts=10, median_max_resolution=None,
-             max_pairs_per_level=None, fine_params=None):
+             max_pairs_per_level=None, fine_params=None, v2p_given=None):
     """The fusion method on one tile.  labels_*: list of per-level label arrays (n,).  coarse/fine: 'only_3d' |
     'fusion' (2D-vote pairs first, 2D-lifted matches appended in the fine stage).  max_pairs_per_level bounds the
     fine-matching sample (CPU arm of bench.py); the merge then covers the sampled pairs only."""
@@ -83,7 +89,7 @@ def c2f_tile(src, tgt, labels_src, labels_tgt, feat_raw_src, feat_raw_tgt, agg_w
     t0 = time.perf_counter()
     src = np.asarray(src, np.float32)
     tgt = np.asarray(tgt, np.float32)
-    vs = voxel_subsampling(src, tgt, voxel_size)
+    vs = voxel_subsampling(src, tgt, voxel_size, v2p_given)
     sec["voxel_subsampling"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     med = oknn.median_resolution(vs["src_pts_sub"], vs["tgt_pts_sub"]) if median_max_resolution is None \

@@ -68,14 +68,20 @@ def test_coarse2fine_class_vs_oracle(cuda, golden_dir, mode):
     med_raw = oknn.median_resolution(d["src"].numpy(), d["tgt"].numpy())
     assert abs(voxel - med_raw) < 1e-5 * med_raw
     med2 = float(c.para.median_max_resolution)
+    di, do = c.data_interim, c.data_output
+    v2p = {k: di["idx_voxel2pts_" + k].cpu().numpy() for k in ("src", "tgt")}
     o = opaths.c2f_tile(d["src"].numpy(), d["tgt"].numpy(), [x.numpy() for x in levels_s], [x.numpy() for x in levels_t],
                         d["src_feat"].numpy(), d["tgt_feat"].numpy(), w, voxel_size=voxel,
                         corr2d=d["corr2d"].numpy() if mode == "fusion" else None, coarse=mode, fine=mode,
-                        median_max_resolution=float(np.float32(med2)))
-    di, do = c.data_interim, c.data_output
-    # voxel subsampling + maps, descriptor matches
+                        median_max_resolution=float(np.float32(med2)), v2p_given=v2p)
+    # voxel subsampling + maps: centroids bit-equal; nearest raw point identical except at distance ties (a voxel of
+    # two points: its centroid is equidistant from both up to rounding), which the fp64 kd-tree resolves arbitrarily
     np.testing.assert_array_equal(di.src_pts_sub.cpu().numpy(), o["src_pts_sub"])
-    np.testing.assert_array_equal(di.idx_voxel2pts_src.cpu().numpy(), o["idx_voxel2pts_src"])
+    for k, raw in (("src", d["src"].numpy()), ("tgt", d["tgt"].numpy())):
+        tie = oknn.tie_rows(o[k + "_pts_sub"], raw, 1)
+        same = v2p[k] == o["idx_voxel2pts_kdtree_" + k]
+        assert (same | tie).all(), (k, int((~same & ~tie).sum()))
+        assert tie.mean() < 0.2
     np.testing.assert_array_equal(di.idx_pts2voxel_tgt.cpu().numpy(), o["idx_pts2voxel_tgt"])
     med_sub = oknn.median_resolution(o["src_pts_sub"], o["tgt_pts_sub"])
     assert abs(med2 - med_sub) < 1e-5 * med_sub
@@ -97,7 +103,13 @@ def test_coarse2fine_class_vs_oracle(cuda, golden_dir, mode):
         assert dn.shape == od.shape and dn.shape[0] > 1000, (lv, dn.shape, od.shape)
         np.testing.assert_array_equal(dn[:, :3], od[:, :3])
         close = np.abs(dn - od).max(1) < TOL + 2 * np.spacing(np.float32(np.abs(od).max()))
-        assert close.mean() > 0.99, (lv, close.mean())
+        # per pair: a pair whose ICP stopped one iteration apart in the two implementations (|delta| < 1e-6 relative
+        # convergence test, Open3D semantics) moves by up to ~1e-4 m; such path flips are counted, not hidden
+        sizes = [x.shape[0] for x in ol["fine"]["dense"] if x is not None]
+        ends = np.cumsum(sizes)
+        bad_pairs = sum(1 for a, b in zip(ends - sizes, ends) if not close[a:b].all())
+        assert bad_pairs <= max(1, len(sizes) // 100), (lv, bad_pairs, len(sizes))
+        assert np.abs(dn - od).max() < 2e-3, lv
     # merged result: level-1 rows first and complete, later levels only add new source points
     merged = do.corres_3d_refine_apply_icp.cpu().numpy()
     om = o["dense"]
