@@ -57,13 +57,28 @@ def parse():
                     help="N > 1: 'fused' = the D5 kernel stores every dense row into all peers' fields over NVLink "
                          "(exchange.PeerExchange), 'nccl' = all_gather_into_tensor after the step (baseline)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="patch pairs in the CPU sample (0 = auto)")
+    ap.add_argument("--scene", default="v2", choices=["v1", "v2"],
+                    help="v2 (default): SURVEY 8(d) scenes -- epoch 2 an INDEPENDENT resample, nested patch hierarchy, "
+                         "~2 %% of the points in patches <= 10 points.  v1: round-1 scenes (epoch 2 = jittered epoch 1)")
+    ap.add_argument("--configs", default="C1,C2,C3,C4",
+                    help="BASELINE.json configs measured next to the headline workload on rank 0 (N = 1 only): "
+                         "comma list out of C1,C2,C3,C4, or 'none'")
+    ap.add_argument("--config-steps", type=int, default=2)
     return ap.parse_args()
 
 
 def workload_name(a):
     return ("C5: %d tiles x %d pts/epoch (%.1fM-point epoch pair), ~%d-pt patches, fusion4landslide fine-matching "
-            "path (A1 median-resolution kNN + F2/F3/D2/E1/D5/A4) per tile" %
-            (a.tiles, a.tile_pts, a.tiles * a.tile_pts / 1e6, a.patch_pts))
+            "path (A1 median-resolution kNN + F2/F3/D2/E1/D5/A4) per tile; scene %s" %
+            (a.tiles, a.tile_pts, a.tiles * a.tile_pts / 1e6, a.patch_pts,
+             "v2 (independent epochs, SURVEY 8d)" if a.scene == "v2" else "v1 (epoch 2 = jittered epoch 1)"))
+
+
+def make_c5_tile(a, seed, dev):
+    from fusion4landslide_b200 import synth
+    if a.scene == "v1":
+        return synth.make_tile(a.tile_pts, seed=seed, device=dev, patch_pts=a.patch_pts, origin=(0.0, 0.0))
+    return synth.make_scene(a.tile_pts, seed=seed, device=dev)          # label_src / label_tgt: ~256-point patches
 
 
 # ---------------------------------------------------------------------------------------------
@@ -208,8 +223,7 @@ def run_b200(a):
     my_tiles = list(range(rank, a.tiles, world))           # equal tiles: round-robin == LPT
     tiles, host_tiles = [], []
     for t in my_tiles:
-        d = synth.make_tile(a.tile_pts, seed=a.seed * 100003 + t, device=dev, patch_pts=a.patch_pts,
-                            origin=(0.0, 0.0))
+        d = make_c5_tile(a, a.seed * 100003 + t, dev)
         tiles.append(pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"]))
         del d
     torch.cuda.synchronize()
@@ -475,9 +489,21 @@ def run_b200(a):
                 kernel_table[name]["hbm_frac"] = b / (kernel_table[name]["ms_avg"] * 1e-3) / 1e9 / peak
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ------------------
-    cpu = None
+    input_gb = sum(t.nbytes() for t in tiles) * world / 1e9
+    cpu, parity = None, None
     if rank == 0 and not a.no_cpu_baseline:
-        cpu = cpu_arm_sample(a, tiles[0], cfg, target_seconds=15.0)
+        raw = []
+        cpu = cpu_arm_sample(a, tiles[0], cfg, target_seconds=15.0, raw_out=raw)
+        parity = c5_parity(raw[0][0], raw[0][1], tiles[0], outs[0])
+
+    # ---- BASELINE configs C1-C4 (rank 0, single GPU runs only) -----------------------------------
+    configs_out = None
+    if rank == 0 and world == 1 and a.configs.lower() != "none":
+        used_graph = graph is not None
+        del tiles, outs, outs_par, arenas, dense_arena, T_arena, graphs, graph
+        graph = True if used_graph else None
+        torch.cuda.empty_cache()
+        configs_out = run_configs(a, dev, L)
 
     if rank == 0:
         line = {
@@ -490,11 +516,12 @@ def run_b200(a):
                                        "NVLink (peer memory), transforms + row counts all-gathered over NCCL" % world) if fused
                        else "tile-sharded x%d, NCCL all-gather of transforms + dense DVF" % world,
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
-                             (sum(t.nbytes() for t in tiles) * world / 1e9),
+                             input_gb,
                        "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type, "streams": a.streams,
                        "cuda_graph": graph is not None, "a1_side_stream": bool(sides)},
             "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline,
-            "kernels": kernel_table, "cpu_baseline": cpu, "breakdown": breakdown,
+            "kernels": kernel_table, "cpu_baseline": cpu, "parity": parity, "breakdown": breakdown,
+            "configs": configs_out,
         }
         print(json.dumps(line))
     if world > 1:
@@ -502,7 +529,31 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-def cpu_arm_sample(a, tile, cfg, target_seconds=15.0, workers=None, pairs=None):
+def c5_parity(r, spt_src, tile, out):
+    """In-run parity of tile 0: the CPU arm's (oracle) per-pair results against the GPU's, reported in the bench line
+    (tie / path-flip counts are part of the gate)."""
+    import numpy as np
+    k = r["pairs"]
+    Kg, Sg, Ig = (x[:k].cpu().numpy() for x in (out.K, out.status, out.iters))
+    ok = (r["status"] == 0) & (Sg == 0)
+    same = ok & (Ig == r["iters"])
+    Tg = out.T[:k].cpu().numpy().astype(np.float64)
+    src = tile.src.cpu().numpy().astype(np.float64)
+    worst = 0.0
+    for q in np.nonzero(same)[0][:2000]:
+        P = src[spt_src[q]]
+        To = r["T"][q].astype(np.float64)
+        worst = max(worst, float(np.abs((P @ Tg[q][:3, :3].T + Tg[q][:3, 3]) - (P @ To[:3, :3].T + To[:3, 3])).max()))
+    rejected = int((r["status"] == 1).sum())
+    return {"checked_against": "oracle/cpu_path.py on the CPU-sampled pairs of tile 0, in this run", "pairs_checked": int(k),
+            "K_mismatch": int((Kg != r["K"]).sum()), "status_mismatch": int((Sg != r["status"]).sum()),
+            "rigidity_rejected_pairs": rejected, "rigidity_flips": int(((Sg == 1) != (r["status"] == 1)).sum()),
+            "fitted_pairs": int(ok.sum()), "icp_path_flips": int((ok & (Ig != r["iters"])).sum()),
+            "icp_iterations_mean": float(r["iters"][ok].mean()) if ok.any() else 0.0,
+            "max_abs_dvf_diff_m_same_path": worst, "tolerance_m": 1e-5}
+
+
+def cpu_arm_sample(a, tile, cfg, target_seconds=15.0, workers=None, pairs=None, raw_out=None):
     """Time the oracle port on a bounded sample of tile 0 (host copy).  Returns the cpu_baseline dict."""
     from oracle import cpu_path
     src = tile.src.cpu().numpy()
@@ -522,6 +573,8 @@ def cpu_arm_sample(a, tile, cfg, target_seconds=15.0, workers=None, pairs=None):
               num_min_fine_match=cfg.num_min_fine_match, icp_refine=cfg.icp_refine, assign_type=cfg.assign_type,
               output_tgt2src=cfg.output_tgt2src, icp_threshold=cfg.icp_threshold, icp_max_iter=cfg.icp_max_iter)
     r = cpu_path.run_tile(src, tgt, corr, spt_src, spt_tgt, workers=workers, max_pairs=pairs, **kw)
+    if raw_out is not None:
+        raw_out.append((r, spt_src))
     # the median-resolution kNN covers the whole tile, the fine matching only the sampled pairs:
     # scale the kNN time by the sampled fraction so both legs describe the same points
     frac = r["src_points"] / max(1, src.shape[0])
@@ -532,6 +585,422 @@ def cpu_arm_sample(a, tile, cfg, target_seconds=15.0, workers=None, pairs=None):
                       "patch pairs spread over %d forked workers" %
                       (r["pairs"], Q, r["src_points"], r["seconds_fine"], r["seconds_median"], frac, workers),
             "seconds": secs}
+
+
+
+# =================================================================================================
+# BASELINE.json configs C1-C4 next to the headline (C5) workload: each returns a dict with its own value,
+# e2e, roofline (dominant kernel by in-stream CUDA-event time) and CPU leg.  Rank 0, one GPU.
+# =================================================================================================
+def _peaks_full():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]),
+                "tf_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "MEASURED_PEAKS.json"}
+    return {"hbm": 6650.0, "tf_burst": 1650.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def _timed(fn, warmup, steps, dev):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / steps, out
+
+
+def _profiled(fn, L, dev):
+    """One extra pass with the library's in-stream per-kernel events: {kernel: {ms_total, launches, share}}."""
+    from fusion4landslide_b200 import _lib
+    L.f4l_profile_reset()
+    L.f4l_profile_enable(1)
+    L.f4l_launch_count_reset()
+    fn()
+    torch.cuda.synchronize(dev)
+    L.f4l_profile_enable(0)
+    launches = int(L.f4l_launch_count())
+    tab = _lib.profile_table()
+    tot = sum(v[0] for v in tab.values()) or 1.0
+    kern = {k: {"ms_total": round(v[0], 4), "launches": v[1], "share": round(v[0] / tot, 4)}
+            for k, v in sorted(tab.items(), key=lambda kv: -kv[1][0])}
+    return kern, launches
+
+
+def _roofline(kern, work, peaks, note=""):
+    """work: {kernel name: ("hbm", bytes per step) | ("tensor", flop per step)} for the kernels that can dominate."""
+    top = next(iter(kern))
+    k = kern[top]
+    r = {"kernel": top, "share_of_step": k["share"], "ms_per_step": k["ms_total"], "launches_per_step": k["launches"],
+         "peak_source": peaks["source"], "note": note}
+    w = work.get(top)
+    if w is None:
+        r.update(bound=None, achieved=None, peak=None, unit=None, frac=None, traffic=None)
+        return r
+    kind, amount = w
+    sec = k["ms_total"] * 1e-3
+    if kind == "tensor":
+        ach = amount / sec / 1e12
+        r.update(bound="tensor", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=ach / peaks["tf_sustained"],
+                 frac_of_burst=ach / peaks["tf_burst"], algorithmic_flop_per_step=amount)
+    else:
+        ach = amount / sec / 1e9
+        r.update(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
+                 algorithmic_bytes_per_step=amount)
+    tr = ncu_traffic(top)
+    r["traffic"] = tr[0] if tr else None
+    r["traffic_source"] = tr[1] if tr else None
+    ctx = ncu_metrics(top, ("sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active",
+                            "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+                            "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+                            "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+                            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                            "smsp__issue_active.avg.pct_of_peak_sustained_active"))
+    if ctx:
+        r["ncu_context"] = ctx
+    return r
+
+
+def _cpu_backends():
+    """Which of the reference's third-party back-ends exist on this host: the CPU legs use
+    them when importable and the exact restatements otherwise."""
+    import importlib.util
+    return {m: importlib.util.find_spec(m) is not None for m in ("open3d", "hnswlib", "faiss", "sklearn", "scipy")}
+
+
+def _cpu_desc_nn_rate(fs, ft, rows, backends):
+    """Seconds per source row of the descriptor search on the host, the way the reference does it:
+    hnswlib HNSW (M=12, efC=300, efS=300, 16 threads; f2s3_brienz.yaml:43-46) when the wheel exists, else the
+    reference's exact branch: torch.cdist + min in batches of 1024 (base.py:2783-2815, 'cdist_cpu'), all cores."""
+    fs = fs[:rows].contiguous()
+    if backends["hnswlib"]:
+        import hnswlib
+        t0 = time.perf_counter()
+        idx = hnswlib.Index(space="l2", dim=ft.shape[1])
+        idx.init_index(max_elements=ft.shape[0], ef_construction=300, M=12)
+        idx.set_num_threads(16)
+        idx.add_items(ft.numpy())
+        t_build = time.perf_counter() - t0
+        idx.set_ef(300)
+        t0 = time.perf_counter()
+        idx.knn_query(fs.numpy(), k=1)
+        return (time.perf_counter() - t0) / rows, "hnswlib HNSW M=12 efC=300 efS=300 (+%.1f s index build per tile)" % t_build, t_build
+    t0 = time.perf_counter()
+    for i in range(0, rows, 1024):
+        d = torch.cdist(fs[i:i + 1024], ft)
+        d.min(dim=1)
+    return (time.perf_counter() - t0) / rows, "torch.cdist + min, batches of 1024 (base.py:2783-2815), %d torch threads" % torch.get_num_threads(), 0.0
+
+
+def bench_c1(a, dev, L, peaks):
+    """C1: Piecewise ICP (main_piecewise_icp.py) on one synthetic 1 M-point tile pair with known block shift."""
+    import numpy as np
+    from fusion4landslide_b200 import ops, synth
+    n = 1_000_000
+    d = synth.make_scene(n, seed=a.seed + 11, device=dev)
+    src64, tgt64 = d["src"].double().contiguous(), d["tgt"].double().contiguous()
+    smax, npmin = 5.0, 10
+    step = lambda: ops.piecewise_icp(src64, tgt64, smax, npmin)
+    ms, out = _timed(step, max(a.warmup, 2), a.config_steps + 1, dev)
+    counts = out[2].tolist()
+    rows = counts[0]
+    kern, launches = _profiled(step, L, dev)
+    work = {name: ("hbm", b) for name, b in (("cub_radix_sort", 2 * 12 * 2 * n * 3), ("k_pw_codes", 2 * n * (24 + 12)),
+                                              ("k_pw_emit", 2 * n * 24 + rows * 48 + rows * 8), ("k_pw_centroids", 2 * n * 28),
+                                              ("k_pw_leaves", 2 * n * 12), ("k_pw_order", 2 * n * 8))}
+    res = {"workload": "C1: piecewise ICP, 1 tile, N = M = %d points, smax %.0f m, number_points_min %d" % (n, smax, npmin),
+           "metric": METRIC, "unit": UNIT, "value": rows / (ms * 1e-3), "ms_per_step": ms, "steps": a.config_steps + 1,
+           "dvf_points_per_step": rows, "src_points_per_step": n, "dtype": "f64", "gpu_launches_per_step": launches,
+           "cells": {"src": counts[2], "tgt": counts[3], "octree_depth": counts[4], "unstable": counts[5]},
+           "kernels": dict(list(kern.items())[:6]),
+           "roofline": _roofline(kern, work, peaks, "bytes: keys+values of the radix-sort passes / the points and rows a kernel streams")}
+    # e2e: pinned host float64 clouds -> device -> path -> rows back on the host
+    hs, ht = src64.cpu().pin_memory(), tgt64.cpu().pin_memory()
+    host_rows = torch.empty((n + 8, 6), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        s_, t_ = hs.to(dev, non_blocking=True), ht.to(dev, non_blocking=True)
+        o = ops.piecewise_icp(s_, t_, smax, npmin)
+        c = o[2].tolist()
+        host_rows[:c[0]].copy_(o[0][:c[0]], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return c[0]
+    ms_e, r_e = _timed(e2e_step, 1, a.config_steps, dev)
+    res["e2e"] = {"value": r_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e, "h2d_bytes_per_step": 2 * n * 24,
+                  "d2h_bytes_per_step": r_e * 48 + 24}
+    if not a.no_cpu_baseline:
+        from oracle import piecewise as opw
+        s_np, t_np = src64.cpu().numpy(), tgt64.cpu().numpy()
+        t0 = time.perf_counter()
+        o = opw.piecewise_icp(s_np, t_np, smax, npmin)
+        sec = time.perf_counter() - t0
+        g = out[0][:rows].cpu().numpy()
+        same_rows = o["dvfs"].shape[0] == rows
+        err = float(np.abs(g - o["dvfs"]).max()) if same_rows else None
+        res["cpu_baseline"] = {"value": o["dvfs"].shape[0] / sec, "unit": UNIT, "cores": 1, "kind": "port", "seconds": sec,
+                               "sample": "the whole 1 M-point tile; oracle/piecewise.py (vectorised numpy + cKDTree restatement of "
+                                         "piecewise_icp.py:89-216; the reference walks an Open3D octree in Python)"}
+        res["parity"] = {"rows_equal": bool(same_rows), "max_abs_row_diff_m": err}
+    del d, src64, tgt64
+    return res
+
+
+def bench_c2(a, dev, L, peaks):
+    """C2: F2S3-style descriptor mutual-NN matching + weighted SVD, 4 tiles x 1 M points per epoch, D = 32 and 64."""
+    import numpy as np
+    from fusion4landslide_b200 import ops, pipeline, synth
+    n, n_tiles = 1_000_000, 4
+    res = {"workload": "C2: F2S3 path, %d tiles x %d pts/epoch: A1 + exact descriptor NN both directions (mutual) + per-"
+                       "supervoxel weighted Kabsch -> median filter -> refit + magnitude gate; weights in [0,1] handed in" % (n_tiles, n),
+           "metric": METRIC, "unit": UNIT, "dtype": "fp16 tensor-core candidates + f64 re-rank (descriptor NN), f32/f64 (Kabsch)", "by_D": {}}
+    backends = _cpu_backends()
+    for D in (32, 64):
+        tiles = []
+        for t in range(n_tiles):
+            d = synth.make_scene(n, seed=a.seed * 7919 + 100 + t, device=dev, desc_dim=D)
+            _, ptr, idx, _ = ops.labels_to_csr(d["label_src"].contiguous(), 10)
+            g = torch.Generator(device=dev).manual_seed(t)
+            w = torch.rand(n, generator=g, device=dev)
+            w = torch.where(torch.rand(n, generator=g, device=dev) < 0.5, torch.ones_like(w), w)
+            tiles.append(dict(src=d["src"], tgt=d["tgt"], fs=d["src_feat"], ft=d["tgt_feat"], ptr=ptr, idx=idx, w=w,
+                              lab=d["label_src"]))
+            del d
+
+        def step():
+            outs = []
+            for t in tiles:
+                outs.append(pipeline.f2s3_tile(t["src"], t["tgt"], t["fs"], t["ft"], t["ptr"], t["idx"], weights=t["w"],
+                                               refine_results=True, max_disp_magnitude=5.0, mutual=True))
+            return outs
+        ms, outs = _timed(step, 1, a.config_steps, dev)
+        rows = sum(int(o["rows"].shape[0]) for o in outs)
+        kern, launches = _profiled(step, L, dev)
+        flop = 2.0 * n * n * D * 2 * n_tiles                       # both directions
+        work = {"k_desc_nn_tc": ("tensor", flop)}
+        r = {"value": rows / (ms * 1e-3), "src_points_per_sec": n * n_tiles / (ms * 1e-3), "ms_per_step": ms,
+             "steps": a.config_steps, "dvf_points_per_step": rows, "src_points_per_step": n * n_tiles,
+             "gpu_launches_per_step": launches, "kernels": dict(list(kern.items())[:6]),
+             "mutual_fraction": float(sum((o["scores"] > 0).float().mean().item() for o in outs) / n_tiles),
+             "roofline": _roofline(kern, work, peaks, "useful FLOP = 2*N*M*D per direction (the kernel issues D+16 K-columns); "
+                                                      "peak = cuBLAS bf16 sustained (kernel timed inside a long step)")}
+        # e2e: pinned host inputs -> device -> path -> kept rows + per-supervoxel transforms back
+        host = [{k: v.cpu().pin_memory() for k, v in t.items() if k != "lab"} for t in tiles[:1]]
+
+        def e2e_step():
+            h = host[0]
+            tt = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+            o = pipeline.f2s3_tile(tt["src"], tt["tgt"], tt["fs"], tt["ft"], tt["ptr"], tt["idx"], weights=tt["w"],
+                                   refine_results=True, max_disp_magnitude=5.0, mutual=True)
+            back = [o["rows"].cpu(), o["mag"].cpu(), o["R"].cpu(), o["t"].cpu()]
+            return o["rows"].shape[0], sum(x.numel() * x.element_size() for x in back)
+        ms_e, (r_e, d2h) = _timed(e2e_step, 1, max(1, a.config_steps - 1), dev)
+        r["e2e"] = {"value": r_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e, "tiles_per_step": 1,
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host[0].values()), "d2h_bytes_per_step": d2h}
+        if not a.no_cpu_baseline:
+            from oracle import paths as opaths
+            t0_ = tiles[0]
+            fs_h, ft_h = t0_["fs"].cpu(), t0_["ft"].cpu()
+            sample_rows = 4096
+            per_row, how, t_build = _cpu_desc_nn_rate(fs_h, ft_h, sample_rows, backends)
+            per_row_b, _, t_build_b = _cpu_desc_nn_rate(ft_h, fs_h, sample_rows, backends)
+            o = opaths.f2s3_tile(t0_["src"].cpu().numpy(), t0_["tgt"].cpu().numpy(), fs_h.numpy(), ft_h.numpy(),
+                                 t0_["lab"].cpu().numpy(), t0_["w"].cpu().numpy(), refine_results=True, max_disp_magnitude=5.0,
+                                 mutual=False, max_rows=60_000, max_segments=200)
+            from oracle import knn as oknn
+            t1 = time.perf_counter()
+            oknn.median_resolution(t0_["src"].cpu().numpy()[:250_000], t0_["tgt"].cpu().numpy()[:250_000])
+            t_med = (time.perf_counter() - t1) * 4.0
+            prune_rate = o["seconds"]["pruning"] / max(1, o["seconds"]["pruning_rows"])
+            n_seg_rows = int(t0_["idx"].numel())
+            sec_tile = (per_row + per_row_b) * n + t_build + t_build_b + prune_rate * n_seg_rows + t_med
+            r["cpu_baseline"] = {"value": (rows / n_tiles) / sec_tile, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                 "seconds_per_tile_estimate": sec_tile,
+                                 "sample": "tile 0, stage by stage, scaled to the tile: descriptor search %d rows x 1 M both directions "
+                                           "(%s): %.2e s/row; pruning of 200 supervoxels (oracle/rigid.py filter_input_tail): %.2e s/row; "
+                                           "median resolution on 250 k points x 4" % (sample_rows, how, per_row, prune_rate),
+                                 "backends_present": backends}
+        res["by_D"]["D%d" % D] = r
+        del tiles, outs
+        torch.cuda.empty_cache()
+    # headline of the config = D = 32 (BASELINE.json configs[1]); D = 64 beside it
+    for k in ("value", "ms_per_step", "steps", "dvf_points_per_step", "src_points_per_step", "e2e", "roofline", "cpu_baseline",
+              "gpu_launches_per_step"):
+        if k in res["by_D"]["D32"]:
+            res[k] = res["by_D"]["D32"][k]
+    return res
+
+
+def _c2f_models(dev):
+    """Random-init superpoint aggregation network of the reference's architecture (64-64-64; no checkpoint offline...
+    the shipped parameters travel with tests/golden/nets_shipped.npz and are used when present)."""
+    import numpy as np
+    from fusion4landslide_b200 import nets
+    m = nets.ClusterFeatureNetWithAttention()
+    p = os.path.join(ROOT, "tests", "golden", "nets_shipped.npz")
+    w = None
+    if os.path.exists(p):
+        z = np.load(p)
+        w = {k[4:]: z[k] for k in z.files if k.startswith("agg/")}
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    else:
+        torch.manual_seed(0)
+        w = {k: v.numpy() for k, v in m.state_dict().items()}
+    return m.to(dev).eval(), w
+
+
+def bench_c2f(a, dev, L, peaks, fusion):
+    """C3 (fusion_3d: coarse-to-fine on 3 superpoint levels, 16 tiles x 625 k) / C4 (C3 + 2D-lifted matches: 2D-vote
+    coarse pairs and the lifted correspondences in the fine stage), through the CLASS-LEVEL entry point
+    Coarse2Fine(cfg).implement_c2f_matching() on in-memory tiles."""
+    import numpy as np
+    from fusion4landslide_b200 import configs, synth
+    from fusion4landslide_b200.entry_c2f import Coarse2Fine
+    n, n_tiles, D = 625_000, 16, 64
+    mode = "fusion" if fusion else "only_3d"
+    model, w_np = _c2f_models(dev)
+    tiles = []
+    for t in range(n_tiles):
+        d = synth.make_scene(n, seed=a.seed * 104729 + 300 + t, device=dev, desc_dim=D, frac_2d=0.05 if fusion else 0.0)
+        tt = dict(src_pts=d["src"], tgt_pts=d["tgt"], partition_src=[d["labels_src"][k] for k in (1, 2, 3)],
+                  partition_tgt=[d["labels_tgt"][k] for k in (1, 2, 3)], feat_raw_src=d["src_feat"], feat_raw_tgt=d["tgt_feat"])
+        if fusion:
+            tt["corres_3d_from_2d_idx"] = d["corr2d"]
+        tiles.append(tt)
+        del d
+    last = {}
+
+    def run_tile(tt):
+        c = Coarse2Fine(configs.fusion_config(tt, mode=mode, levels=[1, 2, 3], feat_aggregate_model=model, device=str(dev)))
+        c.implement_c2f_matching()
+        return c
+
+    def step():
+        rows = 0
+        for tt in tiles:
+            c = run_tile(tt)
+            rows += int(c.data_output.corres_3d_refine_apply_icp.shape[0])
+            last["c"] = c
+        return rows
+    ms, rows = _timed(step, 1, a.config_steps, dev)
+    kern, launches = _profiled(lambda: run_tile(tiles[0]), L, dev)
+    c = last["c"]
+    n_sub = int(c.data_interim.src_pts_sub.shape[0]), int(c.data_interim.tgt_pts_sub.shape[0])
+    work = {"k_desc_nn_tc": ("tensor", 2.0 * n_sub[0] * n_sub[1] * D)}
+    name = "C4" if fusion else "C3"
+    res = {"workload": "%s: fusion_3d coarse-to-fine, %d tiles x %d pts/epoch, 3 superpoint levels (~64/192/576 pts)%s; per tile: voxel "
+                       "subsampling (A1 A2) -> patch tables (F6) -> exact descriptor NN + gate + scatter (B2) -> per level attention "
+                       "pooling (8f-2), mutual coarse NN (B3)%s, fused fine matching (F2 F3 D2 E1 D5 A4) -> level merge (M1); "
+                       "through Coarse2Fine(cfg).implement_c2f_matching()" %
+                       (name, n_tiles, n, " + 2D-lifted matches of 5 % of the source points" if fusion else "",
+                        " + 2D vote (B4)" if fusion else ""),
+           "metric": METRIC, "unit": UNIT, "value": rows / (ms * 1e-3), "src_points_per_sec": n * n_tiles / (ms * 1e-3),
+           "ms_per_step": ms, "steps": a.config_steps, "dvf_points_per_step": rows, "src_points_per_step": n * n_tiles,
+           "dtype": "fp16 tensor-core candidates + f64 re-rank (descriptor NN), f32 i/o + f64 accumulation (fits)",
+           "gpu_launches_per_tile": launches, "voxels_per_tile": list(n_sub),
+           "pairs_per_level_last_tile": [len(x) for x in c.data_output.spt_corres_src_multiple],
+           "kernels_tile0": dict(list(kern.items())[:8]),
+           "roofline": _roofline(kern, work, peaks, "per tile (profiled pass over tile 0); useful FLOP = 2*N_sub*M_sub*D")}
+    # e2e: the same call with HOST tensors (pinned) in tile_tensors, merged DVF rows back on the host
+    host = {k: ([x.cpu().pin_memory() for x in v] if isinstance(v, list) else v.cpu().pin_memory()) for k, v in tiles[0].items()}
+
+    def e2e_step():
+        c = run_tile(host)
+        do = c.data_output
+        back = [do.corres_3d_refine_apply_icp.cpu(), do.corres_3d_refine_apply_icp_discrete.cpu()]
+        return int(back[0].shape[0]), sum(x.numel() * x.element_size() for x in back)
+    ms_e, (r_e, d2h) = _timed(e2e_step, 1, max(1, a.config_steps - 1), dev)
+    h2d = sum(sum(x.numel() * x.element_size() for x in v) if isinstance(v, list) else v.numel() * v.element_size()
+              for v in host.values())
+    res["e2e"] = {"value": r_e / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e, "tiles_per_step": 1,
+                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    if not a.no_cpu_baseline:
+        from oracle import paths as opaths
+        backends = _cpu_backends()
+        tt = tiles[-1]                                          # the tile `c` holds the GPU results of
+        di = c.data_interim
+        fs_sub, ft_sub = di.tile_pts_sub_feat_src.cpu(), di.tile_pts_sub_feat_tgt.cpu()
+        sample_rows = 4096
+        per_row, how, t_build = _cpu_desc_nn_rate(fs_sub, ft_sub, sample_rows, backends)
+        pairs_cap = 60
+        o = opaths.c2f_tile(tt["src_pts"].cpu().numpy(), tt["tgt_pts"].cpu().numpy(), [x.cpu().numpy() for x in tt["partition_src"]],
+                            [x.cpu().numpy() for x in tt["partition_tgt"]], tt["feat_raw_src"].cpu().numpy(),
+                            tt["feat_raw_tgt"].cpu().numpy(), w_np, voxel_size=float(c.method.voxel_size),
+                            corr2d=tt["corres_3d_from_2d_idx"].cpu().numpy() if fusion else None, coarse=mode, fine=mode,
+                            max_pairs_per_level=pairs_cap, corr3d_given=di.corres_3d_voxel_from_3d_idx.cpu().numpy(),
+                            v2p_given={k: di["idx_voxel2pts_" + k].cpu().numpy() for k in ("src", "tgt")})
+        sec = o["seconds"]
+        pairs_all = sum(len(x) for x in c.data_output.spt_corres_src_multiple)
+        pairs_done = sum(len(l["m"]) for l in o["levels"])
+        pts_done = sum(l["n_src_points"] for l in o["levels"])
+        pts_all = sum(int(sum(x.numel() for x in lv)) for lv in c.data_output.spt_corres_src_multiple)
+        fine_full = sec["fine"] * pts_all / max(1, pts_done)
+        sec_tile = (sec["voxel_subsampling"] + sec["median_resolution"] + per_row * n_sub[0] + t_build + sec["pooling"] +
+                    sec["coarse"] + fine_full + sec["merge"])
+        rows_tile = rows / n_tiles
+        res["cpu_baseline"] = {"value": rows_tile / sec_tile, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "seconds_per_tile_estimate": sec_tile,
+                               "stages_s": {"voxel_subsampling": sec["voxel_subsampling"], "median_resolution": sec["median_resolution"],
+                                            "descriptor_nn": per_row * n_sub[0] + t_build, "pooling": sec["pooling"], "coarse": sec["coarse"],
+                                            "fine_scaled": fine_full, "merge_of_sample": sec["merge"]},
+                               "sample": "one tile, stage by stage (oracle/paths.py c2f_tile): descriptor search %d rows x %d (%s) scaled to "
+                                         "%d rows; fine matching of %d of %d patch pairs (one Python process, like the reference's loop) "
+                                         "scaled by source points; all other stages on the whole tile" %
+                                         (sample_rows, n_sub[1], how, n_sub[0], pairs_done, pairs_all),
+                               "backends_present": backends}
+        # in-run parity of the sampled pairs against the GPU result of the same tile
+        flips = bad_status = bad_K = checked = fitted = pair_lists_equal = 0
+        worst = 0.0
+        for lv, l in enumerate(o["levels"]):
+            k = len(l["m"])
+            fr = c.fine_results_multiple[lv]
+            of = l["fine"]
+            firsts_g = [int(x[0]) for x in c.data_output.spt_corres_src_multiple[lv][:k]]
+            _, spt_s = opaths.patch_lists(tt["partition_src"][lv].cpu().numpy(), 10)
+            if firsts_g != [int(spt_s[m_][0]) for m_ in l["m"]]:
+                continue
+            pair_lists_equal += 1
+            Kg, Sg, Ig = (x[:k].cpu().numpy() for x in (fr.K, fr.status, fr.iters))
+            checked += k
+            bad_K += int((Kg != of["K"]).sum())
+            bad_status += int((Sg != of["status"]).sum())
+            ok = (of["status"] == 0) & (Sg == 0)
+            fitted += int(ok.sum())
+            flips += int((ok & (Ig != of["iters"])).sum())
+            Tg = fr.T[:k].cpu().numpy().astype(np.float64)
+            for q in np.nonzero(ok & (Ig == of["iters"]))[0]:
+                P = tt["src_pts"][torch.as_tensor(spt_s[l["m"][q]])].cpu().numpy().astype(np.float64)
+                To = of["T"][q].astype(np.float64)
+                worst = max(worst, float(np.abs((P @ Tg[q][:3, :3].T + Tg[q][:3, 3]) - (P @ To[:3, :3].T + To[:3, 3])).max()))
+        res["parity"] = {"checked_against": "oracle/paths.py on the CPU-sampled pairs of one tile, in this run",
+                         "levels_with_identical_pair_lists": pair_lists_equal, "pairs_checked": checked, "K_mismatch": bad_K,
+                         "status_mismatch": bad_status, "fitted_pairs": fitted, "icp_path_flips": flips,
+                         "max_abs_dvf_diff_m_same_path": worst,
+                         "ties_2d_vote": int(sum(int(l["tie"].sum()) for l in o["levels"]))}
+    del tiles
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_configs(a, dev, L):
+    peaks = _peaks_full()
+    want = [] if a.configs.lower() == "none" else [c.strip().upper() for c in a.configs.split(",") if c.strip()]
+    out = {}
+    fns = {"C1": lambda: bench_c1(a, dev, L, peaks), "C2": lambda: bench_c2(a, dev, L, peaks),
+           "C3": lambda: bench_c2f(a, dev, L, peaks, False), "C4": lambda: bench_c2f(a, dev, L, peaks, True)}
+    for name in want:
+        t0 = time.perf_counter()
+        try:
+            out[name] = fns[name]()
+        except Exception as e:                       # one config failing must not take the headline line down
+            import traceback
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e), "traceback": traceback.format_exc()[-1500:]}
+            torch.cuda.empty_cache()
+        out[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 def run_dips(a):
@@ -620,7 +1089,7 @@ def run_reference(a):
         return
     from fusion4landslide_b200 import pipeline, synth
     cfg = pipeline.FineConfig()
-    d = synth.make_tile(a.tile_pts, seed=a.seed * 100003, device="cpu", patch_pts=a.patch_pts)
+    d = make_c5_tile(a, a.seed * 100003, "cpu")
     tile = pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"])
     workers = os.cpu_count() or 1
     per_step = a.cpu_sample_pairs or max(32, min(tile.n_pairs, int(8.0 * workers * 150)))

@@ -456,10 +456,12 @@ class HotPathMixin:
             if m_.output_tgt2src:
                 do.corres_3d_refine_apply_icp_tgt2src_multiple = []
             do.corres_3d_refine_apply_icp_discrete_multiple = []
+            self.fine_results_multiple = []                        # per-level FineResult (transforms, status, iterations)
             for level_current in m_.level_of_superpoint:
                 do.spt_corres_src = do.spt_corres_src_multiple[level_current - 1]
                 do.spt_corres_tgt = do.spt_corres_tgt_multiple[level_current - 1]
                 self.fine_matching_with_different_types()
+                self.fine_results_multiple.append(self.fine_result)
                 do.corres_3d_refine_apply_icp_multiple.append(do.corres_3d_refine_apply_icp)
                 if m_.output_tgt2src:
                     do.corres_3d_refine_apply_icp_tgt2src_multiple.append(do.corres_3d_refine_apply_icp_tgt2src)

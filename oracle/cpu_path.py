@@ -24,7 +24,7 @@ def _work(args):
     g = _G
     o = ofm.fine_matching(g["src"], g["tgt"], g["corr3d"], None, g["spt_src"][lo:hi], g["spt_tgt"][lo:hi], g["prm"])
     rows = sum(0 if d is None else d.shape[0] for d in o["dense"])
-    return lo, hi, rows, o["status"], o["T"]
+    return lo, hi, rows, o["status"], o["T"], o["iters"], o["K"]
 
 
 def run_tile(src, tgt, corr3d, spt_src, spt_tgt, workers=None, max_pairs=None, **fine_kwargs):
@@ -43,20 +43,22 @@ def run_tile(src, tgt, corr3d, spt_src, spt_tgt, workers=None, max_pairs=None, *
     jobs = [(lo, min(lo + chunk, Q)) for lo in range(0, Q, chunk)]
     status = np.zeros(Q, np.int8)
     T = np.tile(np.eye(4, dtype=np.float32), (Q, 1, 1))
+    iters = np.zeros(Q, np.int64)
+    K = np.zeros(Q, np.int64)
     rows = 0
     if workers > 1 and len(jobs) > 1:
         with mp.get_context("fork").Pool(workers) as pool:
-            for lo, hi, r, st, Tq in pool.imap_unordered(_work, jobs):
-                rows += r
-                status[lo:hi] = st
-                T[lo:hi] = Tq
+            it = pool.imap_unordered(_work, jobs)
+            results = list(it)
     else:
-        for j in jobs:
-            lo, hi, r, st, Tq = _work(j)
-            rows += r
-            status[lo:hi] = st
-            T[lo:hi] = Tq
+        results = [_work(j) for j in jobs]
+    for lo, hi, r, st, Tq, itq, Kq in results:
+        rows += r
+        status[lo:hi] = st
+        T[lo:hi] = Tq
+        iters[lo:hi] = itq
+        K[lo:hi] = Kq
     t2 = time.perf_counter()
     pts = int(sum(len(spt_src[q]) for q in range(Q)))
     return dict(seconds=t2 - t0, seconds_median=t1 - t0, seconds_fine=t2 - t1, src_points=pts,
-                dense_rows=rows, status=status, T=T, workers=workers, median_resolution=med, pairs=Q)
+                dense_rows=rows, status=status, T=T, iters=iters, K=K, workers=workers, median_resolution=med, pairs=Q)

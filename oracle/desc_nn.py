@@ -54,22 +54,39 @@ def global_matches_from_3d(src_feat, tgt_feat, src_sub, tgt_sub, idx_voxel2pts_s
     return C, labels, keep
 
 
-def coarse_matching_3d(coord_s, feat_s, coord_t, feat_t, max_magnitude, kind="nn_mutual"):
-    """base.py:2966-2995.  Returns (src patch ids m, tgt patch ids j*(m)) of accepted pairs."""
+def coarse_matching_3d(coord_s, feat_s, coord_t, feat_t, max_magnitude, kind="nn_mutual", block=1024):
+    """base.py:2966-2995.  Returns (src patch ids m, tgt patch ids j*(m)) of accepted pairs.
+    Row blocks of the (S,T) distance matrices (the reference materialises them whole); first minimum wins, as
+    torch.min / np.argmin do."""
     cs = np.asarray(coord_s, np.float64)
     ct = np.asarray(coord_t, np.float64)
     fs = np.asarray(feat_s, np.float64)
     ft = np.asarray(feat_t, np.float64)
-    Dc = np.sqrt(np.maximum(((cs[:, None, :] - ct[None, :, :]) ** 2).sum(-1), 0))
-    Df = np.sqrt(np.maximum((fs * fs).sum(1)[:, None] + (ft * ft).sum(1)[None, :] - 2 * fs @ ft.T, 0))
-    Df[Dc > max_magnitude] = np.inf                                          # :2969
-    j = Df.argmin(1)                                                         # :2972
-    in_mag = Df[np.arange(Df.shape[0]), j] < np.inf                          # :2989
+    S, T = cs.shape[0], ct.shape[0]
+    j = np.zeros(S, np.int64)
+    dj = np.full(S, np.inf)
+    col_best = np.full(T, np.inf)
+    m_of_j = np.zeros(T, np.int64)
+    ft2 = (ft * ft).sum(1)
+    for lo in range(0, S, block):
+        hi = min(lo + block, S)
+        Dc = np.sqrt(np.maximum(((cs[lo:hi, None, :] - ct[None, :, :]) ** 2).sum(-1), 0))
+        Df = np.sqrt(np.maximum((fs[lo:hi] * fs[lo:hi]).sum(1)[:, None] + ft2[None, :] - 2 * fs[lo:hi] @ ft.T, 0))
+        Df[Dc > max_magnitude] = np.inf                                      # :2969
+        if T:
+            jj = Df.argmin(1)                                                # :2972
+            j[lo:hi] = jj
+            dj[lo:hi] = Df[np.arange(hi - lo), jj]
+            cm = Df.argmin(0)                                                # :2979 (first minimum over ALL rows)
+            cv = Df[cm, np.arange(T)]
+            upd = cv < col_best
+            col_best[upd] = cv[upd]
+            m_of_j[upd] = cm[upd] + lo
+    in_mag = dj < np.inf                                                     # :2989
     if kind == "only_max_mag":
         mask = in_mag
     else:
-        m_of_j = Df.argmin(0)                                                # :2979
-        mask = in_mag & (m_of_j[j] == np.arange(Df.shape[0]))                # :2982-2986
+        mask = in_mag & (m_of_j[j] == np.arange(S))                          # :2982-2986
     m = np.nonzero(mask)[0]
     return m, j[m]
 

@@ -81,7 +81,7 @@ def attention_pool(w, feats, coords, lists, p2v):
 
 def c2f_tile(src, tgt, labels_src, labels_tgt, feat_raw_src, feat_raw_tgt, agg_weights, voxel_size, corr2d=None,
              coarse="only_3d", fine="only_3d", max_magnitude=5.0, min_pts=10, median_max_resolution=None,
-             max_pairs_per_level=None, fine_params=None, v2p_given=None):
+             max_pairs_per_level=None, fine_params=None, v2p_given=None, corr3d_given=None):
     """The fusion method on one tile.  labels_*: list of per-level label arrays (n,).  coarse/fine: 'only_3d' |
     'fusion' (2D-vote pairs first, 2D-lifted matches appended in the fine stage).  max_pairs_per_level bounds the
     fine-matching sample (CPU arm of bench.py); the merge then covers the sampled pairs only."""
@@ -98,8 +98,11 @@ def c2f_tile(src, tgt, labels_src, labels_tgt, feat_raw_src, feat_raw_tgt, agg_w
     fs = np.asarray(feat_raw_src, np.float32)[vs["idx_voxel2pts_src"]]
     ft = np.asarray(feat_raw_tgt, np.float32)[vs["idx_voxel2pts_tgt"]]
     t0 = time.perf_counter()
-    corr3d, labels, _ = odesc.global_matches_from_3d(fs, ft, vs["src_pts_sub"], vs["tgt_pts_sub"], vs["idx_voxel2pts_src"],
-                                                     vs["idx_voxel2pts_tgt"], src.shape[0], max_magnitude)
+    if corr3d_given is not None:            # CPU arm of bench.py: the O(N^2) search is timed on a row sample elsewhere
+        corr3d, labels = np.asarray(corr3d_given), None
+    else:
+        corr3d, labels, _ = odesc.global_matches_from_3d(fs, ft, vs["src_pts_sub"], vs["tgt_pts_sub"], vs["idx_voxel2pts_src"],
+                                                         vs["idx_voxel2pts_tgt"], src.shape[0], max_magnitude)
     sec["global_matches_from_3d"] = time.perf_counter() - t0
     prm = fine_params or ofm.FineParams(mode=fine, median_max_resolution=float(med))
     levels = []
