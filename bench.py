@@ -804,12 +804,12 @@ def bench_c2(a, dev, L, peaks):
             from oracle import paths as opaths
             t0_ = tiles[0]
             fs_h, ft_h = t0_["fs"].cpu(), t0_["ft"].cpu()
-            sample_rows = 4096
+            sample_rows = 1024
             per_row, how, t_build = _cpu_desc_nn_rate(fs_h, ft_h, sample_rows, backends)
-            per_row_b, _, t_build_b = _cpu_desc_nn_rate(ft_h, fs_h, sample_rows, backends)
+            per_row_b, t_build_b = per_row, t_build            # the reverse search has the same shape (N = M)
             o = opaths.f2s3_tile(t0_["src"].cpu().numpy(), t0_["tgt"].cpu().numpy(), fs_h.numpy(), ft_h.numpy(),
                                  t0_["lab"].cpu().numpy(), t0_["w"].cpu().numpy(), refine_results=True, max_disp_magnitude=5.0,
-                                 mutual=False, max_rows=60_000, max_segments=200)
+                                 mutual=False, max_segments=300, labels_given=outs[0]["labels"].long().cpu().numpy())
             from oracle import knn as oknn
             t1 = time.perf_counter()
             oknn.median_resolution(t0_["src"].cpu().numpy()[:250_000], t0_["tgt"].cpu().numpy()[:250_000])
@@ -819,8 +819,8 @@ def bench_c2(a, dev, L, peaks):
             sec_tile = (per_row + per_row_b) * n + t_build + t_build_b + prune_rate * n_seg_rows + t_med
             r["cpu_baseline"] = {"value": (rows / n_tiles) / sec_tile, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                  "seconds_per_tile_estimate": sec_tile,
-                                 "sample": "tile 0, stage by stage, scaled to the tile: descriptor search %d rows x 1 M both directions "
-                                           "(%s): %.2e s/row; pruning of 200 supervoxels (oracle/rigid.py filter_input_tail): %.2e s/row; "
+                                 "sample": "tile 0, stage by stage, scaled to the tile: descriptor search %d rows x 1 M, counted for both directions "
+                                           "(%s): %.2e s/row; pruning of 300 supervoxels (oracle/rigid.py filter_input_tail): %.2e s/row; "
                                            "median resolution on 250 k points x 4" % (sample_rows, how, per_row, prune_rate),
                                  "backends_present": backends}
         res["by_D"]["D%d" % D] = r
@@ -923,7 +923,7 @@ def bench_c2f(a, dev, L, peaks, fusion):
         tt = tiles[-1]                                          # the tile `c` holds the GPU results of
         di = c.data_interim
         fs_sub, ft_sub = di.tile_pts_sub_feat_src.cpu(), di.tile_pts_sub_feat_tgt.cpu()
-        sample_rows = 4096
+        sample_rows = 1024
         per_row, how, t_build = _cpu_desc_nn_rate(fs_sub, ft_sub, sample_rows, backends)
         pairs_cap = 60
         o = opaths.c2f_tile(tt["src_pts"].cpu().numpy(), tt["tgt_pts"].cpu().numpy(), [x.cpu().numpy() for x in tt["partition_src"]],

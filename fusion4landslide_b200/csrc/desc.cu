@@ -33,7 +33,9 @@
 #define DT_RB 256            // query rows per CTA row block (2 tiles)
 #define DT_STAGES 4
 #define DT_CAND 8
-#define DT_THREADS 320       // producer warp, MMA warp, 8 epilogue warps
+#define DT_EPI_WARPS 16      // epilogue warps: (TMEM lane quarter) x (row sub-block) x (column half)
+#define DT_HALVES 2          // column halves of a 128-column accumulator tile, one epilogue warp each
+#define DT_THREADS (64 + DT_EPI_WARPS * 32)   // producer warp, MMA warp, epilogue warps
 #define DT_PAD_BIAS 60000.0f // score of a padding column: never a minimum
 
 // ---------------------------------------------------------------------------------------------
@@ -69,6 +71,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -131,10 +142,14 @@ struct DescScalars {
     float scale;
     unsigned bmax_bits;     // max ||b_j * scale|| (float bits)
     int n_overflow;
+    unsigned bmin2_bits, bmax2_bits;   // min / max of ||b_j * scale||^2 over the real rows (float bits)
+    int use_nobias;         // 1: all reference rows have (almost) the same norm -> the kernel without the bias K-columns runs
+    float norm_spread;      // (bmax2 - bmin2) / 4: what ignoring 1/2||b||^2 can move a score by (about the mid value)
 };
 
 __global__ void k_desc_scalars_init(DescScalars* s) {
     s->absmax_bits = 0u; s->scale = 1.f; s->bmax_bits = 0u; s->n_overflow = 0;
+    s->bmin2_bits = 0x7f800000u; s->bmax2_bits = 0u; s->use_nobias = 0; s->norm_spread = 0.f;
 }
 
 __global__ void __launch_bounds__(256) k_desc_absmax(const float* __restrict__ x, size_t n, DescScalars* s) {
@@ -161,6 +176,17 @@ __global__ void k_desc_scale(DescScalars* s) {
         sc = ldexpf(1.f, -e);
     }
     s->scale = sc;
+}
+
+// After the reference side is packed: if every reference row has (almost) the same norm -- L2-normalised descriptors,
+// the reference's case (src/models/local_feature_descriptor.py:107-109) -- 1/2||b_j||^2 is a constant up to
+// `norm_spread`, the score is -a.b alone, and the kernel variant WITHOUT the 16 bias K-columns runs (a fifth to a
+// third fewer MMAs); the spread is added to the candidate margin, so the result stays exact.  force: 0 auto, 1 bias.
+__global__ void k_desc_choose(DescScalars* s, int force_bias) {
+    const float lo = __uint_as_float(s->bmin2_bits), hi = __uint_as_float(s->bmax2_bits);
+    const bool ok = isfinite(lo) && isfinite(hi) && hi > 0.f && (hi - lo) <= 4e-4f * hi;
+    s->use_nobias = (ok && !force_bias) ? 1 : 0;
+    s->norm_spread = ok ? 0.25f * (hi - lo) : 0.f;
 }
 
 // one warp per row; tile t of 128 rows occupies tile_bytes = 128*Kp*2 contiguous bytes:
@@ -208,7 +234,11 @@ k_desc_pack(const float* __restrict__ x, int n, int n_pad, int is_ref, DescScala
     if (lane == 0) {
         const float nf = (float)nn;
         if (norm2) norm2[row] = nf;
-        if (is_ref && row < n) atomicMax(&sc_->bmax_bits, __float_as_uint(sqrtf(nf) * 1.0000002f));
+        if (is_ref && row < n) {
+            atomicMax(&sc_->bmax_bits, __float_as_uint(sqrtf(nf) * 1.0000002f));
+            atomicMin(&sc_->bmin2_bits, __float_as_uint(nf * 0.9999998f));
+            atomicMax(&sc_->bmax2_bits, __float_as_uint(nf * 1.0000002f));
+        }
     }
 }
 
@@ -241,30 +271,33 @@ __device__ __noinline__ float desc_cand_insert(float v, int j, float margin2, fl
     return thr;
 }
 
-template <int D, int DBG>
+template <int D, int DBG, int BIAS>
 __global__ void __launch_bounds__(DT_THREADS, 1)
-k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_packed, int N, int n_rb, int n_bt,
+k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_packed, int N, int M, int n_rb, int n_bt,
              const float* __restrict__ a_norm2, const DescScalars* __restrict__ scal,
              int32_t* __restrict__ cand_idx, float* __restrict__ cand_val, int32_t* __restrict__ cand_cnt,
              float* __restrict__ cand_thr) {
-    constexpr int KP = D + 16;
+    // two variants are launched back to back; the one k_desc_choose did not pick leaves at once
+    if ((scal->use_nobias != 0) == (BIAS != 0)) return;
+    constexpr int KP = BIAS ? D + 16 : D;                         // K columns this variant multiplies
     constexpr int KSTEPS = KP / 16;
-    constexpr uint32_t TILE_BYTES = DT_TILE * KP * 2;
+    constexpr uint32_t TILE_BYTES = DT_TILE * KP * 2;            // bytes staged per tile (the leading K-chunks)
+    constexpr uint32_t TILE_STRIDE = DT_TILE * (D + 16) * 2;     // bytes per packed tile in HBM (always with bias chunks)
     constexpr uint32_t LBO = DT_TILE * 16;   // K-chunk stride
     constexpr uint32_t SBO = 128;            // 8-row group stride
     extern __shared__ __align__(1024) unsigned char dsm[];
     unsigned char* a_sm = dsm;                                   // 2 tiles
     unsigned char* b_sm = dsm + 2 * TILE_BYTES;                  // DT_STAGES tiles
-    float* cv = reinterpret_cast<float*>(b_sm + DT_STAGES * TILE_BYTES);     // [DT_CAND][DT_RB]
-    int* ci = reinterpret_cast<int*>(cv + DT_CAND * DT_RB);                   // [DT_CAND][DT_RB]
-    float* s_min = reinterpret_cast<float*>(ci + DT_CAND * DT_RB);              // [DT_RB]
-    int* s_cnt = reinterpret_cast<int*>(s_min + DT_RB);                          // [DT_RB]
-    DescTcShared* sh = reinterpret_cast<DescTcShared*>(s_cnt + DT_RB);
+    float* cv = reinterpret_cast<float*>(b_sm + DT_STAGES * TILE_BYTES);     // [DT_HALVES][DT_CAND][DT_RB]
+    int* ci = reinterpret_cast<int*>(cv + DT_HALVES * DT_CAND * DT_RB);        // [DT_HALVES][DT_CAND][DT_RB]
+    float* s_min = reinterpret_cast<float*>(ci + DT_HALVES * DT_CAND * DT_RB);  // [DT_HALVES][DT_RB]
+    int* s_cnt = reinterpret_cast<int*>(s_min + DT_HALVES * DT_RB);              // [DT_HALVES][DT_RB]
+    DescTcShared* sh = reinterpret_cast<DescTcShared*>(s_cnt + DT_HALVES * DT_RB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < DT_STAGES; ++s) { mbar_init(smem_u32(&sh->full[s]), 1); mbar_init(smem_u32(&sh->empty[s]), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&sh->tfull[b]), 1); mbar_init(smem_u32(&sh->tempty[b]), 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&sh->tfull[b]), 1); mbar_init(smem_u32(&sh->tempty[b]), DT_EPI_WARPS); }
         mbar_init(smem_u32(&sh->afull), 1);
         mbar_init(smem_u32(&sh->aempty), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -287,15 +320,15 @@ k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_p
             for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
                 mbar_wait(smem_u32(&sh->aempty), (nblk & 1u) ^ 1u);
                 mbar_expect_tx(smem_u32(&sh->afull), 2 * TILE_BYTES);
-                const unsigned char* asrc = reinterpret_cast<const unsigned char*>(a_packed) + (size_t)rb * 2 * TILE_BYTES;
+                const unsigned char* asrc = reinterpret_cast<const unsigned char*>(a_packed) + (size_t)rb * 2 * TILE_STRIDE;
                 bulk_g2s(smem_u32(a_sm), asrc, TILE_BYTES, smem_u32(&sh->afull));
-                bulk_g2s(smem_u32(a_sm + TILE_BYTES), asrc + TILE_BYTES, TILE_BYTES, smem_u32(&sh->afull));
+                bulk_g2s(smem_u32(a_sm + TILE_BYTES), asrc + TILE_STRIDE, TILE_BYTES, smem_u32(&sh->afull));
                 for (int t = 0; t < n_bt; ++t, ++it) {
                     const uint32_t s = it % DT_STAGES, ph = (it / DT_STAGES) & 1u;
                     mbar_wait(smem_u32(&sh->empty[s]), ph ^ 1u);
                     mbar_expect_tx(smem_u32(&sh->full[s]), TILE_BYTES);
                     bulk_g2s(smem_u32(b_sm + s * TILE_BYTES),
-                             reinterpret_cast<const unsigned char*>(b_packed) + (size_t)t * TILE_BYTES, TILE_BYTES,
+                             reinterpret_cast<const unsigned char*>(b_packed) + (size_t)t * TILE_STRIDE, TILE_BYTES,
                              smem_u32(&sh->full[s]));
                 }
             }
@@ -303,53 +336,63 @@ k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_p
             if (nblk > 0) mbar_wait(smem_u32(&sh->aempty), (nblk & 1u) ^ 1u);
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_f16_128x128();
-            uint32_t it = 0, nblk = 0, tc = 0;
-            for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
-                mbar_wait(smem_u32(&sh->afull), nblk & 1u);
+        // ===== MMA issuer: the whole warp runs the loop (uniform control flow and address arithmetic stay in the
+        // uniform datapath), one elected lane issues.  The shared-memory descriptors are base + constant: the 14-bit
+        // address field (bytes >> 4) of a tile never carries into the LBO field (all tiles lie below 256 KB). =====
+        const uint32_t idesc = instr_desc_f16_128x128();
+        const uint64_t a_desc0 = smem_desc(smem_u32(a_sm), LBO, SBO);
+        const uint64_t b_desc0 = smem_desc(smem_u32(b_sm), LBO, SBO);
+        constexpr uint32_t TILE_U = TILE_BYTES >> 4, KSTEP_U = (2 * LBO) >> 4;
+        uint32_t it = 0, nblk = 0, tc = 0;
+        for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
+            mbar_wait(smem_u32(&sh->afull), nblk & 1u);
+            tc_fence_after();
+            for (int t = 0; t < n_bt; ++t, ++it, ++tc) {
+                const uint32_t s = it % DT_STAGES, ph = (it / DT_STAGES) & 1u;
+                const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
+                mbar_wait(smem_u32(&sh->tempty[buf]), bph ^ 1u);
+                mbar_wait(smem_u32(&sh->full[s]), ph);
                 tc_fence_after();
-                for (int t = 0; t < n_bt; ++t, ++it, ++tc) {
-                    const uint32_t s = it % DT_STAGES, ph = (it / DT_STAGES) & 1u;
-                    const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
-                    mbar_wait(smem_u32(&sh->tempty[buf]), bph ^ 1u);
-                    mbar_wait(smem_u32(&sh->full[s]), ph);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(b_sm + s * TILE_BYTES);
+                if (elect_one()) {
+                    const uint64_t b_desc = b_desc0 + (uint64_t)(s * TILE_U);
 #pragma unroll
                     for (int mb = 0; mb < 2; ++mb) {
-                        const uint32_t a_addr = smem_u32(a_sm + mb * TILE_BYTES);
                         const uint32_t d_addr = tmem + buf * 256u + mb * 128u;
 #pragma unroll
-                        for (int kk = 0; kk < KSTEPS; ++kk) {
-                            tc_mma_f16(d_addr, smem_desc(a_addr + kk * 2 * LBO, LBO, SBO),
-                                       smem_desc(b_addr + kk * 2 * LBO, LBO, SBO), idesc, kk > 0 ? 1u : 0u);
-                        }
+                        for (int kk = 0; kk < KSTEPS; ++kk)
+                            tc_mma_f16(d_addr, a_desc0 + (uint64_t)(mb * TILE_U + kk * KSTEP_U), b_desc + (uint64_t)(kk * KSTEP_U),
+                                       idesc, kk > 0 ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&sh->empty[s]));      // smem stage reusable once these MMAs retire
                     tc_commit(smem_u32(&sh->tfull[buf]));    // accumulators ready for the epilogue
                 }
-                tc_commit(smem_u32(&sh->aempty));            // a tiles reusable
+                __syncwarp();
             }
+            if (elect_one()) tc_commit(smem_u32(&sh->aempty));            // a tiles reusable
+            __syncwarp();
         }
     } else {
-        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
-        const int quarter = warp & 3, mb = (warp - 2) >> 2;
+        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32).  16 warps: every (row sub-block,
+        // lane quarter) is served by two warps, one per 64-column half of the accumulator tile, each with its own
+        // candidate list -- the per-warp dependency chain (TMEM load -> min tree) per tile is what bounds this kernel
+        // at D = 32, so it is kept short and spread over many warps =====
+        const int ew = warp - 2;
+        const int quarter = warp & 3, mb = (ew >> 2) & 1, half = ew >> 3;
         const int rl = mb * 128 + quarter * 32 + lane;           // row inside the row block
-        float* my_cv = cv + rl;
-        int* my_ci = ci + rl;
-        float* my_min = s_min + rl;
-        int* my_cnt = s_cnt + rl;
+        float* my_cv = cv + half * DT_CAND * DT_RB + rl;
+        int* my_ci = ci + half * DT_CAND * DT_RB + rl;
+        float* my_min = s_min + half * DT_RB + rl;
+        int* my_cnt = s_cnt + half * DT_RB + rl;
         const float bmax = __uint_as_float(scal->bmax_bits);
+        const float spread = BIAS ? 0.f : scal->norm_spread;
         uint32_t tc = 0;
         for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
             const size_t row = (size_t)rb * DT_RB + rl;
             const float na = sqrtf(a_norm2[row]);
             // |score' - score| <= E  (fp16 rounding of both operands, fp32 accumulation of <= 80 terms,
-            // fp16 subnormal flush); the true minimum is within 2E of the approximate minimum.
-            // Padding rows record nothing after their first element.
-            const float E = 9.785e-4f * na * bmax + 3.06e-5f * (na * bmax + 0.5f * bmax * bmax) + 8e-6f;
+            // fp16 subnormal flush, and without the bias columns the spread of 1/2||b||^2); the true minimum is
+            // within 2E of the approximate minimum.  Padding rows record nothing after their first element.
+            const float E = 9.785e-4f * na * bmax + 3.06e-5f * (na * bmax + 0.5f * bmax * bmax) + 8e-6f + spread;
             const float margin2 = row < (size_t)N ? 2.f * E : -INFINITY;
             float thr = INFINITY;
             *my_min = INFINITY;
@@ -358,58 +401,67 @@ k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_p
                 const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
                 mbar_wait(smem_u32(&sh->tfull[buf]), bph);
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256u + mb * 128u;
-                // all 128 columns of this warp's rows into registers, then hand the accumulator buffer back
-                // to the MMA warp BEFORE the min trees: the tensor pipe never waits for the CUDA-core work
-                float rA[32], rB[32], rC[32], rD[32];
+                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256u + mb * 128u + half * 64u;
+                // this warp's 64 columns into registers, then hand the accumulator buffer back to the MMA warp
+                // BEFORE the min trees: the tensor pipe never waits for the CUDA-core work
+                float rA[32], rB[32];
                 if (DBG != 2) {
                     TMEM_LD32(rA, taddr);
                     TMEM_LD32(rB, taddr + 32);
-                    TMEM_LD32(rC, taddr + 64);
-                    TMEM_LD32(rD, taddr + 96);
                     TMEM_WAIT32(rA);
                     TMEM_WAIT32(rB);
-                    TMEM_WAIT32(rC);
-                    TMEM_WAIT32(rD);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&sh->tempty[buf]));
+                const int jh = t * DT_TILE + half * 64;
+                if (!BIAS && t == n_bt - 1) {
+                    // without the bias columns a padding column scores 0 and could pass for a minimum: mask it
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        if (jh + k >= M) rA[k] = INFINITY;
+                        if (jh + 32 + k >= M) rB[k] = INFINITY;
+                    }
+                }
+// min of 8 consecutive columns, then of the chunk; the slow path (a column within the margin of the row's running
+// minimum: ~ln(M) times per row over the whole stream, i.e. in ~5 % of a warp's chunks) only scans the groups whose
+// minimum passed -- its instruction count, not its frequency, was a third of this kernel's time at D = 32
+#define DESC_G8(r, o) fminf(fmin3(fmin3(r[o], r[o + 1], r[o + 2]), fmin3(r[o + 3], r[o + 4], r[o + 5]), r[o + 6]), r[o + 7])
+#define DESC_SCAN8(r, o, g, c)                                                                                   \
+    if (g <= thr) {                                                                                              \
+        _Pragma("unroll") for (int k = 0; k < 8; ++k)                                                            \
+            if (r[o + k] <= thr)                                                                                 \
+                thr = desc_cand_insert(r[o + k], jh + (c) * 32 + o + k, margin2, thr, my_cv, my_ci, my_min, my_cnt); \
+    }
 #define DESC_CHUNK(r, c)                                                                                         \
     {                                                                                                            \
-        float m0 = fmin3(r[0], r[1], r[2]), m1 = fmin3(r[3], r[4], r[5]);                                        \
-        float m2 = fmin3(r[6], r[7], r[8]), m3 = fmin3(r[9], r[10], r[11]);                                      \
-        m0 = fmin3(m0, r[12], r[13]); m1 = fmin3(m1, r[14], r[15]);                                              \
-        m2 = fmin3(m2, r[16], r[17]); m3 = fmin3(m3, r[18], r[19]);                                              \
-        m0 = fmin3(m0, r[20], r[21]); m1 = fmin3(m1, r[22], r[23]);                                              \
-        m2 = fmin3(m2, r[24], r[25]); m3 = fmin3(m3, r[26], r[27]);                                              \
-        m0 = fmin3(m0, r[28], r[29]); m1 = fmin3(m1, r[30], r[31]);                                              \
-        const float m = fminf(fmin3(m0, m1, m2), m3);                                                            \
-        if (m <= thr) {                                                                                          \
-            const int j0 = t * DT_TILE + (c) * 32;                                                               \
-            _Pragma("unroll") for (int k = 0; k < 32; ++k)                                                       \
-                if (r[k] <= thr) thr = desc_cand_insert(r[k], j0 + k, margin2, thr, my_cv, my_ci, my_min, my_cnt); \
+        const float g0 = DESC_G8(r, 0), g1 = DESC_G8(r, 8), g2 = DESC_G8(r, 16), g3 = DESC_G8(r, 24);            \
+        const float m = fminf(fmin3(g0, g1, g2), g3);                                                            \
+        if (DBG == 3) { thr = fminf(thr, m + margin2); }                                                         \
+        else if (m <= thr) {                                                                                     \
+            DESC_SCAN8(r, 0, g0, c) DESC_SCAN8(r, 8, g1, c) DESC_SCAN8(r, 16, g2, c) DESC_SCAN8(r, 24, g3, c)    \
         }                                                                                                        \
     }
-                if (DBG == 0) {
+                if (DBG == 0 || DBG == 3) {
                     DESC_CHUNK(rA, 0)
                     DESC_CHUNK(rB, 1)
-                    DESC_CHUNK(rC, 2)
-                    DESC_CHUNK(rD, 3)
                 } else if (DBG == 1) {          // experiment: TMEM reads only
-                    thr = fminf(thr, rA[0] + rB[0] + rC[0] + rD[0]);
+                    thr = fminf(thr, rA[0] + rB[0]);
                 }
 #undef DESC_CHUNK
+#undef DESC_SCAN8
+#undef DESC_G8
             }
-            // row block done: this thread owns its row's candidates
+            // row block done: this thread owns the candidates of its (row, column half)
             const int cnt = *my_cnt;
             const int n = cnt & 0xffff;
+            const size_t slot = row * DT_HALVES + half;
             for (int s = 0; s < DT_CAND; ++s) {
-                cand_idx[row * DT_CAND + s] = s < n ? my_ci[s * DT_RB] : -1;
-                cand_val[row * DT_CAND + s] = s < n ? my_cv[s * DT_RB] : INFINITY;
+                cand_idx[slot * DT_CAND + s] = s < n ? my_ci[s * DT_RB] : -1;
+                cand_val[slot * DT_CAND + s] = s < n ? my_cv[s * DT_RB] : INFINITY;
             }
-            cand_cnt[row] = cnt;
-            cand_thr[row] = thr;
+            cand_cnt[slot] = cnt;
+            cand_thr[slot] = thr;
         }
     }
     tc_fence_before();
@@ -431,20 +483,23 @@ k_desc_rerank(const float* __restrict__ a, const float* __restrict__ b, int N, i
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= N) return;
-    const int cnt = cand_cnt[i];
-    if (cnt & 0x10000) {
+    const int cnt0 = cand_cnt[(size_t)i * DT_HALVES], cnt1 = cand_cnt[(size_t)i * DT_HALVES + 1];
+    if ((cnt0 | cnt1) & 0x10000) {
         if (lane == 0) ovf_list[atomicAdd(&scal->n_overflow, 1)] = i;
         return;
     }
-    const float thr = cand_thr[i];
+    // the two column halves kept candidates within the margin of THEIR minimum: the row's threshold is the lower one
+    const float thr = fminf(cand_thr[(size_t)i * DT_HALVES], cand_thr[(size_t)i * DT_HALVES + 1]);
     float av[D / 32];
 #pragma unroll
     for (int u = 0; u < D / 32; ++u) av[u] = __ldg(a + (size_t)i * D + u * 32 + lane);
     double best = INFINITY;
     int bj = -1;
-    for (int s = 0; s < (cnt & 0xffff); ++s) {
-        const int j = cand_idx[(size_t)i * DT_CAND + s];
-        if (j < 0 || j >= M || !(cand_val[(size_t)i * DT_CAND + s] <= thr)) continue;
+    for (int s = 0; s < DT_HALVES * DT_CAND; ++s) {
+        const int h = s / DT_CAND;
+        if ((s % DT_CAND) >= ((h ? cnt1 : cnt0) & 0xffff)) continue;
+        const int j = cand_idx[(size_t)i * DT_HALVES * DT_CAND + s];
+        if (j < 0 || j >= M || !(cand_val[(size_t)i * DT_HALVES * DT_CAND + s] <= thr)) continue;
         double acc = 0.0;
 #pragma unroll
         for (int u = 0; u < D / 32; ++u) {
@@ -614,10 +669,10 @@ static DescWs desc_layout(void* base, int N, int M, int D) {
     w.a_packed = (__half*)take(n_pad * KP * 2);
     w.b_packed = (__half*)take(m_pad * KP * 2);
     w.a_norm2 = (float*)take(n_pad * 4);
-    w.cand_idx = (int32_t*)take(n_pad * DT_CAND * 4);
-    w.cand_val = (float*)take(n_pad * DT_CAND * 4);
-    w.cand_cnt = (int32_t*)take(n_pad * 4);
-    w.cand_thr = (float*)take(n_pad * 4);
+    w.cand_idx = (int32_t*)take(n_pad * DT_HALVES * DT_CAND * 4);
+    w.cand_val = (float*)take(n_pad * DT_HALVES * DT_CAND * 4);
+    w.cand_cnt = (int32_t*)take(n_pad * DT_HALVES * 4);
+    w.cand_thr = (float*)take(n_pad * DT_HALVES * 4);
     w.ovf_list = (int32_t*)take((size_t)N * 4);
     w.total = off;
     return w;
@@ -662,9 +717,12 @@ static int desc_one_direction(const float* a, int N, const float* b, int M, cons
     f4l_mark("k_desc_pack", st);
     k_desc_pack<D><<<f4l_div_up(n_pad, 8), 256, 0, st>>>(a, N, n_pad, 0, w.scal, w.a_packed, w.a_norm2);
     k_desc_pack<D><<<f4l_div_up(m_pad, 8), 256, 0, st>>>(b, M, m_pad, 1, w.scal, w.b_packed, nullptr);
-    f4l_count_launches(1);
+    static int force_bias = -1;
+    if (force_bias < 0) { const char* e = getenv("F4L_DESC_FORCE_BIAS"); force_bias = e ? atoi(e) : 0; }
+    k_desc_choose<<<1, 1, 0, st>>>(w.scal, force_bias);
+    f4l_count_launches(2);
     constexpr int KP = D + 16;
-    const size_t smem = (size_t)(2 + DT_STAGES) * DT_TILE * KP * 2 + (size_t)DT_CAND * DT_RB * 8 + (size_t)DT_RB * 8 + sizeof(DescTcShared) + 16;
+    const size_t smem = (size_t)(2 + DT_STAGES) * DT_TILE * KP * 2 + (size_t)DT_HALVES * (DT_CAND * DT_RB * 8 + DT_RB * 8) + sizeof(DescTcShared) + 16;
     const int n_rb = n_pad / DT_RB, n_bt = m_pad / DT_TILE;
     int sms = 148;
     int dev = 0;
@@ -677,12 +735,17 @@ static int desc_one_direction(const float* a, int N, const float* b, int M, cons
     f4l_mark("k_desc_nn_tc", st);
 #define F4L_LAUNCH_TC(DBGV)                                                                                          \
     {                                                                                                                \
-        cudaFuncSetAttribute(k_desc_nn_tc<D, DBGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        k_desc_nn_tc<D, DBGV><<<grid, DT_THREADS, smem, st>>>(w.a_packed, w.b_packed, N, n_rb, n_bt, w.a_norm2, w.scal, \
-                                                             w.cand_idx, w.cand_val, w.cand_cnt, w.cand_thr);        \
+        cudaFuncSetAttribute(k_desc_nn_tc<D, DBGV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        cudaFuncSetAttribute(k_desc_nn_tc<D, DBGV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        k_desc_nn_tc<D, DBGV, 0><<<grid, DT_THREADS, smem, st>>>(w.a_packed, w.b_packed, N, M, n_rb, n_bt, w.a_norm2, w.scal, \
+                                                                w.cand_idx, w.cand_val, w.cand_cnt, w.cand_thr);     \
+        k_desc_nn_tc<D, DBGV, 1><<<grid, DT_THREADS, smem, st>>>(w.a_packed, w.b_packed, N, M, n_rb, n_bt, w.a_norm2, w.scal, \
+                                                                w.cand_idx, w.cand_val, w.cand_cnt, w.cand_thr);     \
+        f4l_count_launches(1);                                                                                       \
     }
     if (dbg == 1) F4L_LAUNCH_TC(1)
     else if (dbg == 2) F4L_LAUNCH_TC(2)
+    else if (dbg == 3) F4L_LAUNCH_TC(3)
     else F4L_LAUNCH_TC(0)
 #undef F4L_LAUNCH_TC
     f4l_mark("k_desc_rerank", st);

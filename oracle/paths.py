@@ -137,7 +137,7 @@ def c2f_tile(src, tgt, labels_src, labels_tgt, feat_raw_src, feat_raw_tgt, agg_w
 
 
 def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_labels, weights, coeff=1.0, refine_results=False,
-              max_disp_magnitude=0.0, mutual=False, min_pts=10, max_rows=None, max_segments=None):
+              max_disp_magnitude=0.0, mutual=False, min_pts=10, max_rows=None, max_segments=None, labels_given=None):
     """src/f2s3.py:248-441 with the filtering-network output (`weights`, one per source point) handed in.
     mutual: correspondences whose target's nearest source is another point get weight 0 (BASELINE config C2
     "mutual-NN"; the reference's F2S3 is one-directional).  max_rows / max_segments bound the CPU sample: the
@@ -147,7 +147,10 @@ def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_labels, weights, coeff=1.0, refi
     fs, ft = np.asarray(feat_src, np.float32), np.asarray(feat_tgt, np.float32)
     n = src64.shape[0] if max_rows is None else min(max_rows, src64.shape[0])
     t0 = time.perf_counter()
-    labels, _ = odesc.desc_nn(fs[:n], ft)                                            # :273-281 (exact index)
+    if labels_given is not None:            # CPU arm of bench.py: the O(N^2) search is timed on a row sample elsewhere
+        labels = np.asarray(labels_given)[:n]
+    else:
+        labels, _ = odesc.desc_nn(fs[:n], ft)                                        # :273-281 (exact index)
     sec["desc_nn_rows"] = n
     sec["desc_nn"] = time.perf_counter() - t0
     back = None

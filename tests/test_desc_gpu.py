@@ -109,6 +109,23 @@ def test_desc_nn_tensor_adversarial(cuda):
         assert neq.sum() <= 64
 
 
+@pytest.mark.parametrize("D", [32, 64])
+def test_desc_nn_tensor_mixed_norms_use_the_bias_columns(cuda, D):
+    """Reference rows of very different norms: 1/2||b||^2 is not a constant, the kernel variant WITH the bias
+    K-columns must run (k_desc_choose); rows of (almost) equal norm but a spread just below the switch point run the
+    variant without them with the spread added to the margin.  Both exact."""
+    from fusion4landslide_b200 import ops
+    rng = np.random.default_rng(21 + D)
+    N, M = 3000, 5300
+    for spread in (0.5, 1.5e-4, 0.0):
+        b = _unit(rng, M, D) * (1.0 + spread * rng.uniform(-1, 1, size=(M, 1))).astype(np.float32)
+        a = _unit(rng, N, D)
+        a[:1500] = b[:1500] + 0.1 * rng.standard_normal((1500, D)).astype(np.float32)
+        idx, d2 = ops.desc_nn(torch.from_numpy(a).to(cuda), torch.from_numpy(b.astype(np.float32)).to(cuda), algo="tensor")
+        torch.cuda.synchronize()
+        _check(idx, d2, a, b.astype(np.float32), "spread %g D=%d" % (spread, D))
+
+
 def test_desc_nn_both_dirs_and_auto(cuda):
     from fusion4landslide_b200 import ops
     rng = np.random.default_rng(5)
