@@ -51,19 +51,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a broken pipeline traps after ~4 s instead of hanging the device.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// Bounded wait: a broken pipeline traps after ~4 s instead of hanging the device.  The clock is only read once the
+// first probe has failed (a CS2R per wait on the fast path cost the MMA-issuing warp more than its MMAs).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
+    if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
+    while (!mbar_try(bar, parity)) {
         if (clock64() - t0 > 8000000000ll) __trap();
     }
 }
@@ -271,6 +275,26 @@ __device__ __noinline__ float desc_cand_insert(float v, int j, float margin2, fl
     return thr;
 }
 
+// min of 8 consecutive columns, then of the chunk; the slow path (a column within the margin of the row's running
+// minimum: ~ln(M) times per row over the whole stream, i.e. in ~5 % of a warp's chunks) only scans the groups whose
+// minimum passed -- its instruction count, not its frequency, was a third of this kernel's time at D = 32
+#define DESC_G8(r, o) fminf(fmin3(fmin3(r[o], r[o + 1], r[o + 2]), fmin3(r[o + 3], r[o + 4], r[o + 5]), r[o + 6]), r[o + 7])
+#define DESC_SCAN8(r, o, g, c)                                                                                   \
+    if (g <= thr) {                                                                                              \
+        _Pragma("unroll") for (int k = 0; k < 8; ++k)                                                            \
+            if (r[o + k] <= thr)                                                                                 \
+                thr = desc_cand_insert(r[o + k], jh + (c) * 32 + o + k, margin2, thr, my_cv, my_ci, my_min, my_cnt); \
+    }
+#define DESC_CHUNK(r, c)                                                                                         \
+    {                                                                                                            \
+        const float g0 = DESC_G8(r, 0), g1 = DESC_G8(r, 8), g2 = DESC_G8(r, 16), g3 = DESC_G8(r, 24);            \
+        const float m = fminf(fmin3(g0, g1, g2), g3);                                                            \
+        if (DBG == 3) { thr = fminf(thr, m + margin2); }                                                         \
+        else if (m <= thr) {                                                                                     \
+            DESC_SCAN8(r, 0, g0, c) DESC_SCAN8(r, 8, g1, c) DESC_SCAN8(r, 16, g2, c) DESC_SCAN8(r, 24, g3, c)    \
+        }                                                                                                        \
+    }
+
 template <int D, int DBG, int BIAS>
 __global__ void __launch_bounds__(DT_THREADS, 1)
 k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_packed, int N, int M, int n_rb, int n_bt,
@@ -423,34 +447,12 @@ k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_p
                         if (jh + 32 + k >= M) rB[k] = INFINITY;
                     }
                 }
-// min of 8 consecutive columns, then of the chunk; the slow path (a column within the margin of the row's running
-// minimum: ~ln(M) times per row over the whole stream, i.e. in ~5 % of a warp's chunks) only scans the groups whose
-// minimum passed -- its instruction count, not its frequency, was a third of this kernel's time at D = 32
-#define DESC_G8(r, o) fminf(fmin3(fmin3(r[o], r[o + 1], r[o + 2]), fmin3(r[o + 3], r[o + 4], r[o + 5]), r[o + 6]), r[o + 7])
-#define DESC_SCAN8(r, o, g, c)                                                                                   \
-    if (g <= thr) {                                                                                              \
-        _Pragma("unroll") for (int k = 0; k < 8; ++k)                                                            \
-            if (r[o + k] <= thr)                                                                                 \
-                thr = desc_cand_insert(r[o + k], jh + (c) * 32 + o + k, margin2, thr, my_cv, my_ci, my_min, my_cnt); \
-    }
-#define DESC_CHUNK(r, c)                                                                                         \
-    {                                                                                                            \
-        const float g0 = DESC_G8(r, 0), g1 = DESC_G8(r, 8), g2 = DESC_G8(r, 16), g3 = DESC_G8(r, 24);            \
-        const float m = fminf(fmin3(g0, g1, g2), g3);                                                            \
-        if (DBG == 3) { thr = fminf(thr, m + margin2); }                                                         \
-        else if (m <= thr) {                                                                                     \
-            DESC_SCAN8(r, 0, g0, c) DESC_SCAN8(r, 8, g1, c) DESC_SCAN8(r, 16, g2, c) DESC_SCAN8(r, 24, g3, c)    \
-        }                                                                                                        \
-    }
                 if (DBG == 0 || DBG == 3) {
                     DESC_CHUNK(rA, 0)
                     DESC_CHUNK(rB, 1)
                 } else if (DBG == 1) {          // experiment: TMEM reads only
                     thr = fminf(thr, rA[0] + rB[0]);
                 }
-#undef DESC_CHUNK
-#undef DESC_SCAN8
-#undef DESC_G8
             }
             // row block done: this thread owns the candidates of its (row, column half)
             const int cnt = *my_cnt;
@@ -470,6 +472,7 @@ k_desc_nn_tc(const __half* __restrict__ a_packed, const __half* __restrict__ b_p
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // fp64 re-rank of the candidates: warp per row
