@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--dips-pts", type=int, default=625_000)
     ap.add_argument("--dips-cpu-queries", type=int, default=300)
     ap.add_argument("--a1-overlap", type=int, default=1, help="1: A1 of a tile runs on a side stream next to its rigid fits")
+    ap.add_argument("--fit", default="batched", choices=["batched", "per-tile"],
+                    help="batched (default): the rigid fits of all tiles of a rank in ONE persistent queue-driven launch "
+                         "(pipeline.displacement_field_tiles_batched); per-tile: one fit launch per tile")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the exchange (N > 1)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -194,6 +197,7 @@ def algorithmic_bytes(name, q):
         # matched pairs: 8 B indices + 24 B coordinates, outputs 64+128+... per pair
         "k_patch_fit": 32 * K + 240 * P,
         "k_patch_fit_warp": 32 * K + 240 * P,
+        "k_patch_fit_warp_tiles": 32 * q.get("matched_all", K) + 240 * q.get("pairs_all", P),     # one launch, all tiles of the rank
         # src patch points 12+4, tgt patch points 12+4, dense rows 24, nn 4
         "k_apply_assign": 16 * ns + 16 * nt + 24 * ns + 4 * ns + 64 * P,
         "k_emit_sparse": 8 * ns + 2 * 24 * q["sparse_half"] + 24 * q["sparse_half"],
@@ -291,8 +295,14 @@ def run_b200(a):
     streams = pipeline.make_streams(a.streams, dev) if a.streams > 1 else None
     sides = pipeline.make_streams(a.streams, dev) if (a.streams > 1 and a.a1_overlap) else None
 
+    caches = [{} for _ in arenas]
+
     def step_tiles(par=0):
-        pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par], side_streams=sides)
+        if a.fit == "batched":
+            pipeline.displacement_field_tiles_batched(tiles, cfg, outs_par[par], meds, streams, peers_par[par],
+                                                      side_streams=sides, cache=caches[par])
+        else:
+            pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par], side_streams=sides)
 
     # The per-tile launch sequence is static (all buffers preallocated, no host round trip inside the path):
     # capture one step -- all tiles, all side streams -- into a CUDA graph and replay it (one graph per
@@ -446,11 +456,16 @@ def run_b200(a):
     if rank == 0:
         L.f4l_profile_reset()
         L.f4l_profile_enable(1)
+        prof_cache = {}
         for _ in range(max(1, min(a.steps, 3))):
-            for i, t in enumerate(tiles):
-                pipeline.displacement_field(t, cfg, out=outs[i], med_out=meds[i:i + 1])
+            if a.fit == "batched":               # the timed step on ONE stream, so that in-stream events time each kernel alone
+                pipeline.displacement_field_tiles_batched(tiles, cfg, outs, meds, None, None, None, cache=prof_cache)
+            else:
+                for i, t in enumerate(tiles):
+                    pipeline.displacement_field(t, cfg, out=outs[i], med_out=meds[i:i + 1])
         torch.cuda.synchronize()
         L.f4l_profile_enable(0)
+        del prof_cache
         tab = _lib.profile_table()
         tot = sum(v[0] for v in tab.values()) or 1.0
         kernel_table = {k: {"ms_avg": v[0] / v[1], "launches": v[1], "share": v[0] / tot}
@@ -459,7 +474,8 @@ def run_b200(a):
         t0_ = tiles[0]
         c = counts_arena[0].tolist()
         q = dict(n_src=t0_.src.shape[0], n_tgt=t0_.tgt.shape[0], pairs=t0_.n_pairs, src_items=t0_.n_src_items,
-                 tgt_items=t0_.n_tgt_items, matched=int(outs[0].K.sum()), sparse_half=c[1] // 2)
+                 tgt_items=t0_.n_tgt_items, matched=int(outs[0].K.sum()), sparse_half=c[1] // 2,
+                 matched_all=int(sum(int(o.K.sum()) for o in outs)), pairs_all=sum(t.n_pairs for t in tiles))
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(top, q)
         ach = ab / (kernel_table[top]["ms_avg"] * 1e-3) / 1e9 if ab else None
@@ -482,7 +498,7 @@ def run_b200(a):
         if ctx:
             roofline["ncu_context"] = ctx          # from the committed capture, not measured in this run
         # also report the two kernels the north star names (kNN search, Kabsch/ICP reduction)
-        for name in ("k_a1_search", "k_a1_scatter", "k_a1_count", "k_a1_bbox", "k_patch_fit_warp", "k_patch_fit",
+        for name in ("k_a1_search", "k_a1_scatter", "k_a1_count", "k_a1_bbox", "k_patch_fit_warp", "k_patch_fit_warp_tiles", "k_patch_fit",
                      "k_apply_assign"):
             if name in kernel_table:
                 b = algorithmic_bytes(name, q)
@@ -500,7 +516,7 @@ def run_b200(a):
     configs_out = None
     if rank == 0 and world == 1 and a.configs.lower() != "none":
         used_graph = graph is not None
-        del tiles, outs, outs_par, arenas, dense_arena, T_arena, graphs, graph
+        del tiles, outs, outs_par, arenas, dense_arena, T_arena, graphs, graph, caches
         graph = True if used_graph else None
         torch.cuda.empty_cache()
         configs_out = run_configs(a, dev, L)
@@ -518,7 +534,7 @@ def run_b200(a):
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
                              input_gb,
                        "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type, "streams": a.streams,
-                       "cuda_graph": graph is not None, "a1_side_stream": bool(sides)},
+                       "cuda_graph": graph is not None, "a1_side_stream": bool(sides), "fit": a.fit},
             "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline,
             "kernels": kernel_table, "cpu_baseline": cpu, "parity": parity, "breakdown": breakdown,
             "configs": configs_out,

@@ -47,7 +47,7 @@ class FineBuffers(ctypes.Structure):
         ("ratio_inlier", c_void_p), ("dist_mean", c_void_p),
         ("dense", c_void_p), ("sparse", c_void_p), ("tgt2src", c_void_p), ("counts", c_void_p),
         ("n_peers", c_i32), ("peer_dense", c_void_p * MAX_PEERS),
-        ("sparse_pair_rows", c_void_p), ("median_ready_event", c_void_p),
+        ("sparse_pair_rows", c_void_p), ("median_ready_event", c_void_p), ("phases", c_i32),
     ]
 
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "f4l_segmented_nn": (c_int, [P, P, P, P, P, P, P, P, c_i32, P, P, P, P, P]),
     "f4l_patch_icp": (c_int, [P, P, P, P, P, P, P, P, P, c_i32, P, c_f64, c_i32, c_f64, c_f64,
                               P, P, P, P, P, P]),
+    "f4l_fine_fit_tiles": (c_int, [P, P, P, c_i32, P, P]),
     "f4l_desc_nn_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_int]),
     "f4l_desc_nn": (c_int, [P, c_i32, P, c_i32, c_i32, P, P, c_f32, c_int, c_int, P, P, P, P, P, c_size, P]),
     "f4l_scatter_global_matches_workspace_bytes": (c_size, [c_i32]),

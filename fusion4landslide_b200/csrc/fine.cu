@@ -109,7 +109,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
             ratio_inlier[q] = ratio;
             dist_mean[q] = dmean;
         }
-        if (st == 0 && k < prm.num_min_fine_match) st = 2;                                          // base.py:3338
+        if (st == 0 && (k < prm.num_min_fine_match || k < 1)) st = 2;   // (no fit without a match)                                          // base.py:3338
         double* T64q = T64 + (size_t)q * 16;
         if (st != 0) {
             if (tid < 16) {
@@ -159,86 +159,138 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
 #ifndef FITW_MIN_BLOCKS
 #define FITW_MIN_BLOCKS (16 / FITW_WARPS)
 #endif
+// The per-pair outputs / inputs of one tile, as the fit kernels see them.
+struct FitTile {
+    const float* src_pts; const float* tgt_pts;
+    const int32_t* cs; const int32_t* ct; const int32_t* kstart; const int32_t* K;
+    float* T32; double* T64; int8_t* status; double* fitness; double* rmse; int32_t* iters;
+    float* ratio_inlier; float* dist_mean;
+    int32_t Q;
+};
+
+// One small pair (K <= WICP_CAP) fitted by one warp.
+__device__ __forceinline__ void fit_pair_warp(const FitTile& tl, int q, const f4l_fine_params& prm, WarpIcpSmem& sm, int lane) {
+    const float* __restrict__ src_pts = tl.src_pts;
+    const float* __restrict__ tgt_pts = tl.tgt_pts;
+    const int32_t* __restrict__ cs = tl.cs;
+    const int32_t* __restrict__ ct = tl.ct;
+    const int32_t* __restrict__ kstart = tl.kstart;
+    const int32_t* __restrict__ K = tl.K;
+    float* __restrict__ T32 = tl.T32;
+    double* __restrict__ T64 = tl.T64;
+    int8_t* __restrict__ status = tl.status;
+    double* __restrict__ fitness = tl.fitness;
+    double* __restrict__ rmse = tl.rmse;
+    int32_t* __restrict__ iters = tl.iters;
+    float* __restrict__ ratio_inlier = tl.ratio_inlier;
+    float* __restrict__ dist_mean = tl.dist_mean;
+    const int k0 = kstart[q], k = K[q];
+    if (k > WICP_CAP) return;             // fitted by the CTA kernel
+    __syncwarp();
+    DBG_T0
+#ifdef F4L_DEBUG_SCANS
+    const long long dbg_start = dbg_t;
+#endif
+    int st = 0;
+    double* T64q = T64 + (size_t)q * 16;
+    float ra = 0.f, dm = 0.f;
+    const bool staged = prm.remove_low_quality && k >= prm.num_min_quality;
+    if (staged) {
+        float* arena = reinterpret_cast<float*>(&sm);          // aliases the ICP staging area (filled later)
+        warp_rigidity_stage(arena, src_pts, tgt_pts, cs, ct, k0, k, lane);
+        __syncwarp();
+        DBG_T(17)
+        double sum;
+        unsigned cnt;
+        warp_rigidity(arena, k, prm.thres_dist_diff, lane, sum, cnt);
+        const double ne = 0.5 * (double)k * (double)(k - 1);
+        dm = (float)(sum / ne);
+        ra = (float)((double)(2ull * cnt) / (ne * 2.0));
+        if (ra <= prm.thres_inlier_ratio || dm >= prm.thres_dist_diff) st = 1;                   // base.py:3320
+        __syncwarp();
+    }
+    DBG_T(8)
+    if (st == 0 && (k < prm.num_min_fine_match || k < 1)) st = 2;   // (no fit without a match)                                            // base.py:3338
+    if (lane == 0) { ratio_inlier[q] = ra; dist_mean[q] = dm; }
+    if (st != 0) {
+        if (lane < 16) {
+            const double v = (lane % 5 == 0) ? 1.0 : 0.0;
+            T64q[lane] = v;
+            T32[(size_t)q * 16 + lane] = (float)v;
+        }
+        if (lane == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
+        return;
+    }
+    // D2: Procrustes (weights None, eps 1e-6)
+    double R[9], t[3], Tsvd[16];
+    __syncwarp();
+    if (lane < 9) sm.Vw[lane] = (lane % 4 == 0) ? 1.0 : 0.0;          // cold start; later fits of this pair start warm
+    __syncwarp();
+    if (staged) warp_fit_arena(reinterpret_cast<const float*>(&sm), k, 1e-6, 0, lane, R, t, sm.Vw);
+    else warp_fit_segment(src_pts, tgt_pts, cs, ct, nullptr, k0, k, 1e-6, 0.f, 0, lane, R, t, sm.Vw);
+    __syncwarp();                  // the arena is dead from here: warp_icp restages over it
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Tsvd[r * 4 + 0] = R[r * 3 + 0]; Tsvd[r * 4 + 1] = R[r * 3 + 1];
+        Tsvd[r * 4 + 2] = R[r * 3 + 2]; Tsvd[r * 4 + 3] = t[r];
+    }
+    Tsvd[12] = 0; Tsvd[13] = 0; Tsvd[14] = 0; Tsvd[15] = 1;
+    DBG_T(9)
+    IcpResult r;
+    r.fitness = 0; r.rmse = 0; r.iters = 0;
+    if (prm.icp_refine) {
+        r = warp_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, Tsvd, prm.icp_threshold, prm.icp_max_iter, 1e-6, 1e-6,
+                     T64q, nullptr, sm, lane);
+    } else {
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+            if (lane == a) T64q[a] = Tsvd[a];
+    }
+    __syncwarp();
+    if (lane < 16) T32[(size_t)q * 16 + lane] = (float)T64q[lane];                                // base.py:3366
+    if (lane == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+#ifdef F4L_DEBUG_SCANS
+    if (lane == 0) atomicAdd(&g_dbg[16], (unsigned long long)(clock64() - dbg_start));
+#endif
+}
+
 __global__ void __launch_bounds__(FITW_WARPS * 32, FITW_MIN_BLOCKS)
-k_patch_fit_warp(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
-                 const int32_t* __restrict__ cs, const int32_t* __restrict__ ct,
-                 const int32_t* __restrict__ kstart, const int32_t* __restrict__ K, int Q, f4l_fine_params prm,
-                 float* __restrict__ T32, double* __restrict__ T64, int8_t* __restrict__ status,
-                 double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
-                 float* __restrict__ ratio_inlier, float* __restrict__ dist_mean) {
+k_patch_fit_warp(FitTile tl, f4l_fine_params prm) {
     extern __shared__ __align__(16) unsigned char fitw_raw[];
     WarpIcpSmem* smem = reinterpret_cast<WarpIcpSmem*>(fitw_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpIcpSmem& sm = smem[wid];
-    for (int q = blockIdx.x * FITW_WARPS + wid; q < Q; q += gridDim.x * FITW_WARPS) {
-        const int k0 = kstart[q], k = K[q];
-        if (k > WICP_CAP) continue;           // fitted by the CTA kernel
-        __syncwarp();
-        DBG_T0
-#ifdef F4L_DEBUG_SCANS
-        const long long dbg_start = dbg_t;
-#endif
-        int st = 0;
-        double* T64q = T64 + (size_t)q * 16;
-        float ra = 0.f, dm = 0.f;
-        const bool staged = prm.remove_low_quality && k >= prm.num_min_quality;
-        if (staged) {
-            float* arena = reinterpret_cast<float*>(&sm);          // aliases the ICP staging area (filled later)
-            warp_rigidity_stage(arena, src_pts, tgt_pts, cs, ct, k0, k, lane);
-            __syncwarp();
-            DBG_T(17)
-            double sum;
-            unsigned cnt;
-            warp_rigidity(arena, k, prm.thres_dist_diff, lane, sum, cnt);
-            const double ne = 0.5 * (double)k * (double)(k - 1);
-            dm = (float)(sum / ne);
-            ra = (float)((double)(2ull * cnt) / (ne * 2.0));
-            if (ra <= prm.thres_inlier_ratio || dm >= prm.thres_dist_diff) st = 1;                   // base.py:3320
-            __syncwarp();
+    for (int q = blockIdx.x * FITW_WARPS + wid; q < tl.Q; q += gridDim.x * FITW_WARPS) fit_pair_warp(tl, q, prm, smem[wid], lane);
+}
+
+// Persistent form over the pairs of MANY tiles (f4l_fine_fit_tiles): every resident warp draws the next pair from a
+// global queue, so the launch has no wave quantisation (784 CTAs on 592 slots = 1.32 waves per tile before) and its
+// tail is one pair long instead of one pair per tile.  Pair i of the concatenation belongs to tile t with
+// prefix[t] <= i < prefix[t+1].  The table travels as a kernel parameter (CUDA >= 12.1: up to 32 KB), so the launch
+// captures into a CUDA graph by value.
+#define FIT_MAX_TILES 128
+struct FitTable {
+    int32_t n;
+    int32_t prefix[FIT_MAX_TILES + 1];
+    FitTile t[FIT_MAX_TILES];
+};
+
+__global__ void __launch_bounds__(FITW_WARPS * 32, FITW_MIN_BLOCKS)
+k_patch_fit_warp_tiles(const __grid_constant__ FitTable tab, f4l_fine_params prm, int32_t* __restrict__ queue) {
+    extern __shared__ __align__(16) unsigned char fitw_raw[];
+    WarpIcpSmem* smem = reinterpret_cast<WarpIcpSmem*>(fitw_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int total = tab.prefix[tab.n];
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(queue, 1);
+        i = __shfl_sync(F4L_FULL, i, 0);
+        if (i >= total) break;
+        int lo = 0, hi = tab.n;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tab.prefix[mid] <= i) lo = mid; else hi = mid;
         }
-        DBG_T(8)
-        if (st == 0 && k < prm.num_min_fine_match) st = 2;                                            // base.py:3338
-        if (lane == 0) { ratio_inlier[q] = ra; dist_mean[q] = dm; }
-        if (st != 0) {
-            if (lane < 16) {
-                const double v = (lane % 5 == 0) ? 1.0 : 0.0;
-                T64q[lane] = v;
-                T32[(size_t)q * 16 + lane] = (float)v;
-            }
-            if (lane == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
-            continue;
-        }
-        // D2: Procrustes (weights None, eps 1e-6)
-        double R[9], t[3], Tsvd[16];
-        __syncwarp();
-        if (lane < 9) sm.Vw[lane] = (lane % 4 == 0) ? 1.0 : 0.0;          // cold start; later fits of this pair start warm
-        __syncwarp();
-        if (staged) warp_fit_arena(reinterpret_cast<const float*>(&sm), k, 1e-6, 0, lane, R, t, sm.Vw);
-        else warp_fit_segment(src_pts, tgt_pts, cs, ct, nullptr, k0, k, 1e-6, 0.f, 0, lane, R, t, sm.Vw);
-        __syncwarp();                  // the arena is dead from here: warp_icp restages over it
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            Tsvd[r * 4 + 0] = R[r * 3 + 0]; Tsvd[r * 4 + 1] = R[r * 3 + 1];
-            Tsvd[r * 4 + 2] = R[r * 3 + 2]; Tsvd[r * 4 + 3] = t[r];
-        }
-        Tsvd[12] = 0; Tsvd[13] = 0; Tsvd[14] = 0; Tsvd[15] = 1;
-        DBG_T(9)
-        IcpResult r;
-        r.fitness = 0; r.rmse = 0; r.iters = 0;
-        if (prm.icp_refine) {
-            r = warp_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, Tsvd, prm.icp_threshold, prm.icp_max_iter, 1e-6, 1e-6,
-                         T64q, nullptr, sm, lane);
-        } else {
-#pragma unroll
-            for (int a = 0; a < 16; ++a)
-                if (lane == a) T64q[a] = Tsvd[a];
-        }
-        __syncwarp();
-        if (lane < 16) T32[(size_t)q * 16 + lane] = (float)T64q[lane];                                // base.py:3366
-        if (lane == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
-#ifdef F4L_DEBUG_SCANS
-        if (lane == 0) atomicAdd(&g_dbg[16], (unsigned long long)(clock64() - dbg_start));
-#endif
+        fit_pair_warp(tab.t[lo], i - tab.prefix[lo], prm, smem[wid], lane);
     }
 }
 
@@ -657,6 +709,61 @@ extern "C" size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t
     return fine_layout(nullptr, n_src_items < 0 ? 0 : n_src_items, Q < 0 ? 0 : Q, mode).total;
 }
 
+static bool fine_optin() {
+    static F4lPerDevice once;
+    if (once.done()) return true;
+    if (!f4l_optin_smem(k_patch_fit, (size_t)ICP_SMEM_PTS * 3 * sizeof(float), "k_patch_fit") ||
+        !f4l_optin_smem(k_apply_assign, (size_t)AA_SMEM_PTS * sizeof(float4), "k_apply_assign") ||
+        !f4l_optin_smem(k_patch_fit_warp, FITW_WARPS * sizeof(WarpIcpSmem), "k_patch_fit_warp") ||
+        !f4l_optin_smem(k_patch_fit_warp_tiles, FITW_WARPS * sizeof(WarpIcpSmem), "k_patch_fit_warp_tiles"))
+        return false;
+    once.mark();
+    return true;
+}
+
+static FitTile fit_tile_of(const f4l_fine_buffers* bf, const FineWs& w) {
+    FitTile t;
+    t.src_pts = bf->src_pts; t.tgt_pts = bf->tgt_pts;
+    t.cs = w.cs; t.ct = w.ct; t.kstart = w.kstart; t.K = bf->K;
+    t.T32 = bf->T; t.T64 = bf->T64; t.status = bf->status; t.fitness = bf->fitness; t.rmse = bf->rmse; t.iters = bf->iters;
+    t.ratio_inlier = bf->ratio_inlier; t.dist_mean = bf->dist_mean;
+    t.Q = bf->Q;
+    return t;
+}
+
+// The small-pair fits of MANY tiles in one persistent launch (k_patch_fit_warp_tiles): between the
+// F4L_FINE_SELECT phase of every tile and their F4L_FINE_FIT_LARGE | F4L_FINE_FINISH phases.
+extern "C" int f4l_fine_fit_tiles(const f4l_fine_params* prm, const f4l_fine_buffers* bufs, void* const* workspaces,
+                                  int32_t n_tiles, int32_t* queue, void* stream) {
+    F4L_REQUIRE(prm && bufs && workspaces && queue, "null argument");
+    F4L_REQUIRE(n_tiles >= 0 && n_tiles <= FIT_MAX_TILES, "n_tiles out of range (at most 128 per call)");
+    if (n_tiles == 0) return F4L_OK;
+    if (!fine_optin()) return F4L_E_CUDA;
+    static_assert(sizeof(FitTable) <= 32000, "the table must fit the kernel parameter space");
+    FitTable tab;
+    tab.n = n_tiles;
+    tab.prefix[0] = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        const f4l_fine_buffers* bf = bufs + i;
+        F4L_REQUIRE(bf->Q >= 0 && bf->n_src_items >= 0, "negative size");
+        F4L_REQUIRE(bf->Q == 0 || (workspaces[i] && bf->src_pts && bf->tgt_pts && bf->K && bf->T && bf->T64 && bf->status &&
+                                   bf->fitness && bf->rmse && bf->iters && bf->ratio_inlier && bf->dist_mean), "null pointer");
+        tab.t[i] = fit_tile_of(bf, fine_layout(workspaces[i], bf->n_src_items, bf->Q, prm->mode));
+        tab.prefix[i + 1] = tab.prefix[i] + bf->Q;
+    }
+    for (int i = n_tiles; i < FIT_MAX_TILES; ++i) tab.prefix[i + 1] = tab.prefix[n_tiles];
+    if (tab.prefix[n_tiles] == 0) return F4L_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = sms * FITW_MIN_BLOCKS;                      // one resident wave, every warp loops on the queue
+    const int need = f4l_div_up(tab.prefix[n_tiles], FITW_WARPS);
+    f4l_mark("k_patch_fit_warp_tiles", st);
+    k_patch_fit_warp_tiles<<<need < slots ? need : slots, FITW_WARPS * 32, FITW_WARPS * sizeof(WarpIcpSmem), st>>>(tab, *prm, queue);
+    return f4l_finish("f4l_fine_fit_tiles", stream);
+}
+
 extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buffers* bf, void* workspace,
                                  size_t workspace_bytes, void* stream) {
     F4L_REQUIRE(prm && bf, "null params");
@@ -689,49 +796,50 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
         f4l_set_error("f4l_fine_matching: workspace too small (%zu < %zu)", workspace_bytes, w.total);
         return F4L_E_WORKSPACE;
     }
-    static F4lPerDevice once;
+    if (!fine_optin()) return F4L_E_CUDA;
     const size_t smem_fit = (size_t)ICP_SMEM_PTS * 3 * sizeof(float);
     const size_t smem_aa = (size_t)AA_SMEM_PTS * sizeof(float4);
-    if (!once.done()) {
-        if (!f4l_optin_smem(k_patch_fit, smem_fit, "k_patch_fit") ||
-            !f4l_optin_smem(k_apply_assign, smem_aa, "k_apply_assign") ||
-            !f4l_optin_smem(k_patch_fit_warp, FITW_WARPS * sizeof(WarpIcpSmem), "k_patch_fit_warp"))
-            return F4L_E_CUDA;
-        once.mark();
+    const int phases = bf->phases ? bf->phases : F4L_FINE_ALL;
+    const FitTile tl = fit_tile_of(bf, w);
+    if (phases & F4L_FINE_SELECT) {
+        f4l_mark("k_select_corr", st);
+        k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
+                                                       bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
+                                                       prm->mode, w.cs, w.ct, w.kstart, bf->K);
     }
-    f4l_mark("k_select_corr", st);
-    k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
-                                                   bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
-                                                   prm->mode, w.cs, w.ct, w.kstart, bf->K);
-    const int grid_w = f4l_div_up(Q, FITW_WARPS) < 148 * 32 / FITW_WARPS ? f4l_div_up(Q, FITW_WARPS) : 148 * 32 / FITW_WARPS;
-    f4l_mark("k_patch_fit_warp", st);
-    k_patch_fit_warp<<<grid_w, FITW_WARPS * 32, FITW_WARPS * sizeof(WarpIcpSmem), st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q, *prm,
-                                                        bf->T, bf->T64, bf->status, bf->fitness, bf->rmse, bf->iters,
-                                                        bf->ratio_inlier, bf->dist_mean);
-    const int grid_fit = Q < 148 * 16 ? Q : 148 * 16;
-    f4l_mark("k_patch_fit", st);
-    k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
-                                                        *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
-                                                        bf->iters, bf->ratio_inlier, bf->dist_mean);
-    f4l_mark("k_row_offsets", st);
-    k_row_offsets<<<1, 1024, 0, st>>>(bf->status, bf->sp_ptr, bf->tp_ptr, Q, prm->icp_refine ? 1 : 0, w.dense_off,
-                                      w.t2s_off, bf->counts);
-    const int grid_aa = Q < 148 * 8 ? Q : 148 * 8;
-    if (bf->median_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)bf->median_ready_event, 0);
-    f4l_mark("k_apply_assign", st);
-    k_apply_assign<<<grid_aa, AA_THREADS, smem_aa, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
-                                                        bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T,
-                                                        bf->rmse, w.dense_off, w.t2s_off, Q, *prm,
-                                                        bf->d_median_resolution, bf->dense, bf->tgt2src, w.nn,
-                                                        w.sparse_cnt, bf->n_peers, peers);
-    if (bf->sparse_pair_rows)
-        cudaMemcpyAsync(bf->sparse_pair_rows, w.sparse_cnt, (size_t)Q * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-    f4l_mark("k_sparse_offsets", st);
-    k_sparse_offsets<<<1, 1024, 0, st>>>(w.sparse_cnt, Q, w.sparse_off, bf->counts);
-    f4l_mark("k_emit_sparse", st);
-    k_emit_sparse<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
-                                                   bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T, w.nn,
-                                                   w.sparse_cnt, w.sparse_off, Q, *prm, bf->sparse);
+    if (phases & F4L_FINE_FIT_SMALL) {
+        const int grid_w = f4l_div_up(Q, FITW_WARPS) < 148 * 32 / FITW_WARPS ? f4l_div_up(Q, FITW_WARPS) : 148 * 32 / FITW_WARPS;
+        f4l_mark("k_patch_fit_warp", st);
+        k_patch_fit_warp<<<grid_w, FITW_WARPS * 32, FITW_WARPS * sizeof(WarpIcpSmem), st>>>(tl, *prm);
+    }
+    if (phases & F4L_FINE_FIT_LARGE) {
+        const int grid_fit = Q < 148 * 16 ? Q : 148 * 16;
+        f4l_mark("k_patch_fit", st);
+        k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
+                                                            *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
+                                                            bf->iters, bf->ratio_inlier, bf->dist_mean);
+    }
+    if (phases & F4L_FINE_FINISH) {
+        f4l_mark("k_row_offsets", st);
+        k_row_offsets<<<1, 1024, 0, st>>>(bf->status, bf->sp_ptr, bf->tp_ptr, Q, prm->icp_refine ? 1 : 0, w.dense_off,
+                                          w.t2s_off, bf->counts);
+        const int grid_aa = Q < 148 * 8 ? Q : 148 * 8;
+        if (bf->median_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)bf->median_ready_event, 0);
+        f4l_mark("k_apply_assign", st);
+        k_apply_assign<<<grid_aa, AA_THREADS, smem_aa, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
+                                                            bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T,
+                                                            bf->rmse, w.dense_off, w.t2s_off, Q, *prm,
+                                                            bf->d_median_resolution, bf->dense, bf->tgt2src, w.nn,
+                                                            w.sparse_cnt, bf->n_peers, peers);
+        if (bf->sparse_pair_rows)
+            cudaMemcpyAsync(bf->sparse_pair_rows, w.sparse_cnt, (size_t)Q * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+        f4l_mark("k_sparse_offsets", st);
+        k_sparse_offsets<<<1, 1024, 0, st>>>(w.sparse_cnt, Q, w.sparse_off, bf->counts);
+        f4l_mark("k_emit_sparse", st);
+        k_emit_sparse<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->src_pts, bf->tgt_pts, bf->sp_idx, bf->sp_ptr, bf->tp_idx,
+                                                       bf->tp_ptr, w.cs, w.kstart, bf->K, bf->status, bf->T, w.nn,
+                                                       w.sparse_cnt, w.sparse_off, Q, *prm, bf->sparse);
+    }
     return f4l_finish("f4l_fine_matching", stream);
 }
 

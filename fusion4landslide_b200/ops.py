@@ -294,16 +294,32 @@ _MODES = {"only_3d": 0, "only_2d": 1, "fusion": 2}
 _ASSIGN = {"assign_all_src": 0, "assign_then_nn": 1, "assign_then_nn_once": 2}
 
 
-def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_point, pair_tgt_patch,
-                  corr3d=None, corr2d=None, mode="only_3d", remove_low_quality_patch_matches=True,
-                  num_min_matches_for_quality_check=10, thres_dist_diff=0.5, thres_inlier_ratio=0.15,
-                  num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
-                  output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
-                  d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None,
-                  peer_dense=None, median_event=None):
-    """Fused fine-matching stage of one tile (f4l_fine_matching).  n_*_items = sp_ptr[-1], tp_ptr[-1]
-    (pass them to avoid a device->host read).  peer_dense: device pointers (ints) of the slot of `out.dense`
-    in every peer GPU's exchange buffer (exchange.PeerExchange); the D5 kernel stores each dense row there too."""
+class FineCall:
+    """One tile's fused fine-matching stage, prepared but not yet enqueued: result tensors, parameter / buffer structs and
+    the tile's own workspace.  `run(phases)` enqueues the selected phases on the current stream."""
+    __slots__ = ("result", "prm", "bf", "ws", "device", "_keep")
+
+    def run(self, phases=0):
+        import ctypes
+        self.bf.phases = int(phases)
+        check(lib().f4l_fine_matching(ctypes.byref(self.prm), ctypes.byref(self.bf), ptr(self.ws), self.ws.numel(),
+                                      stream_ptr(self.device)), "f4l_fine_matching")
+        return self.result
+
+
+PHASE_SELECT, PHASE_FIT_SMALL, PHASE_FIT_LARGE, PHASE_FINISH = 1, 2, 4, 8
+
+
+def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_point, pair_tgt_patch,
+                 corr3d=None, corr2d=None, mode="only_3d", remove_low_quality_patch_matches=True,
+                 num_min_matches_for_quality_check=10, thres_dist_diff=0.5, thres_inlier_ratio=0.15,
+                 num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
+                 output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
+                 d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None,
+                 peer_dense=None, median_event=None, own_workspace=False):
+    """Builds the FineCall of one tile (see fine_matching for the arguments).  own_workspace: allocate a workspace that
+    belongs to this call (needed when the phases of several tiles interleave: fine_fit_tiles); default: the per-stream
+    cached one."""
     dev = src_pts.device
     Q = sp_ptr.numel() - 1
     if n_src_items is None:
@@ -353,11 +369,42 @@ def fine_matching(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of
         for i, pp in enumerate(peer_dense):
             bf.peer_dense[i] = int(pp)
     nbytes = lib().f4l_fine_matching_workspace_bytes(n_src_items, n_tgt_items, Q, _MODES[mode])
-    ws = _workspace(nbytes, dev)
+    c = FineCall()
+    c.result, c.prm, c.bf, c.device = r, prm, bf, dev
+    c.ws = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev) if own_workspace else _workspace(nbytes, dev)
+    c._keep = (src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_point, pair_tgt_patch, corr3d, corr2d,
+               d_median_resolution, median_event)
+    return c
+
+
+def fine_matching(*args, **kw):
+    """Fused fine-matching stage of one tile (f4l_fine_matching).  n_*_items = sp_ptr[-1], tp_ptr[-1]
+    (pass them to avoid a device->host read).  peer_dense: device pointers (ints) of the slot of `out.dense`
+    in every peer GPU's exchange buffer (exchange.PeerExchange); the D5 kernel stores each dense row there too."""
+    return fine_prepare(*args, **kw).run(0)
+
+
+_FIT_QUEUES = {}
+
+
+def fine_fit_tiles(calls):
+    """The small-pair fits (rigidity check, Procrustes, ICP; <= 224 matches) of many prepared tiles in ONE persistent
+    launch on the current stream (f4l_fine_fit_tiles): run every call's PHASE_SELECT before (stream-ordered), and
+    PHASE_FIT_LARGE | PHASE_FINISH after.  The calls must own their workspaces (fine_prepare(own_workspace=True))."""
     import ctypes
-    check(lib().f4l_fine_matching(ctypes.byref(prm), ctypes.byref(bf), ptr(ws), ws.numel(), stream_ptr(dev)),
-          "f4l_fine_matching")
-    return r
+    if not calls:
+        return
+    dev = calls[0].device
+    key = (dev.index, stream_ptr(dev))
+    q = _FIT_QUEUES.get(key)
+    if q is None:
+        q = _FIT_QUEUES[key] = torch.zeros((1,), dtype=I32, device=dev)
+    for lo in range(0, len(calls), 128):
+        chunk = calls[lo:lo + 128]
+        arr = (_lib.FineBuffers * len(chunk))(*[c.bf for c in chunk])
+        wss = (ctypes.c_void_p * len(chunk))(*[ptr(c.ws) for c in chunk])
+        check(lib().f4l_fine_fit_tiles(ctypes.byref(chunk[0].prm), arr, wss, len(chunk), ptr(q), stream_ptr(dev)),
+              "f4l_fine_fit_tiles")
 
 
 class DipsIndex:

@@ -137,6 +137,74 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
     return res
 
 
+def displacement_field_tiles_batched(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None, side_streams=None,
+                                     cache=None):
+    """The hot path over many tiles with the rigid fits of ALL tiles in one persistent launch.
+
+    Per tile (on its stream): A1 on a side stream, correspondence selection.  Then, on the caller's stream, one launch
+    in which every resident warp draws the next patch pair of any tile from a device-side queue (ops.fine_fit_tiles:
+    no per-tile wave quantisation, one tail).  Then per tile again: the large pairs, apply + assign, sparse rows.
+    Same results as displacement_field_tiles (the per-pair computation is the same device function).
+    cache: a dict the caller keeps between steps with static buffers (benchmarks, CUDA-graph capture): the prepared
+    calls, their workspaces and events are then built once."""
+    cfg = cfg or FineConfig()
+    if not tiles:
+        return []
+    dev = tiles[0].src.device
+    cur = torch.cuda.current_stream(dev)
+    streams = streams or [cur]
+    n = len(streams)
+    for s in streams:
+        if s is not cur:
+            s.wait_stream(cur)
+    entries = []
+    for i, t in enumerate(tiles):
+        st = streams[i % n]
+        ent = None if cache is None else cache.get(i)
+        with torch.cuda.stream(st):
+            if ent is None:
+                med = (meds[i:i + 1] if meds is not None else torch.empty((1,), dtype=torch.float32, device=dev))
+                side = side_streams[i % len(side_streams)] if side_streams else None
+                ev = torch.cuda.Event() if side is not None else None
+                call = ops.fine_prepare(t.src, t.tgt, t.sp_idx, t.sp_ptr, t.tp_idx, t.tp_ptr, t.tgt_patch_of_point,
+                                        t.pair_tgt_patch, corr3d=t.corr3d, corr2d=t.corr2d, d_median_resolution=med,
+                                        n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items,
+                                        out=None if outs is None else outs[i],
+                                        peer_dense=None if peers is None else peers[i], median_event=ev,
+                                        own_workspace=True, **cfg.fine_kwargs())
+                ent = (call, med, side, ev)
+                if cache is not None:
+                    cache[i] = ent
+            call, med, side, ev = ent
+            if side is None:
+                ops.median_resolution(t.src, t.tgt, out=med)                                   # A1
+            else:
+                side.wait_stream(st)
+                with torch.cuda.stream(side):
+                    ops.median_resolution(t.src, t.tgt, out=med)
+                    ev.record(side)
+            call.run(ops.PHASE_SELECT)
+        entries.append(ent)
+    for s in streams:
+        if s is not cur:
+            cur.wait_stream(s)
+    ops.fine_fit_tiles([e[0] for e in entries])
+    for s in streams:
+        if s is not cur:
+            s.wait_stream(cur)
+    res = []
+    for i, (call, med, side, ev) in enumerate(entries):
+        with torch.cuda.stream(streams[i % n]):
+            res.append((call.run(ops.PHASE_FIT_LARGE | ops.PHASE_FINISH), med))
+    for s in streams:
+        if s is not cur:
+            cur.wait_stream(s)
+    if side_streams:
+        for s in side_streams:                 # every A1 was awaited in-stream by its tile's FINISH phase; join for lifetime
+            cur.wait_stream(s)
+    return res
+
+
 class HostTile:
     """Pinned host copy of a TileInputs (what a caller holding numpy / CPU tensors passes)."""
 

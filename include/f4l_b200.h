@@ -224,12 +224,29 @@ typedef struct f4l_fine_buffers {
     void* median_ready_event;    /* cudaEvent_t or NULL: d_median_resolution is produced on ANOTHER stream (A1 is
                                     independent of correspondence selection and the rigid fits); the library makes
                                     `stream` wait for this event right before the first kernel that reads it */
+    int32_t phases;              /* 0 = the whole stage; else an OR of F4L_FINE_*: a caller that fits the small pairs of
+                                    many tiles in one launch (f4l_fine_fit_tiles) runs SELECT, then that, then
+                                    FIT_LARGE | FINISH on the same buffers and workspace */
 } f4l_fine_buffers;
+
+#define F4L_FINE_SELECT 1      /* F2: correspondence selection                       (k_select_corr) */
+#define F4L_FINE_FIT_SMALL 2   /* F3 D2 E1 of pairs with <= 224 matches, warp per pair (k_patch_fit_warp) */
+#define F4L_FINE_FIT_LARGE 4   /* F3 D2 E1 of the larger pairs, CTA per pair           (k_patch_fit) */
+#define F4L_FINE_FINISH 8      /* D5 A4: row offsets, apply + assign, sparse rows */
+#define F4L_FINE_ALL 15
 
 F4L_API size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t n_tgt_items, int32_t Q,
                                          int32_t mode);
 F4L_API int f4l_fine_matching(const f4l_fine_params* h_params, const f4l_fine_buffers* h_buffers,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* The per-patch loop of base.py:3254-3368 (rigidity check, Procrustes, ICP) for the small pairs of n_tiles (<= 128)
+ * tiles in ONE persistent launch: every resident warp draws the next patch pair from a device-side queue, so there is
+ * no per-tile wave quantisation and only one tail.  h_buffers: n_tiles structs (host array) whose F4L_FINE_SELECT
+ * phase has been enqueued before this call in stream order; workspaces[i]: the workspace tile i uses in all its
+ * phases (one per tile -- they are live at the same time); queue: one int32 of device memory (zeroed here). */
+F4L_API int f4l_fine_fit_tiles(const f4l_fine_params* h_params, const f4l_fine_buffers* h_buffers,
+                       void* const* workspaces, int32_t n_tiles, int32_t* queue, void* stream);
 
 /* HOST function (host pointers, no CUDA): the reference appends the sparse rows of a pair twice
  * (base.py:3430,3436).  A caller that moves results over PCIe runs the path with

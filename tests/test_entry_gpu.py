@@ -105,11 +105,22 @@ def test_coarse2fine_class_vs_oracle(cuda, golden_dir, mode):
         close = np.abs(dn - od).max(1) < TOL + 2 * np.spacing(np.float32(np.abs(od).max()))
         # per pair: a pair whose ICP stopped one iteration apart in the two implementations (|delta| < 1e-6 relative
         # convergence test, Open3D semantics) moves by up to ~1e-4 m; such path flips are counted, not hidden
-        sizes = [x.shape[0] for x in ol["fine"]["dense"] if x is not None]
+        of = ol["fine"]
+        qs = [q for q, x in enumerate(of["dense"]) if x is not None]
+        sizes = np.array([of["dense"][q].shape[0] for q in qs])
         ends = np.cumsum(sizes)
-        bad_pairs = sum(1 for a, b in zip(ends - sizes, ends) if not close[a:b].all())
+        # a pair whose ICP ends with fewer than 3 inlier correspondences has a rank-deficient Umeyama problem (rotation
+        # about the line through two points is free): Open3D / Eigen, numpy and the Jacobi SVD here each return SOME
+        # valid minimiser.  Such pairs are counted and exempt; they arise from wrong coarse pairs (fitness ~ 0.1).
+        degenerate = np.array([round(of["fitness"][q] * of["K"][q]) < 3 for q in qs])
+        bad_pairs = 0
+        for k, (a, b) in enumerate(zip(ends - sizes, ends)):
+            if degenerate[k]:
+                continue
+            bad_pairs += not close[a:b].all()
+            assert np.abs(dn[a:b] - od[a:b]).max() < 2e-3, (lv, qs[k])
         assert bad_pairs <= max(1, len(sizes) // 100), (lv, bad_pairs, len(sizes))
-        assert np.abs(dn - od).max() < 2e-3, lv
+        assert degenerate.sum() <= max(1, len(sizes) // 50), (lv, int(degenerate.sum()))
     # merged result: level-1 rows first and complete, later levels only add new source points
     merged = do.corres_3d_refine_apply_icp.cpu().numpy()
     om = o["dense"]

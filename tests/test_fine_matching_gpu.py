@@ -159,3 +159,32 @@ def test_prepare_tile_kernels_match_host_twin(cuda):
     from fusion4landslide_b200 import ops
     e = ops.labels_to_csr(torch.zeros((0,), dtype=torch.int64, device=cuda))
     assert e[0].numel() == 0 and e[1].tolist() == [0] and e[2].numel() == 0
+
+
+def test_batched_fit_over_tiles_equals_per_tile(cuda):
+    """pipeline.displacement_field_tiles_batched (the rigid fits of all tiles in one queue-driven persistent launch,
+    f4l_fine_fit_tiles) returns bit-identical results to the per-tile launches, with and without side streams, and
+    again when the prepared calls are reused from the cache (second step)."""
+    from fusion4landslide_b200 import pipeline, synth
+    tiles = []
+    for k, n in enumerate((9000, 30000, 14000)):
+        d = synth.make_scene(n, seed=40 + k)
+        tiles.append(pipeline.prepare_tile(d["src"].to(cuda), d["tgt"].to(cuda), d["label_src"].to(cuda), d["label_tgt"].to(cuda),
+                                           d["corr3d"].to(cuda)))
+    ref = pipeline.displacement_field_tiles(tiles)
+    torch.cuda.synchronize()
+    streams = pipeline.make_streams(2, cuda)
+    sides = pipeline.make_streams(2, cuda)
+    cache = {}
+    for attempt in range(2):
+        for kw in (dict(), dict(streams=streams, side_streams=sides, cache=cache)):
+            got = pipeline.displacement_field_tiles_batched(tiles, **kw)
+            torch.cuda.synchronize()
+            for (r0, m0), (r1, m1) in zip(ref, got):
+                assert torch.equal(m0, m1)
+                for name in ("T", "T64", "status", "K", "fitness", "rmse", "iters", "ratio_inlier", "dist_mean", "counts"):
+                    assert torch.equal(getattr(r0, name), getattr(r1, name)), name
+                c = r0.counts.tolist()
+                assert c[0] > 1000 and torch.equal(r0.dense[:c[0]], r1.dense[:c[0]])
+                assert torch.equal(r0.sparse[:c[1]], r1.sparse[:c[1]])
+    assert len(cache) == 3

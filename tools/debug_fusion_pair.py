@@ -51,3 +51,21 @@ for lv in range(3):
                 r = oicp.icp_point_to_point(A, B, Tcur, 0.1, 1)
                 print("        it", itn, "fitness %.4f rmse %.6f" % (r["fitness"], r["inlier_rmse"]))
                 Tcur = r["transformation"]
+
+do = c.data_output
+for lv in range(3):
+    fr = c.fine_results_multiple[lv]
+    of = o["levels"][lv]["fine"]
+    dn = do.corres_3d_refine_apply_icp_multiple[lv].cpu().numpy()
+    od = ofm.stack(of["dense"])
+    sizes = [x.shape[0] for x in of["dense"] if x is not None]
+    qs = [q for q, x in enumerate(of["dense"]) if x is not None]
+    ends = np.cumsum(sizes)
+    T = fr.T.cpu().numpy()
+    for q, a, b in zip(qs, ends - np.array(sizes), ends):
+        e = np.abs(dn[a:b] - od[a:b]).max()
+        if e > 1e-4:
+            print("level", lv, "pair", q, "rows", a, b, "max row diff %.4f" % e, "K", of["K"][q], "iters", of["iters"][q], fr.iters[q].item(),
+                  "|dT| %.3e" % np.abs(T[q] - of["T"][q]).max(), "fitness %.4f/%.4f" % (fr.fitness[q].item(), of["fitness"][q]))
+            print("   T gpu\n", T[q], "\n   T oracle\n", of["T"][q], "\n   Tsvd oracle\n", of["Tsvd64"][q])
+            print("   T64 gpu\n", fr.T64[q].cpu().numpy())
