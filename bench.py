@@ -51,9 +51,13 @@ def parse():
     ap.add_argument("--dips-pts", type=int, default=625_000)
     ap.add_argument("--dips-cpu-queries", type=int, default=300)
     ap.add_argument("--a1-overlap", type=int, default=1, help="1: A1 of a tile runs on a side stream next to its rigid fits")
-    ap.add_argument("--fit", default="batched", choices=["batched", "per-tile"],
-                    help="batched (default): the rigid fits of all tiles of a rank in ONE persistent queue-driven launch "
-                         "(pipeline.displacement_field_tiles_batched); per-tile: one fit launch per tile")
+    ap.add_argument("--fit", default="per-tile", choices=["batched", "per-tile"],
+                    help="per-tile (default): one fit launch per tile, tiles overlapped on streams.  batched: the rigid fits of "
+                         "a group of tiles in ONE persistent queue-driven launch (pipeline.displacement_field_tiles_batched): "
+                         "the fit kernel alone is 21 %% faster (no wave quantisation), the step 13 %% slower (it fills every "
+                         "register and leaves the other phases no tail to overlap with) -- measured, DESIGN.md section 4")
+    ap.add_argument("--fit-groups", type=int, default=1, help="batched fit: tile groups per rank (one fit launch each)")
+    ap.add_argument("--fit-ctas", type=int, default=0, help="batched fit: CTAs per SM of the persistent kernel (0 = 4)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the exchange (N > 1)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -296,11 +300,13 @@ def run_b200(a):
     sides = pipeline.make_streams(a.streams, dev) if (a.streams > 1 and a.a1_overlap) else None
 
     caches = [{} for _ in arenas]
+    fit_stream = torch.cuda.Stream(device=dev) if (streams and a.fit == "batched") else None
 
     def step_tiles(par=0):
         if a.fit == "batched":
             pipeline.displacement_field_tiles_batched(tiles, cfg, outs_par[par], meds, streams, peers_par[par],
-                                                      side_streams=sides, cache=caches[par])
+                                                      side_streams=sides, cache=caches[par], groups=a.fit_groups,
+                                                      fit_stream=fit_stream, fit_ctas_per_sm=a.fit_ctas)
         else:
             pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par], side_streams=sides)
 
@@ -534,7 +540,7 @@ def run_b200(a):
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
                              input_gb,
                        "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type, "streams": a.streams,
-                       "cuda_graph": graph is not None, "a1_side_stream": bool(sides), "fit": a.fit},
+                       "cuda_graph": graph is not None, "a1_side_stream": bool(sides), "fit": a.fit, "fit_groups": a.fit_groups, "fit_ctas_per_sm": a.fit_ctas or 4},
             "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline,
             "kernels": kernel_table, "cpu_baseline": cpu, "parity": parity, "breakdown": breakdown,
             "configs": configs_out,

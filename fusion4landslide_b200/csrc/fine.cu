@@ -734,7 +734,7 @@ static FitTile fit_tile_of(const f4l_fine_buffers* bf, const FineWs& w) {
 // The small-pair fits of MANY tiles in one persistent launch (k_patch_fit_warp_tiles): between the
 // F4L_FINE_SELECT phase of every tile and their F4L_FINE_FIT_LARGE | F4L_FINE_FINISH phases.
 extern "C" int f4l_fine_fit_tiles(const f4l_fine_params* prm, const f4l_fine_buffers* bufs, void* const* workspaces,
-                                  int32_t n_tiles, int32_t* queue, void* stream) {
+                                  int32_t n_tiles, int32_t ctas_per_sm, int32_t* queue, void* stream) {
     F4L_REQUIRE(prm && bufs && workspaces && queue, "null argument");
     F4L_REQUIRE(n_tiles >= 0 && n_tiles <= FIT_MAX_TILES, "n_tiles out of range (at most 128 per call)");
     if (n_tiles == 0) return F4L_OK;
@@ -757,7 +757,10 @@ extern "C" int f4l_fine_fit_tiles(const f4l_fine_params* prm, const f4l_fine_buf
     cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int slots = sms * FITW_MIN_BLOCKS;                      // one resident wave, every warp loops on the queue
+    // one resident wave, every warp loops on the queue; fewer CTAs per SM than fit (4: registers and shared memory
+    // are then exhausted) leave room for the kernels of other tiles' phases to run next to it
+    const int per_sm = ctas_per_sm > 0 && ctas_per_sm < FITW_MIN_BLOCKS ? ctas_per_sm : FITW_MIN_BLOCKS;
+    const int slots = sms * per_sm;
     const int need = f4l_div_up(tab.prefix[n_tiles], FITW_WARPS);
     f4l_mark("k_patch_fit_warp_tiles", st);
     k_patch_fit_warp_tiles<<<need < slots ? need : slots, FITW_WARPS * 32, FITW_WARPS * sizeof(WarpIcpSmem), st>>>(tab, *prm, queue);

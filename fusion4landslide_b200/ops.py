@@ -387,7 +387,7 @@ def fine_matching(*args, **kw):
 _FIT_QUEUES = {}
 
 
-def fine_fit_tiles(calls):
+def fine_fit_tiles(calls, ctas_per_sm=0):
     """The small-pair fits (rigidity check, Procrustes, ICP; <= 224 matches) of many prepared tiles in ONE persistent
     launch on the current stream (f4l_fine_fit_tiles): run every call's PHASE_SELECT before (stream-ordered), and
     PHASE_FIT_LARGE | PHASE_FINISH after.  The calls must own their workspaces (fine_prepare(own_workspace=True))."""
@@ -403,7 +403,7 @@ def fine_fit_tiles(calls):
         chunk = calls[lo:lo + 128]
         arr = (_lib.FineBuffers * len(chunk))(*[c.bf for c in chunk])
         wss = (ctypes.c_void_p * len(chunk))(*[ptr(c.ws) for c in chunk])
-        check(lib().f4l_fine_fit_tiles(ctypes.byref(chunk[0].prm), arr, wss, len(chunk), ptr(q), stream_ptr(dev)),
+        check(lib().f4l_fine_fit_tiles(ctypes.byref(chunk[0].prm), arr, wss, len(chunk), int(ctas_per_sm), ptr(q), stream_ptr(dev)),
               "f4l_fine_fit_tiles")
 
 

@@ -138,12 +138,14 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
 
 
 def displacement_field_tiles_batched(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None, side_streams=None,
-                                     cache=None):
-    """The hot path over many tiles with the rigid fits of ALL tiles in one persistent launch.
+                                     cache=None, groups=1, fit_stream=None, fit_ctas_per_sm=0):
+    """The hot path over many tiles with the rigid fits of a GROUP of tiles in one persistent launch.
 
-    Per tile (on its stream): A1 on a side stream, correspondence selection.  Then, on the caller's stream, one launch
-    in which every resident warp draws the next patch pair of any tile from a device-side queue (ops.fine_fit_tiles:
-    no per-tile wave quantisation, one tail).  Then per tile again: the large pairs, apply + assign, sparse rows.
+    Per tile (on its stream): A1 on a side stream, correspondence selection.  Per group of tiles, on `fit_stream`: one
+    launch in which every resident warp draws the next patch pair of any tile of the group from a device-side queue
+    (ops.fine_fit_tiles: no per-tile wave quantisation, one tail per group).  Then per tile again: the large pairs,
+    apply + assign, sparse rows.  With groups > 1 the fit launch of one group runs while the tiles of the previous
+    group finish and those of the next one select (the fit kernel is issue-bound, the others memory/latency-bound).
     Same results as displacement_field_tiles (the per-pair computation is the same device function).
     cache: a dict the caller keeps between steps with static buffers (benchmarks, CUDA-graph capture): the prepared
     calls, their workspaces and events are then built once."""
@@ -154,53 +156,69 @@ def displacement_field_tiles_batched(tiles, cfg=None, outs=None, meds=None, stre
     cur = torch.cuda.current_stream(dev)
     streams = streams or [cur]
     n = len(streams)
-    for s in streams:
+    fit_stream = fit_stream or cur
+    for s in list(streams) + [fit_stream]:
         if s is not cur:
             s.wait_stream(cur)
-    entries = []
-    for i, t in enumerate(tiles):
-        st = streams[i % n]
-        ent = None if cache is None else cache.get(i)
-        with torch.cuda.stream(st):
-            if ent is None:
-                med = (meds[i:i + 1] if meds is not None else torch.empty((1,), dtype=torch.float32, device=dev))
-                side = side_streams[i % len(side_streams)] if side_streams else None
-                ev = torch.cuda.Event() if side is not None else None
-                call = ops.fine_prepare(t.src, t.tgt, t.sp_idx, t.sp_ptr, t.tp_idx, t.tp_ptr, t.tgt_patch_of_point,
-                                        t.pair_tgt_patch, corr3d=t.corr3d, corr2d=t.corr2d, d_median_resolution=med,
-                                        n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items,
-                                        out=None if outs is None else outs[i],
-                                        peer_dense=None if peers is None else peers[i], median_event=ev,
-                                        own_workspace=True, **cfg.fine_kwargs())
-                ent = (call, med, side, ev)
-                if cache is not None:
-                    cache[i] = ent
-            call, med, side, ev = ent
-            if side is None:
-                ops.median_resolution(t.src, t.tgt, out=med)                                   # A1
-            else:
-                side.wait_stream(st)
-                with torch.cuda.stream(side):
-                    ops.median_resolution(t.src, t.tgt, out=med)
-                    ev.record(side)
-            call.run(ops.PHASE_SELECT)
-        entries.append(ent)
-    for s in streams:
+    groups = max(1, min(int(groups), len(tiles)))
+    per = (len(tiles) + groups - 1) // groups
+    res = [None] * len(tiles)
+    group_idx = [list(range(g0, min(g0 + per, len(tiles)))) for g0 in range(0, len(tiles), per)]
+
+    def select(idx):
+        entries = []
+        for i in idx:
+            t = tiles[i]
+            st = streams[i % n]
+            ent = None if cache is None else cache.get(i)
+            with torch.cuda.stream(st):
+                if ent is None:
+                    med = (meds[i:i + 1] if meds is not None else torch.empty((1,), dtype=torch.float32, device=dev))
+                    side = side_streams[i % len(side_streams)] if side_streams else None
+                    ev = torch.cuda.Event() if side is not None else None
+                    call = ops.fine_prepare(t.src, t.tgt, t.sp_idx, t.sp_ptr, t.tp_idx, t.tp_ptr, t.tgt_patch_of_point,
+                                            t.pair_tgt_patch, corr3d=t.corr3d, corr2d=t.corr2d, d_median_resolution=med,
+                                            n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items,
+                                            out=None if outs is None else outs[i],
+                                            peer_dense=None if peers is None else peers[i], median_event=ev,
+                                            own_workspace=True, **cfg.fine_kwargs())
+                    ent = (call, med, side, ev)
+                    if cache is not None:
+                        cache[i] = ent
+                call, med, side, ev = ent
+                if side is None:
+                    ops.median_resolution(t.src, t.tgt, out=med)                               # A1
+                else:
+                    side.wait_stream(st)
+                    with torch.cuda.stream(side):
+                        ops.median_resolution(t.src, t.tgt, out=med)
+                        ev.record(side)
+                call.run(ops.PHASE_SELECT)
+                sel_ev = torch.cuda.Event()
+                sel_ev.record(st)
+            entries.append(ent + (sel_ev,))
+        return entries
+
+    # software pipeline over the groups: the selections of group g+1 are enqueued on the tile streams BEFORE the finish
+    # phases of group g, so the fit launch of g+1 follows that of g on the fit stream while group g finishes
+    pending = select(group_idx[0])
+    for g, idx in enumerate(group_idx):
+        entries = pending
+        with torch.cuda.stream(fit_stream):
+            for e in entries:
+                fit_stream.wait_event(e[4])
+            ops.fine_fit_tiles([e[0] for e in entries], fit_ctas_per_sm)
+            fit_ev = torch.cuda.Event()
+            fit_ev.record(fit_stream)
+        if g + 1 < len(group_idx):
+            pending = select(group_idx[g + 1])
+        for i, (call, med, side, ev, sel_ev) in zip(idx, entries):
+            st = streams[i % n]
+            with torch.cuda.stream(st):
+                st.wait_event(fit_ev)
+                res[i] = (call.run(ops.PHASE_FIT_LARGE | ops.PHASE_FINISH), med)
+    for s in list(streams) + [fit_stream] + list(side_streams or []):
         if s is not cur:
-            cur.wait_stream(s)
-    ops.fine_fit_tiles([e[0] for e in entries])
-    for s in streams:
-        if s is not cur:
-            s.wait_stream(cur)
-    res = []
-    for i, (call, med, side, ev) in enumerate(entries):
-        with torch.cuda.stream(streams[i % n]):
-            res.append((call.run(ops.PHASE_FIT_LARGE | ops.PHASE_FINISH), med))
-    for s in streams:
-        if s is not cur:
-            cur.wait_stream(s)
-    if side_streams:
-        for s in side_streams:                 # every A1 was awaited in-stream by its tile's FINISH phase; join for lifetime
             cur.wait_stream(s)
     return res
 

@@ -244,9 +244,11 @@ F4L_API int f4l_fine_matching(const f4l_fine_params* h_params, const f4l_fine_bu
  * tiles in ONE persistent launch: every resident warp draws the next patch pair from a device-side queue, so there is
  * no per-tile wave quantisation and only one tail.  h_buffers: n_tiles structs (host array) whose F4L_FINE_SELECT
  * phase has been enqueued before this call in stream order; workspaces[i]: the workspace tile i uses in all its
- * phases (one per tile -- they are live at the same time); queue: one int32 of device memory (zeroed here). */
+ * phases (one per tile -- they are live at the same time); queue: one int32 of device memory (zeroed here).
+ * ctas_per_sm: 0 = as many as fit (4); 1-3 leave registers / shared memory for the other phases' kernels of other
+ * tiles to run concurrently on other streams. */
 F4L_API int f4l_fine_fit_tiles(const f4l_fine_params* h_params, const f4l_fine_buffers* h_buffers,
-                       void* const* workspaces, int32_t n_tiles, int32_t* queue, void* stream);
+                       void* const* workspaces, int32_t n_tiles, int32_t ctas_per_sm, int32_t* queue, void* stream);
 
 /* HOST function (host pointers, no CUDA): the reference appends the sparse rows of a pair twice
  * (base.py:3430,3436).  A caller that moves results over PCIe runs the path with
