@@ -409,7 +409,9 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
     extern __shared__ float4 sref[];
     // dense rows of one chunk of AA_THREADS source points: written out as contiguous float2 runs to the local
     // arena AND to the same rows of every peer GPU's arena (the displacement-field all-gather, fused)
-    __shared__ __align__(16) float srow[AA_THREADS * 6];
+    // (+4 floats: the staging is shifted by 8 bytes when the peers' destination is 8 mod 16, so that the bulk copy's
+    // source and destination are both 16-byte aligned)
+    __shared__ __align__(16) float srow_buf[AA_THREADS * 6 + 4];
     __shared__ int s_cnt;
     __shared__ unsigned s_maxabs;
     __shared__ unsigned s_bb[6];
@@ -551,6 +553,8 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
         const size_t row0 = (size_t)dense_off[q];
         for (int base = 0; base < ns; base += AA_THREADS) {
           const int i = base + tid;
+          const unsigned mis = n_peers > 0 ? (unsigned)((uintptr_t)(peers.p[0] + (row0 + base) * 6) & 15u) : 0u;   // 0 or 8
+          float* srow = srow_buf + (mis >> 2);
           if (i < ns) {
             double x, y, z;
             load_pt(src_pts, sp_idx, s0 + i, x, y, z);
@@ -606,9 +610,31 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
               const float2* s2 = reinterpret_cast<const float2*>(srow);
               float2* d2 = reinterpret_cast<float2*>(dense + (row0 + base) * 6);
               for (int t = tid; t < n2; t += AA_THREADS) d2[t] = s2[t];
-              for (int p = 0; p < n_peers; ++p) {
-                  float2* r2 = reinterpret_cast<float2*>(peers.p[p] + (row0 + base) * 6);
-                  for (int t = tid; t < n2; t += AA_THREADS) r2[t] = s2[t];
+              if (n_peers > 0) {
+                  // the same rows into every peer GPU's field over NVLink: one bulk copy (TMA, shared -> peer global)
+                  // per peer, issued by one thread -- the CTA does not wait for the link (7 unicast float2 store
+                  // loops stalled it before: 0.74 scaling efficiency at 8 GPUs); the 8-byte head / tail that the
+                  // 16-byte granularity of the bulk copy leaves over go as plain stores
+                  const unsigned bytes = (unsigned)n2 * 8u;
+                  const unsigned head = mis ? 8u : 0u;
+                  const unsigned body = (bytes - head) & ~15u;
+                  const unsigned tail = bytes - head - body;
+                  if (tid == 0 && body) {
+                      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                      const uint32_t src = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<const char*>(srow) + head);
+                      for (int p = 0; p < n_peers; ++p) {
+                          char* dst = reinterpret_cast<char*>(peers.p[p] + (row0 + base) * 6) + head;
+                          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(body)
+                                       : "memory");
+                      }
+                      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  }
+                  if (tid >= 32 && tid < 32 + n_peers) {
+                      float2* r2 = reinterpret_cast<float2*>(peers.p[tid - 32] + (row0 + base) * 6);
+                      if (head) r2[0] = s2[0];
+                      if (tail) r2[n2 - 1] = s2[n2 - 1];
+                  }
+                  if (tid == 0 && body) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // srow reusable
               }
           }
           __syncthreads();
@@ -622,6 +648,7 @@ k_apply_assign(const float* __restrict__ src_pts, const float* __restrict__ tgt_
             sparse_cnt[q] = K[q];                              // assign_all_src: the matched points
         }
     }
+    if (n_peers > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // pushed rows are complete
 }
 
 __global__ void __launch_bounds__(128)
