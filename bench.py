@@ -60,9 +60,11 @@ def parse():
     ap.add_argument("--fit-ctas", type=int, default=0, help="batched fit: CTAs per SM of the persistent kernel (0 = 4)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the exchange (N > 1)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: 'fused' = the D5 kernel stores every dense row into all peers' fields over NVLink "
-                         "(exchange.PeerExchange), 'nccl' = all_gather_into_tensor after the step (baseline)")
+    ap.add_argument("--exchange", default="push", choices=["push", "fused", "nccl"],
+                    help="N > 1: 'push' (default) = a copy kernel per tile (TMA bulk: local rows -> shared memory -> every "
+                         "peer's field over NVLink) on an exchange stream next to the following tiles' fits; 'fused' = the D5 "
+                         "kernel itself stores every dense row into all peers' fields; 'nccl' = all_gather_into_tensor after "
+                         "the step (baseline)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="patch pairs in the CPU sample (0 = auto)")
     ap.add_argument("--scene", default="v2", choices=["v1", "v2"],
                     help="v2 (default): SURVEY 8(d) scenes -- epoch 2 an INDEPENDENT resample, nested patch hierarchy, "
@@ -244,7 +246,8 @@ def run_b200(a):
         caps = torch.tensor([cap_rows, cap_pairs], device=dev, dtype=torch.int64)
         dist.all_reduce(caps, op=dist.ReduceOp.MAX)
         cap_rows, cap_pairs = int(caps[0]), int(caps[1])
-    fused = world > 1 and a.exchange == "fused" and not a.no_gather
+    fused = world > 1 and a.exchange in ("fused", "push") and not a.no_gather      # dense rows travel through peer memory
+    pushing = fused and a.exchange == "push"
     ex = None
     if fused:
         from fusion4landslide_b200.exchange import PeerExchange
@@ -301,12 +304,16 @@ def run_b200(a):
 
     caches = [{} for _ in arenas]
     fit_stream = torch.cuda.Stream(device=dev) if (streams and a.fit == "batched") else None
+    xstream = torch.cuda.Stream(device=dev) if pushing else None
 
     def step_tiles(par=0):
         if a.fit == "batched":
             pipeline.displacement_field_tiles_batched(tiles, cfg, outs_par[par], meds, streams, peers_par[par],
                                                       side_streams=sides, cache=caches[par], groups=a.fit_groups,
                                                       fit_stream=fit_stream, fit_ctas_per_sm=a.fit_ctas)
+        elif pushing:
+            pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, None, side_streams=sides,
+                                              push=(xstream, peers_par[par]))
         else:
             pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par], side_streams=sides)
 
@@ -534,8 +541,11 @@ def run_b200(a):
             "vs_baseline": None, "dtype": "f32 i/o, f64 accumulation", "data": "synthetic",
             "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts,
                        "src_points_per_step": src_points, "dvf_points_per_step": dvf_points,
-                       "parallelism": ("tile-sharded x%d; dense DVF rows stored into every GPU's field by the producing kernel over "
-                                       "NVLink (peer memory), transforms + row counts all-gathered over NCCL" % world) if fused
+                       "parallelism": ("tile-sharded x%d; dense DVF rows of every finished tile copied into every GPU's field over NVLink by "
+                                       "a TMA copy kernel on an exchange stream (peer memory), transforms + row counts all-gathered "
+                                       "over NCCL" % world) if pushing
+                       else ("tile-sharded x%d; dense DVF rows stored into every GPU's field by the producing kernel over "
+                             "NVLink (peer memory), transforms + row counts all-gathered over NCCL" % world) if fused
                        else "tile-sharded x%d, NCCL all-gather of transforms + dense DVF" % world,
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no explicit flush" %
                              input_gb,

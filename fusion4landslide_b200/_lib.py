@@ -77,6 +77,7 @@ SIGNATURES = {
     "f4l_segmented_nn": (c_int, [P, P, P, P, P, P, P, P, c_i32, P, P, P, P, P]),
     "f4l_patch_icp": (c_int, [P, P, P, P, P, P, P, P, P, c_i32, P, c_f64, c_i32, c_f64, c_f64,
                               P, P, P, P, P, P]),
+    "f4l_peer_push": (c_int, [P, P, c_i32, ctypes.c_int64, P, c_i32, c_i32, P]),
     "f4l_fine_fit_tiles": (c_int, [P, P, P, c_i32, c_i32, P, P]),
     "f4l_desc_nn_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_int]),
     "f4l_desc_nn": (c_int, [P, c_i32, P, c_i32, c_i32, P, P, c_f32, c_int, c_int, P, P, P, P, P, c_size, P]),

@@ -407,6 +407,17 @@ def fine_fit_tiles(calls, ctas_per_sm=0):
               "f4l_fine_fit_tiles")
 
 
+def peer_push(rows, d_count, peer_ptrs, n_ctas=0):
+    """Copy rows[:d_count[0]] (device scalar count) into the same slot of every peer's field (f4l_peer_push) on the
+    current stream.  rows: contiguous (n, c) tensor; peer_ptrs: device pointers (ints) of the slot in each peer."""
+    import ctypes
+    if not peer_ptrs:
+        return
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    check(lib().f4l_peer_push(ptr(rows), ptr(d_count, I32), int(rows.shape[1] * rows.element_size()), int(rows.shape[0]),
+                              arr, len(peer_ptrs), int(n_ctas), stream_ptr(rows.device)), "f4l_peer_push")
+
+
 class DipsIndex:
     """Ball-query index of one reference cloud (the counterpart of o3d.geometry.KDTreeFlann(pcd),
     data_loader.py:26): the cloud binned for queries of `radius`, resident in a workspace tensor."""

@@ -94,7 +94,8 @@ def make_streams(n, device):
     return [torch.cuda.Stream(device=device) for _ in range(max(1, int(n)))]
 
 
-def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None, side_streams=None):
+def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None, peers=None, side_streams=None,
+                             push=None):
     """The hot path over many tiles.  With `streams`, tile i runs on streams[i % n]: the small kernels and the
     tail of one tile's patch loop overlap with the next tile's work.  The caller's current stream waits for all
     of them at the end, so events recorded around this call time the whole batch.  `peers[i]`: peer pointers
@@ -102,15 +103,35 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
     gathered field while the tile is computed."""
     cfg = cfg or FineConfig()
     res = []
+
+    def push_rows(i, r, st):
+        # push = (exchange stream, per-tile pointer lists): the finished dense rows of tile i go to every peer's field
+        # through the copy kernel (ops.peer_push) on the exchange stream, while the next tiles are computed
+        xs, ptr_lists = push
+        ev = torch.cuda.Event()
+        ev.record(st)
+        with torch.cuda.stream(xs):
+            xs.wait_event(ev)
+            ops.peer_push(r.dense, r.counts, ptr_lists[i])
+
     if not streams or len(streams) == 1 and streams[0] is None:
+        cur = torch.cuda.current_stream(tiles[0].src.device) if tiles else None
+        if push is not None and tiles:
+            push[0].wait_stream(cur)
         for i, t in enumerate(tiles):
             res.append(displacement_field(t, cfg, out=None if outs is None else outs[i],
                                           med_out=None if meds is None else meds[i:i + 1],
                                           peer_dense=None if peers is None else peers[i]))
+            if push is not None:
+                push_rows(i, res[-1][0], cur)
+        if push is not None and tiles:
+            cur.wait_stream(push[0])
         return res
     cur = torch.cuda.current_stream(tiles[0].src.device) if tiles else None
     for s in streams:
         s.wait_stream(cur)
+    if push is not None:
+        push[0].wait_stream(cur)
     if os.environ.get("F4L_TILE_ORDER", "") == "phased":
         # experiment: every tile's A1 chain first, then every tile's fine matching (same stream per tile)
         med_l = []
@@ -132,8 +153,12 @@ def displacement_field_tiles(tiles, cfg=None, outs=None, meds=None, streams=None
                                               med_out=None if meds is None else meds[i:i + 1],
                                               peer_dense=None if peers is None else peers[i],
                                               side_stream=None if not side_streams else side_streams[i % len(side_streams)]))
+                if push is not None:
+                    push_rows(i, res[-1][0], streams[i % len(streams)])
     for s in streams:
         cur.wait_stream(s)
+    if push is not None:
+        cur.wait_stream(push[0])
     return res
 
 

@@ -371,6 +371,15 @@ F4L_API int f4l_peer_close(void* d_ptr);
 F4L_API int f4l_peer_free(void* d_ptr);
 F4L_API int f4l_peer_enable_access(int32_t peer_device);
 
+/* The displacement-field all-gather as a copy kernel next to the compute (per-step path): rows [0, d_rows[0]) of
+ * `src` (device scalar row count, e.g. f4l_fine_buffers.counts; at most max_rows rows of row_bytes bytes) into the same
+ * slot of every peer's field (peer_dst[i]: mapped pointers from f4l_peer_open; when one of them does not share src's
+ * alignment mod 16 a plain-store kernel is used instead of the bulk copies).
+ * A few CTAs (n_ctas, 0 = 32) stream local HBM -> shared memory -> all peers with TMA bulk copies; enqueue it on a side
+ * stream after the tile's f4l_fine_matching so the transfer overlaps the next tile's fits. */
+F4L_API int f4l_peer_push(const void* src, const int32_t* d_rows, int32_t row_bytes, int64_t max_rows,
+                  void* const* peer_dst, int32_t n_peers, int32_t n_ctas, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 8(f) rank 1 -- DIPs patch front-end.  Replaces src/data_loader.py:16-109
  * (Preprocess_Dataset.__init__ / extract_patch / __getitem__), called from src/f2s3.py:104-134 and

@@ -48,6 +48,48 @@ def test_fused_push_equals_local_rows_same_device(cuda):
         assert bool((p[:off] == -7.0).all()) and bool((p[off + n:] == -7.0).all())      # nothing outside the slot
 
 
+@pytest.mark.parametrize("off,n", [(0, 100_003), (37, 100_000), (1, 1), (3, 0), (2, 5462), (5, 1366)])
+def test_copy_kernel_push_same_device(cuda, off, n):
+    """f4l_peer_push: rows [0, count) of a slot into the same slot of every 'peer' buffer (here on the same device), for
+    16-byte-aligned and 8-mod-16 slots, sizes around the 32 KB chunk, an empty tile; nothing outside the slot."""
+    from fusion4landslide_b200 import ops
+    cap = max(n, 1) + 11
+    arena = torch.randn((off + cap + 7, 6), device=cuda)
+    count = torch.tensor([n, 9, 9, 9], dtype=torch.int32, device=cuda)
+    peers = [torch.full((off + cap + 7, 6), -7.0, device=cuda) for _ in range(3)]
+    ops.peer_push(arena[off:off + cap], count, [p.data_ptr() + off * 24 for p in peers])
+    torch.cuda.synchronize()
+    for p in peers:
+        assert torch.equal(p[off:off + n], arena[off:off + n])
+        assert bool((p[:off] == -7.0).all()) and bool((p[off + n:] == -7.0).all())
+    if n:                                   # destination slot at a different alignment than the source: plain-store path
+        q = torch.full((off + cap + 8, 6), -7.0, device=cuda)
+        ops.peer_push(arena[off:off + cap], count, [q.data_ptr() + (off + 1) * 24])
+        torch.cuda.synchronize()
+        assert torch.equal(q[off + 1:off + 1 + n], arena[off:off + n]) and bool((q[off + 1 + n:] == -7.0).all())
+
+
+def test_tiles_with_copy_kernel_exchange_same_device(cuda):
+    """displacement_field_tiles(push=...): every tile's dense rows land in the 'peer' fields (same device), on an
+    exchange stream, identical to the local rows."""
+    from fusion4landslide_b200 import pipeline
+    tiles = [_tile(cuda, 20_000, 3), _tile(cuda, 26_000, 4), _tile(cuda, 9_000, 5)]
+    offs, o = [], 0
+    for t in tiles:
+        offs.append(o)
+        o += t.n_src_items + 1                                   # odd slot offsets appear
+    fields = [torch.full((o + 4, 6), -3.0, device=cuda) for _ in range(2)]
+    ptrs = [[f.data_ptr() + offs[i] * 24 for f in fields] for i in range(len(tiles))]
+    xs = torch.cuda.Stream(device=cuda)
+    res = pipeline.displacement_field_tiles(tiles, streams=pipeline.make_streams(2, cuda), push=(xs, ptrs))
+    torch.cuda.synchronize()
+    for i, (r, _) in enumerate(res):
+        n = int(r.counts[0])
+        assert n > 1000
+        for f in fields:
+            assert torch.equal(f[offs[i]:offs[i] + n], r.dense[:n])
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_fused_push_to_other_device_one_process(cuda):
     from fusion4landslide_b200 import _lib, pipeline
