@@ -23,7 +23,11 @@ import sys
 import threading
 import time
 
-import torch
+# more hardware work queues than the default 8: the step uses 4 tile streams + 4 side streams (inside a CUDA graph), NCCL's
+# stream and the exchange stream; with 8 queues the exchange stream shares one with graph work and serialises behind it
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -259,7 +263,9 @@ def run_b200(a):
     T_arena = torch.empty((cap_pairs, 4, 4), dtype=torch.float32, device=dev)
     n_tiles_max = (a.tiles + world - 1) // world
     counts_arena = torch.zeros((n_tiles_max, 4), dtype=torch.int32, device=dev)
+    counts_arenas = [counts_arena] + [torch.zeros_like(counts_arena) for _ in arenas[1:]]
     meds = torch.empty((max(len(tiles), 1),), dtype=torch.float32, device=dev)
+    from fusion4landslide_b200 import ops as ops_mod
     from fusion4landslide_b200.ops import FineResult
     outs_par, peers_par = [], []
     shared = None
@@ -286,6 +292,8 @@ def run_b200(a):
             else:                                           # parity 1 differs only in the dense arena
                 for k in FineResult.__slots__:
                     setattr(r, k, getattr(outs_par[0][i], k, None))
+            if par > 0:                                     # the copy kernels of step k read the counts while step k+1 runs
+                r.counts = counts_arenas[par][i]
             r.dense = arena[ro:ro + t.n_src_items]
             outs.append(r)
             peers.append(ex.peer_ptrs(par, ro) if fused else None)
@@ -304,16 +312,16 @@ def run_b200(a):
 
     caches = [{} for _ in arenas]
     fit_stream = torch.cuda.Stream(device=dev) if (streams and a.fit == "batched") else None
-    xstream = torch.cuda.Stream(device=dev) if pushing else None
+    # high priority: the copy kernels are a handful of one-warp CTAs that must not queue behind the fit kernels' waves
+    xstream = torch.cuda.Stream(device=dev, priority=-1) if pushing else None
 
     def step_tiles(par=0):
         if a.fit == "batched":
             pipeline.displacement_field_tiles_batched(tiles, cfg, outs_par[par], meds, streams, peers_par[par],
                                                       side_streams=sides, cache=caches[par], groups=a.fit_groups,
                                                       fit_stream=fit_stream, fit_ctas_per_sm=a.fit_ctas)
-        elif pushing:
-            pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, None, side_streams=sides,
-                                              push=(xstream, peers_par[par]))
+        elif pushing:                                   # the copy kernels are enqueued by step(), after the graph
+            pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, None, side_streams=sides)
         else:
             pipeline.displacement_field_tiles(tiles, cfg, outs_par[par], meds, streams, peers_par[par], side_streams=sides)
 
@@ -347,28 +355,57 @@ def run_b200(a):
         else:
             step_tiles(par)
 
-    def exchange():
+    def exchange(par=0):
         # fused: the dense rows are already in every rank's field; this small all-gather is also the barrier
         # that orders all ranks' pushed rows before anyone reads the field
         dist.all_gather_into_tensor(gathered_T, T_arena)
         if not fused:
             dist.all_gather_into_tensor(gathered_dense, dense_arena)
-        dist.all_gather_into_tensor(gathered_counts, counts_arena.reshape(-1))
+        dist.all_gather_into_tensor(gathered_counts, counts_arenas[par % len(counts_arenas)].reshape(-1))
+
+    push_done = [None]
+
+    def launch_pushes(par):
+        """Exchange of the step just computed, pipelined with the NEXT step: one copy kernel per tile on the exchange
+        stream (ops.peer_push: local rows -> shared memory -> every peer's field, TMA bulk copies).  Half of a rank's
+        rows are produced by its last wave of tiles, so an exchange that must end with the step exposes ~0.7 ms of
+        NVLink time at 8 GPUs (measured: 5.2 ms per step fused or per-tile pushed, 4.1 ms without any exchange); the
+        fields are double-buffered by step parity, so step k's copies run under step k+1's fits instead."""
+        cur = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(xstream):
+            xstream.wait_event(ev)
+            for i in range(len(tiles)):
+                ops_mod.peer_push(outs_par[par][i].dense, outs_par[par][i].counts, peers_par[par][i])
+            done = torch.cuda.Event()
+            done.record(xstream)
+        push_done[0] = done
+
+    def drain_pushes():
+        if push_done[0] is not None:
+            torch.cuda.current_stream(dev).wait_event(push_done[0])
+            push_done[0] = None
 
     def step():
         par = step_no[0] % len(arenas)
         step_no[0] += 1
         compute(par)
         if world > 1 and not a.no_gather:
-            exchange()
+            if pushing:
+                drain_pushes()             # the previous step's rows have left: its field is complete on every rank
+                launch_pushes(par)         # ... once the small all-gather below has passed on all of them
+            exchange(par)
 
     def barrier():
+        torch.cuda.synchronize()           # own copy kernels first: a peer may read its field right after the barrier
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(a.warmup):
         step()
+    drain_pushes()
     barrier()
     L.f4l_launch_count_reset()
     sampler = ClockSampler(local)
@@ -378,6 +415,7 @@ def run_b200(a):
     e0.record()
     for _ in range(a.steps):
         step()
+    drain_pushes()                         # the last step's exchange ends inside the timed region
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -409,10 +447,14 @@ def run_b200(a):
         ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         barrier()
         ea.record()
-        compute(step_no[0] % len(arenas))
+        par_b = step_no[0] % len(arenas)
+        compute(par_b)
         step_no[0] += 1
         eb.record()
-        exchange()
+        if pushing:
+            launch_pushes(par_b)
+            drain_pushes()                 # un-pipelined here: the copies' own duration shows up in exchange_ms
+        exchange(par_b)
         ec.record()
         barrier()
         bd = torch.tensor([ea.elapsed_time(eb), eb.elapsed_time(ec)], device=dev, dtype=torch.float64)
@@ -541,9 +583,10 @@ def run_b200(a):
             "vs_baseline": None, "dtype": "f32 i/o, f64 accumulation", "data": "synthetic",
             "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts,
                        "src_points_per_step": src_points, "dvf_points_per_step": dvf_points,
-                       "parallelism": ("tile-sharded x%d; dense DVF rows of every finished tile copied into every GPU's field over NVLink by "
-                                       "a TMA copy kernel on an exchange stream (peer memory), transforms + row counts all-gathered "
-                                       "over NCCL" % world) if pushing
+                       "parallelism": ("tile-sharded x%d; dense DVF rows copied into every GPU's field over NVLink by TMA copy kernels (one "
+                                       "per tile, peer memory) on an exchange stream, pipelined with the next step's fits (fields "
+                                       "double-buffered by step parity; the last step's copies end inside the timed region); "
+                                       "transforms + row counts all-gathered over NCCL" % world) if pushing
                        else ("tile-sharded x%d; dense DVF rows stored into every GPU's field by the producing kernel over "
                              "NVLink (peer memory), transforms + row counts all-gathered over NCCL" % world) if fused
                        else "tile-sharded x%d, NCCL all-gather of transforms + dense DVF" % world,

@@ -83,7 +83,7 @@ extern "C" int f4l_peer_enable_access(int32_t peer_device) {
 // buffered, one elected thread per CTA.  The row count is a device scalar (f4l_fine_buffers.counts[0]): no host
 // round trip.
 #define PUSH_CHUNK 32768u
-#define PUSH_STAGES 2
+#define PUSH_STAGES 3
 
 struct PushPeers { char* p[F4L_MAX_PEERS]; };
 
