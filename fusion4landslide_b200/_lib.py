@@ -99,6 +99,7 @@ SIGNATURES = {
     "f4l_dips_workspace_bytes": (c_size, [c_i32]),
     "f4l_dips_build": (c_int, [P, c_i32, c_f64, P, c_size, P]),
     "f4l_dips_patches": (c_int, [P, c_i32, c_i32, c_f64, c_i32, P, ctypes.c_uint64, P, P, P, P, c_size, P]),
+    "f4l_dips_patches_large": (c_int, [P, c_i32, c_i32, c_f64, c_i32, ctypes.c_uint64, P, P, P, P, c_size, P]),
     "f4l_voxel_downsample_workspace_bytes": (c_size, [c_i32]),
     "f4l_voxel_downsample": (c_int, [P, c_i32, c_f64, P, P, P, P, c_size, P]),
     "f4l_fine_matching_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),

@@ -33,6 +33,7 @@
 #define DIPS_MIN_BLOCKS 8      // 64 registers, 6.5 KB of shared memory per warp: 32 warps per SM (measured: 8.2 -> 6.5 ms per tile)
 #endif
 #define DIPS_MAXP 256
+#define DIPS_CAP_LARGE 8192    // the dense-cloud variant (f4l_dips_patches_large): one CTA of 4 warps per SM, 33 KB per warp
 
 struct DipsGrid {
     unsigned long long lo[3], hi[3];   // ordered-uint images of the bounding box (atomicMin / atomicMax)
@@ -146,8 +147,9 @@ __global__ void __launch_bounds__(256) k_dips_gather(const double* __restrict__ 
 
 // ---- the per-query kernel ------------------------------------------------------------------------
 #define DIPS_ROWCAP 128
+template <int CAP>
 struct DipsWarpSmem {
-    unsigned list[DIPS_CAP];        // positions of the hits in `sorted`
+    unsigned list[CAP];             // positions of the hits in `sorted`
     int rows[2 * DIPS_ROWCAP];      // pass 1: [begin | end) of the candidate range of every grid row the ball touches
 };
 struct DipsRankSmem {               // ranked mode only
@@ -199,16 +201,16 @@ __device__ __forceinline__ double dips_slab(double v, double a, double b, bool f
     return d;
 }
 
-template <bool RANKED>
-__global__ void __launch_bounds__(DIPS_WARPS * 32, DIPS_MIN_BLOCKS)
+template <bool RANKED, int CAP, int MIN_BLOCKS>
+__global__ void __launch_bounds__(DIPS_WARPS * 32, MIN_BLOCKS)
 k_dips_patches(const double* __restrict__ query, int nq, const double4* __restrict__ sorted,
                const int* __restrict__ cell_start, const DipsGrid* __restrict__ gp, double radius, int num_points,
                const int32_t* __restrict__ ranks, unsigned long long seed, float* __restrict__ patches,
                double* __restrict__ lrf, int32_t* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char dips_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    DipsWarpSmem& sm = reinterpret_cast<DipsWarpSmem*>(dips_raw)[wid];
-    DipsRankSmem* rk = RANKED ? reinterpret_cast<DipsRankSmem*>(dips_raw + DIPS_WARPS * sizeof(DipsWarpSmem)) + wid : nullptr;
+    DipsWarpSmem<CAP>& sm = reinterpret_cast<DipsWarpSmem<CAP>*>(dips_raw)[wid];
+    DipsRankSmem* rk = RANKED ? reinterpret_cast<DipsRankSmem*>(dips_raw + DIPS_WARPS * sizeof(DipsWarpSmem<CAP>)) + wid : nullptr;
     const DipsGrid g = *gp;
     const double r2 = radius * radius;
     const double inv_r = 1.0 / radius;
@@ -246,7 +248,7 @@ k_dips_patches(const double* __restrict__ query, int nq, const double4* __restri
             const unsigned m = __ballot_sync(F4L_FULL, hit);
             if (hit) {
                 const int slot = n + __popc(m & ((1u << lane) - 1u));
-                if (slot < DIPS_CAP) sm.list[slot] = (unsigned)j;
+                if (slot < CAP) sm.list[slot] = (unsigned)j;
             }
             n += __popc(m);
         };
@@ -309,8 +311,9 @@ k_dips_patches(const double* __restrict__ query, int nq, const double4* __restri
         __syncwarp();
         if (lane == 0) count[q] = n;
         float* outq = patches + (size_t)q * 3 * num_points;
-        if (n > DIPS_CAP) {
-            // documented limit: the patch is left zero and count[q] reports the size (host mirror raises)
+        if (n > CAP) {
+            // more neighbours than this variant keeps on chip: the patch is left zero and count[q] reports the size;
+            // the host mirror re-runs such queries through f4l_dips_patches_large (CAP 8192) and raises beyond that
             for (int t = lane; t < 3 * num_points; t += 32) outq[t] = 0.f;
             if (lrf && lane < 9) lrf[(size_t)q * 9 + lane] = 0.0;
             continue;
@@ -507,37 +510,62 @@ extern "C" int f4l_dips_build(const double* ref64, int32_t n_ref, double radius,
     return f4l_finish("f4l_dips_build", stream);
 }
 
-extern "C" int f4l_dips_patches(const double* query64, int32_t n_query, int32_t n_ref, double radius, int32_t num_points,
-                                const int32_t* ranks, uint64_t seed, float* patches, double* lrf, int32_t* count,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+static int dips_patches_launch(const double* query64, int32_t n_query, int32_t n_ref, double radius, int32_t num_points,
+                               const int32_t* ranks, uint64_t seed, float* patches, double* lrf, int32_t* count,
+                               void* workspace, size_t workspace_bytes, void* stream, bool large, const char* what) {
     F4L_REQUIRE(n_query >= 0, "n_query < 0");
     if (n_query == 0) return F4L_OK;
     F4L_REQUIRE(query64 && patches && count && workspace, "null pointer");
     F4L_REQUIRE(n_ref >= 1, "empty reference cloud");
     F4L_REQUIRE(num_points >= 1 && num_points <= DIPS_MAXP, "num_points must be in [1, 256]");
     F4L_REQUIRE(radius > 0.0, "radius must be positive");
+    F4L_REQUIRE(!(large && ranks), "the large variant has no ranked mode");
     const DipsWs w = dips_layout(workspace, n_ref);
     if (workspace_bytes < w.total) {
-        f4l_set_error("f4l_dips_patches: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        f4l_set_error("%s: workspace too small (%zu < %zu)", what, workspace_bytes, w.total);
         return F4L_E_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = min(f4l_div_up(n_query, DIPS_WARPS), 148 * 16);
-    if (ranks) {
-        const size_t smem = DIPS_WARPS * (sizeof(DipsWarpSmem) + sizeof(DipsRankSmem));
+    if (large) {
+        const size_t smem = DIPS_WARPS * sizeof(DipsWarpSmem<DIPS_CAP_LARGE>);
         static F4lPerDevice once;
         if (!once.done()) {
-            if (!f4l_optin_smem(k_dips_patches<true>, smem, "k_dips_patches<ranked>")) return F4L_E_CUDA;
+            if (!f4l_optin_smem(k_dips_patches<false, DIPS_CAP_LARGE, 1>, smem, "k_dips_patches<large>")) return F4L_E_CUDA;
+            once.mark();
+        }
+        f4l_mark("k_dips_patches_large", st);
+        k_dips_patches<false, DIPS_CAP_LARGE, 1><<<min(grid, 148), DIPS_WARPS * 32, smem, st>>>(
+            query64, n_query, w.sorted, w.table, w.grid, radius, num_points, nullptr, seed, patches, lrf, count);
+    } else if (ranks) {
+        const size_t smem = DIPS_WARPS * (sizeof(DipsWarpSmem<DIPS_CAP>) + sizeof(DipsRankSmem));
+        static F4lPerDevice once;
+        if (!once.done()) {
+            if (!f4l_optin_smem(k_dips_patches<true, DIPS_CAP, DIPS_MIN_BLOCKS>, smem, "k_dips_patches<ranked>")) return F4L_E_CUDA;
             once.mark();
         }
         f4l_mark("k_dips_patches_ranked", st);
-        k_dips_patches<true><<<grid, DIPS_WARPS * 32, smem, st>>>(query64, n_query, w.sorted, w.table, w.grid, radius,
-                                                                   num_points, ranks, seed, patches, lrf, count);
+        k_dips_patches<true, DIPS_CAP, DIPS_MIN_BLOCKS><<<grid, DIPS_WARPS * 32, smem, st>>>(
+            query64, n_query, w.sorted, w.table, w.grid, radius, num_points, ranks, seed, patches, lrf, count);
     } else {
-        const size_t smem = DIPS_WARPS * sizeof(DipsWarpSmem);
+        const size_t smem = DIPS_WARPS * sizeof(DipsWarpSmem<DIPS_CAP>);
         f4l_mark("k_dips_patches", st);
-        k_dips_patches<false><<<grid, DIPS_WARPS * 32, smem, st>>>(query64, n_query, w.sorted, w.table, w.grid, radius,
-                                                                    num_points, nullptr, seed, patches, lrf, count);
+        k_dips_patches<false, DIPS_CAP, DIPS_MIN_BLOCKS><<<grid, DIPS_WARPS * 32, smem, st>>>(
+            query64, n_query, w.sorted, w.table, w.grid, radius, num_points, nullptr, seed, patches, lrf, count);
     }
-    return f4l_finish("f4l_dips_patches", stream);
+    return f4l_finish(what, stream);
+}
+
+extern "C" int f4l_dips_patches(const double* query64, int32_t n_query, int32_t n_ref, double radius, int32_t num_points,
+                                const int32_t* ranks, uint64_t seed, float* patches, double* lrf, int32_t* count,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    return dips_patches_launch(query64, n_query, n_ref, radius, num_points, ranks, seed, patches, lrf, count, workspace,
+                               workspace_bytes, stream, false, "f4l_dips_patches");
+}
+
+extern "C" int f4l_dips_patches_large(const double* query64, int32_t n_query, int32_t n_ref, double radius,
+                                      int32_t num_points, uint64_t seed, float* patches, double* lrf, int32_t* count,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    return dips_patches_launch(query64, n_query, n_ref, radius, num_points, nullptr, seed, patches, lrf, count, workspace,
+                               workspace_bytes, stream, true, "f4l_dips_patches_large");
 }

@@ -133,7 +133,11 @@ __device__ __forceinline__ float ring_margin2(const GridParams& g, float qx, flo
     if (cz - R > 0) margin = fminf(margin, qz - (g.minz + (float)(cz - R) * g.cell));
     if (cz + R < g.nz - 1) margin = fminf(margin, (g.minz + (float)(cz + R + 1) * g.cell) - qz);
     if (margin == INFINITY) return INFINITY;
-    margin = fmaxf(margin - 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + g.cell), 0.f);
+    // f32 error budget: the border positions (min + c * cell) round with |coordinate|, the binning
+    // floor((x - min) * inv) with the extent of the grid -- both terms, so that a reference point binned one cell
+    // off its geometric cell can never lie beyond a ring that was declared final
+    const float extent = ((float)g.nx + (float)g.ny + (float)g.nz) * g.cell;
+    margin = fmaxf(margin - 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + extent + g.cell), 0.f);
     return margin * margin;
 }
 

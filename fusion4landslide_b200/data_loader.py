@@ -13,6 +13,7 @@ from . import ops
 from ._lib import F4LError
 
 DIPS_CAP = 1408
+DIPS_CAP_LARGE = 8192
 
 
 def _cloud(x, device):
@@ -47,9 +48,17 @@ class Preprocess_Dataset(torch.utils.data.Dataset):
         if idx < 0 or offset >= self.data.shape[0]:
             raise IndexError(idx)
         patches, count = self.patches(offset, self.points_per_batch)[:2]
-        if int(count.max()) > DIPS_CAP:
-            raise F4LError("a point has %d neighbours within the feature radius (supported: %d); the reference's "
-                           "radius rule sqrt(3)*10*resolution yields about 940" % (int(count.max()), DIPS_CAP))
+        cmax = int(count.max())
+        if cmax > DIPS_CAP:
+            # denser neighbourhoods than the fast kernel keeps on chip: those queries again through the large variant
+            if cmax > DIPS_CAP_LARGE:
+                raise F4LError("a point has %d neighbours within the feature radius (supported: %d); the reference's "
+                               "radius rule sqrt(3)*10*resolution yields about 940" % (cmax, DIPS_CAP_LARGE))
+            big = torch.nonzero(count > DIPS_CAP).reshape(-1)
+            q = self.data[offset:offset + self.points_per_batch][big].contiguous()
+            p2, _ = ops.dips_patches(self.pcd_tree, q, self.num_points, seed=self.seed * 0x9E3779B97F4A7C15 + offset + 1,
+                                     large=True)
+            patches[big] = p2
         return patches
 
     def __len__(self):

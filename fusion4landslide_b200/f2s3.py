@@ -41,10 +41,14 @@ def filter_input_tail(corr, scores, seg_ptr, coeff=1.0):
 
 
 def correspondence_pruning(corr, scores, seg_ptr, data_dir="", refine_results=False, max_disp_magnitude=0.0,
-                           filter_median_magnitude=False):
+                           filter_median_magnitude=False, return_saved=False):
     """src/f2s3.py:340-441 after the network: keep mask per row (robust and refine_results -> whole supervoxel,
-    else score > 0.99999), saved rows are the UNREFINED coordinates (quirk q6), then magnitude <= max and the
-    optional 30 x median gate.  Returns (kept rows (k,6), magnitudes (k,), keep mask (K,))."""
+    else score > 0.99999), saved rows are the UNREFINED coordinates (quirk q6).  The two magnitude gates as the
+    reference applies them: the SAVED rows (`final_results`, :392-393) pass `mag <= max_disp_magnitude`
+    unconditionally (so max = 0 keeps only zero displacements); the population of the 30 x median gate (:419-431) is
+    gated strictly, `mag < max`, and only when max > 0.  Returns (rows (k,6), magnitudes (k,), keep mask (K,)): the
+    median-filtered rows when filter_median_magnitude, else the saved rows; return_saved=True appends the saved rows
+    and their magnitudes."""
     corr = _dev_f32(corr)
     coeff = 2.5 if 'Rockfall_Simulator' in data_dir else 1.0
     _, _, robust, _ = filter_input_tail(corr, scores, seg_ptr, coeff)
@@ -56,13 +60,22 @@ def correspondence_pruning(corr, scores, seg_ptr, data_dir="", refine_results=Fa
     if refine_results:
         keep = keep | robust[seg_of_row]
     rows = corr[keep].contiguous()
-    mask, mag = ops.magnitude_mask(rows, max_mag=max_disp_magnitude if max_disp_magnitude > 0 else float("inf"))
+    mask, mag = ops.magnitude_mask(rows, max_mag=float(max_disp_magnitude))                    # :392-393, non-strict
     sel = mask.bool()
-    rows, mag = rows[sel], mag[sel]
-    if filter_median_magnitude and rows.shape[0] > 0:
-        n = mag.shape[0]
-        kth = ops.select_kth(mag.contiguous(), (n - 1) // 2, n // 2)          # np.median: mean of the middle two
-        med = (0.5 * (kth[0] + kth[1])).reshape(1)
-        m2 = ops.magnitude_mask(rows.contiguous(), d_max=med, factor=30.0, strict=True, want_mag=False).bool()
-        rows, mag = rows[m2], mag[m2]
-    return rows, mag, keep
+    saved, saved_mag = rows[sel], mag[sel]
+    out_rows, out_mag = saved, saved_mag
+    if filter_median_magnitude:
+        if max_disp_magnitude > 0:                                                             # :419-424, strict
+            m1 = ops.magnitude_mask(rows, max_mag=float(max_disp_magnitude), strict=True, want_mag=False).bool()
+            out_rows, out_mag = rows[m1], mag[m1]
+        else:
+            out_rows, out_mag = rows, mag
+        if out_rows.shape[0] > 0:
+            n = out_mag.shape[0]
+            kth = ops.select_kth(out_mag.contiguous(), (n - 1) // 2, n // 2)          # np.median: mean of the middle two
+            med = (0.5 * (kth[0] + kth[1])).reshape(1)
+            m2 = ops.magnitude_mask(out_rows.contiguous(), d_max=med, factor=30.0, strict=True, want_mag=False).bool()
+            out_rows, out_mag = out_rows[m2], out_mag[m2]
+    if return_saved:
+        return out_rows, out_mag, keep, saved, saved_mag
+    return out_rows, out_mag, keep

@@ -25,6 +25,28 @@ def _dev_f32(x, device=None):
     return x.to(torch.float32).contiguous()
 
 
+def _dev_f32_local(a, b):
+    """Two clouds as float32 device tensors in a COMMON LOCAL FRAME: float64 inputs (the reference hands Open3D /
+    numpy float64 coordinates to sklearn here, src/f2s3.py:453-454) are shifted by their joint minimum in float64
+    before the cast, so georeferenced coordinates (~1e6 m, float32 spacing 0.06-0.25 m) lose nothing that matters to a
+    distance.  float32 inputs pass through unchanged."""
+    ta = a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a))
+    tb = b if torch.is_tensor(b) else torch.as_tensor(np.asarray(b))
+    if ta.dtype != torch.float64 and tb.dtype != torch.float64:
+        fa = _dev_f32(ta)
+        return fa, _dev_f32(tb, fa.device)
+    if not ta.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("fusion4landslide_b200 needs a CUDA device (no CPU fallback)")
+        ta = ta.to(torch.device("cuda", torch.cuda.current_device()))
+    tb = tb.to(ta.device)
+    ta, tb = ta.to(torch.float64), tb.to(torch.float64)
+    if ta.numel() == 0 or tb.numel() == 0:
+        return ta.float().contiguous(), tb.float().contiguous()
+    piv = torch.minimum(ta.min(0).values, tb.min(0).values)
+    return (ta - piv).float().contiguous(), (tb - piv).float().contiguous()
+
+
 def _batched_ptr(b, n, device):
     return torch.arange(0, (b + 1) * n, n, dtype=torch.int32, device=device)
 
@@ -85,8 +107,7 @@ def transform_point_cloud(x1, R, t):
 def compute_c2c(source_pc, target_pc):
     """Cloud-to-cloud 1-NN distances, [n,1] (src/functions.py:127-144).  numpy in -> numpy float64 out."""
     as_numpy = not torch.is_tensor(source_pc)
-    s = _dev_f32(source_pc)
-    t = _dev_f32(target_pc, s.device)
+    s, t = _dev_f32_local(source_pc, target_pc)
     _, d2 = ops.knn_grid(s, t, 1)
     d = torch.sqrt(d2.to(torch.float64))
     return d.cpu().numpy() if as_numpy else d

@@ -434,18 +434,27 @@ class DipsIndex:
                                    stream_ptr(ref64.device)), "f4l_dips_build")
 
 
-def dips_patches(index, query64, num_points=256, ranks=None, seed=0, want_lrf=False, out=None):
+def dips_patches(index, query64, num_points=256, ranks=None, seed=0, want_lrf=False, out=None, large=False):
     """K-h.  (n,3,num_points) f32 patches of data_loader.py:37-105 for the rows of query64 (n,3) f64.
     ranks: optional (n,num_points) i32 distance ranks to keep (the reference's `inds`).
-    Returns patches, count (n) i32 [, lrf (n,9) f64]."""
+    large: the variant that keeps up to 8192 neighbours per query on chip (default: 1408; a query beyond the limit gets a
+    zero patch, count tells).  Returns patches, count (n) i32 [, lrf (n,9) f64]."""
     n = int(query64.shape[0])
     patches = out if out is not None else _empty((n, 3, num_points), F32, query64)
     count = _empty((n,), I32, query64)
     lrf = _empty((n, 9), F64, query64) if want_lrf else None
-    check(lib().f4l_dips_patches(ptr(query64, F64), n, index.n_ref, index.radius, int(num_points),
-                                 ptr(ranks, I32, True), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(patches, F32),
-                                 ptr(lrf, F64, True), ptr(count, I32), ptr(index.ws), index.ws.numel(),
-                                 stream_ptr(query64.device)), "f4l_dips_patches")
+    if large:
+        if ranks is not None:
+            raise F4LError("dips_patches: the large variant has no ranked mode")
+        check(lib().f4l_dips_patches_large(ptr(query64, F64), n, index.n_ref, index.radius, int(num_points),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(patches, F32), ptr(lrf, F64, True),
+                                           ptr(count, I32), ptr(index.ws), index.ws.numel(), stream_ptr(query64.device)),
+              "f4l_dips_patches_large")
+    else:
+        check(lib().f4l_dips_patches(ptr(query64, F64), n, index.n_ref, index.radius, int(num_points),
+                                     ptr(ranks, I32, True), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(patches, F32),
+                                     ptr(lrf, F64, True), ptr(count, I32), ptr(index.ws), index.ws.numel(),
+                                     stream_ptr(query64.device)), "f4l_dips_patches")
     if want_lrf:
         return patches, count, lrf
     return patches, count

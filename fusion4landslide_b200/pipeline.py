@@ -422,7 +422,7 @@ class HostPipeline:
 
 
 def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_ptr, svl_idx, weights=None, filter_net=None, coeff=1.0,
-              refine_results=False, max_disp_magnitude=0.0, mutual=False, want_median=True):
+              refine_results=False, max_disp_magnitude=5.0, mutual=False, want_median=True):
     """The F2S3 hot path on one tile, device -> device (BASELINE config C2; src/f2s3.py:248-441 without the files):
     A1 median resolution (the descriptor radius of compute_features, f2s3.py:106) -> B1 exact descriptor 1-NN on the
     tensor cores -> rows [src | tgt[label]] in supervoxel order (CSR svl_ptr / svl_idx over source points) -> weights
@@ -458,11 +458,11 @@ def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_ptr, svl_idx, weights=None, filt
         seg = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=src.device), (ptr[1:] - ptr[:-1]).long())
         keep = keep | robust[seg]
     rows = X[keep].contiguous()
-    if max_disp_magnitude > 0 and rows.shape[0] > 0:
-        mask, mag = ops.magnitude_mask(rows, max_mag=max_disp_magnitude)
+    if rows.shape[0] > 0:                                        # f2s3.py:392-393: `<= max`, unconditional
+        mask, mag = ops.magnitude_mask(rows, max_mag=float(max_disp_magnitude))
         m = mask.bool()
         rows, mag = rows[m], mag[m]
     else:
-        mag = torch.linalg.norm(rows[:, 3:6] - rows[:, :3], dim=1)
+        mag = torch.zeros((0,), dtype=torch.float32, device=rows.device)
     out.update(rows=rows, mag=mag, keep=keep, scores=scores, R=R, t=t, robust=robust, residuals=res, corr=X)
     return out

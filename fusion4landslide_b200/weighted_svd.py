@@ -58,6 +58,8 @@ def refine_local_rigid_correspondences(corr_neigh_2, refine_type='SVD', weights=
         raise NotImplementedError("refine_type 'RANSAC' is Open3D ransac_registration and stays in the reference")
     corr = _dev_f32(corr_neigh_2)
     K = corr.shape[0]
+    if K == 0:                                                         # empty in, empty out (and the identity)
+        return corr.reshape(0, 6), torch.eye(4, device=corr.device)
     src, tgt = corr[:, :3].contiguous(), corr[:, 3:6].contiguous()
     ptr = torch.tensor([0, K], dtype=torch.int32, device=corr.device)
     w = None if weights is None else _dev_f32(weights, corr.device).reshape(-1)

@@ -397,14 +397,18 @@ F4L_API int f4l_peer_push(const void* src, const int32_t* d_rows, int32_t row_by
  *                  (ties by original index; a rank >= the neighbour count selects a zero row), i.e. the
  *                  reference's `ptall[inds]`.
  * lrf (n_query,9) f64 or NULL: rows xp, yp, zp of the frame (zeros when no frame was estimated);
- * count (n_query) i32: neighbours found.  More than 1408 neighbours is outside the supported range: the patch
- * is zero-filled and count reports the size. */
+ * count (n_query) i32: neighbours found.  f4l_dips_patches keeps up to 1408 neighbours of a query on chip (the
+ * reference's radius rule yields ~940); a query with more gets a zero patch and count reports the size -- the caller
+ * re-runs those queries through f4l_dips_patches_large (up to 8192 neighbours, one CTA per SM, no ranked mode). */
 F4L_API size_t f4l_dips_workspace_bytes(int32_t n_ref);
 F4L_API int f4l_dips_build(const double* ref64, int32_t n_ref, double radius, void* workspace,
                    size_t workspace_bytes, void* stream);
 F4L_API int f4l_dips_patches(const double* query64, int32_t n_query, int32_t n_ref, double radius,
                    int32_t num_points, const int32_t* ranks, uint64_t seed, float* patches, double* lrf,
                    int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+F4L_API int f4l_dips_patches_large(const double* query64, int32_t n_query, int32_t n_ref, double radius,
+                   int32_t num_points, uint64_t seed, float* patches, double* lrf, int32_t* count,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 8(f) rank 3 -- voxel subsampling.  Replaces Open3D PointCloud.voxel_down_sample as called at

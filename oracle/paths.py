@@ -137,7 +137,7 @@ def c2f_tile(src, tgt, labels_src, labels_tgt, feat_raw_src, feat_raw_tgt, agg_w
 
 
 def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_labels, weights, coeff=1.0, refine_results=False,
-              max_disp_magnitude=0.0, mutual=False, min_pts=10, max_rows=None, max_segments=None, labels_given=None):
+              max_disp_magnitude=5.0, mutual=False, min_pts=10, max_rows=None, max_segments=None, labels_given=None):
     """src/f2s3.py:248-441 with the filtering-network output (`weights`, one per source point) handed in.
     mutual: correspondences whose target's nearest source is another point get weight 0 (BASELINE config C2
     "mutual-NN"; the reference's F2S3 is one-directional).  max_rows / max_segments bound the CPU sample: the
@@ -181,8 +181,7 @@ def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_labels, weights, coeff=1.0, refi
     idx = np.concatenate(keep_rows) if keep_rows else np.zeros(0, np.int64)
     rows = corr[idx]
     mag = np.linalg.norm(rows[:, 3:6] - rows[:, :3], axis=1)
-    if max_disp_magnitude > 0:
-        sel = mag <= max_disp_magnitude                                              # :392-393
-        rows, mag, idx = rows[sel], mag[sel], idx[sel]
+    sel = mag <= max_disp_magnitude                                                  # :392-393 (unconditional)
+    rows, mag, idx = rows[sel], mag[sel], idx[sel]
     return dict(labels=labels, back=back, rows=rows, mag=mag, idx=idx, R=np.asarray(R), t=np.asarray(T),
                 robust=np.asarray(robust, bool), lists=lists, seconds=sec)

@@ -145,3 +145,38 @@ def test_preprocess_dataset_mirror(cuda, golden_dir):
     small = c <= 256                                                # all neighbours kept: identical multisets
     b = np.sort(np.abs(p).sum(1), axis=1)
     np.testing.assert_allclose(a[small], b[small], atol=1e-5)
+
+
+def test_dips_dense_neighbourhoods_use_the_large_variant(cuda):
+    """More than 1408 neighbours inside the feature radius (denser clouds / larger radii than the reference's rule of
+    thumb): the fast kernel reports the count and leaves the patch zero, f4l_dips_patches_large (8192 on chip) fills it,
+    and the Dataset mirror does that re-run by itself.  Every kept row must be one of the oracle's neighbours."""
+    from fusion4landslide_b200 import ops
+    from fusion4landslide_b200.data_loader import Preprocess_Dataset
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(12)
+    ref = np.vstack([rng.uniform(0, 10, (6000, 3)) * [1, 1, 0.05],
+                     rng.normal(5, 0.25, (4000, 3)) * [1, 1, 0.05] + [0, 0, 0.2]])        # a dense blob on a sparse sheet
+    data = np.vstack([[5.0, 5.0, 0.45], ref[:30]])
+    radius = 1.0
+    index = ops.DipsIndex(torch.from_numpy(ref).to(cuda), radius)
+    q = torch.from_numpy(data).to(cuda)
+    p, c = ops.dips_patches(index, q, seed=3)
+    pl, cl, lrf = ops.dips_patches(index, q, seed=3, want_lrf=True, large=True)
+    torch.cuda.synchronize()
+    c, cl = c.cpu().numpy(), cl.cpu().numpy()
+    np.testing.assert_array_equal(c, cl)
+    assert c[0] > 1408 and (c[1:] <= 8192).all()
+    assert not p[0].any() and pl[0].any()                                               # zero patch vs filled patch
+    small = torch.from_numpy(np.nonzero(c <= 1408)[0]).to(cuda)
+    assert torch.equal(p[small], pl[small])                                             # same kernel body, same seeds
+    tree = cKDTree(ref)
+    full, lRg, idx = odips.extract_all(data[0], tree, ref, radius)
+    assert idx.size == c[0]
+    np.testing.assert_allclose(lrf[0].cpu().numpy().reshape(3, 3), lRg.T, atol=1e-7)
+    rows = pl[0].cpu().numpy().T
+    dist = np.abs(rows[:, None, :] - full[None, :, :].astype(np.float32)).max(2)
+    assert (dist.min(1) <= TOL).all() and np.unique(dist.argmin(1)).size == 256
+    ds = Preprocess_Dataset(data, ref, 16, radius, device=cuda)
+    b0 = ds[0]
+    assert b0[0].any() and b0.shape == (16, 3, 256)
