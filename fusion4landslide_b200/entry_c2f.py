@@ -79,13 +79,71 @@ class _Cloud:
 
     def device_points(self, dev):
         """float64 (n,3) tensor on `dev` without a host round trip when the cloud already lives there."""
-        if self._dev is not None and self._dev.device == dev:
+        if self._dev is not None and self._dev.device.type == dev.type and dev.index in (None, self._dev.device.index):
             return self._dev.to(torch.float64)
         return torch.from_numpy(np.ascontiguousarray(self.points, dtype=np.float64)).to(dev)
 
 
+class _SegmentList:
+    """The reference's `idx_spt2pts_*` (a Python list with one index tensor per patch, base.py:1340-1344) as a read-only
+    sequence over the CSR tables the kernels use: element i is the view idx[ptr[i]:ptr[i+1]] (int64), created on access.
+    Building ~10^4 tensor objects per level and epoch up front cost more host time than the level's kernels."""
+    _next_key = [0]
+
+    def __init__(self, idx64, ptr_host):
+        self.idx, self.ptr = idx64, ptr_host
+        _SegmentList._next_key[0] += 1
+        self.key = ("seg", _SegmentList._next_key[0])
+
+    def __len__(self):
+        return len(self.ptr) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self.idx[int(self.ptr[i]):int(self.ptr[i + 1])]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class _IndexedList:
+    """`[base[a] for a in positions]` (spt_corres_src / spt_corres_tgt, base.py:3156-3157) without building it: the
+    positions stay on the device until an element is asked for."""
+
+    def __init__(self, base, positions):
+        self.base, self.pos = base, positions
+        self._host = None
+        _SegmentList._next_key[0] += 1
+        self.key = ("pairs", _SegmentList._next_key[0])
+
+    def __len__(self):
+        return int(self.pos.numel())
+
+    def _positions(self):
+        if self._host is None:
+            self._host = self.pos.cpu().numpy()
+        return self._host
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        return self.base[int(self._positions()[int(i)])]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 def _list_key(lst):
     """Identity of a list of index tensors that survives EasyDict's copy-on-assign of list values."""
+    key = getattr(lst, "key", None)
+    if key is not None:
+        return key
     if not len(lst):
         return (0, 0, 0)
     return (len(lst), int(lst[0].data_ptr()), int(lst[-1].data_ptr()))
@@ -165,10 +223,8 @@ class HotPathMixin:
         t = _LevelTables()
         t.lab_s, t.ptr_s, t.idx_s, t.pop_s = ops.labels_to_csr(di.idx_pts2spt_src.to(dev, I64).contiguous(), min_pts)
         t.lab_t, t.ptr_t, t.idx_t, t.pop_t = ops.labels_to_csr(di.idx_pts2spt_tgt.to(dev, I64).contiguous(), min_pts)
-        cs = (t.ptr_s[1:] - t.ptr_s[:-1]).tolist()
-        ct = (t.ptr_t[1:] - t.ptr_t[:-1]).tolist()
-        t.list_s = list(torch.split(t.idx_s.long(), cs)) if cs else []
-        t.list_t = list(torch.split(t.idx_t.long(), ct)) if ct else []
+        t.list_s = _SegmentList(t.idx_s.long(), t.ptr_s.cpu().numpy())
+        t.list_t = _SegmentList(t.idx_t.long(), t.ptr_t.cpu().numpy())
         di.idx_spt_src, di.idx_spt_tgt = t.lab_s, t.lab_t          # :1340-1344
         di.idx_spt2pts_src, di.idx_spt2pts_tgt = t.list_s, t.list_t
         levels, _ = self._b200_tables()
@@ -263,7 +319,8 @@ class HotPathMixin:
                 vox = p2v[idx.long()]                              # cluster_feature_net_self_attention.py:80-81
                 ok = vox >= 0
                 cnt = torch.zeros(ptr.numel() - 1, dtype=I64, device=dev)
-                seg = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=dev), (ptr[1:] - ptr[:-1]).long())
+                seg = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=dev), (ptr[1:] - ptr[:-1]).long(),
+                                              output_size=int(idx.numel()))
                 cnt.index_add_(0, seg[ok], torch.ones_like(seg[ok]))
                 vptr = torch.zeros(ptr.numel(), dtype=I64, device=dev)
                 vptr[1:] = torch.cumsum(cnt, 0)
@@ -323,9 +380,8 @@ class HotPathMixin:
             self.spt_length.append(int(parts[k][0].numel()))
         m = torch.cat([parts[k][0] for k in order])
         j = torch.cat([parts[k][1] for k in order])
-        ml, jl = m.tolist(), j.tolist()
-        src_list = [t.list_s[a] for a in ml]
-        tgt_list = [t.list_t[b] for b in jl]
+        src_list = _IndexedList(t.list_s, m)
+        tgt_list = _IndexedList(t.list_t, j)
         self.data_output.spt_corres_src = src_list                 # :3156-3157
         self.data_output.spt_corres_tgt = tgt_list
         _, pairs = self._b200_tables()
