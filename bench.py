@@ -581,7 +581,7 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 i/o, f64 accumulation", "data": "synthetic",
-            "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts,
+            "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts, "scene": a.scene,
                        "src_points_per_step": src_points, "dvf_points_per_step": dvf_points,
                        "parallelism": ("tile-sharded x%d; dense DVF rows copied into every GPU's field over NVLink by TMA copy kernels (one "
                                        "per tile, peer memory) on an exchange stream, pipelined with the next step's fits (fields "
@@ -1182,7 +1182,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 (numpy/scipy), f32 i/o", "data": "synthetic",
-            "config": {"workload": workload_name(a), "step": "bounded sample: %d patch pairs of one tile per step" % per_step},
+            "config": {"workload": workload_name(a), "tiles": a.tiles, "tile_pts": a.tile_pts, "scene": a.scene,
+                       "icp_threshold": cfg.icp_threshold, "assign_type": cfg.assign_type,
+                       "step": "bounded sample of the same workload: %d patch pairs of one tile per step, all host cores" % per_step},
             "cpu_baseline": r,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
