@@ -856,7 +856,9 @@ def bench_c2(a, dev, L, peaks):
         kern, launches = _profiled(step, L, dev)
         flop = 2.0 * n * n * D * 2 * n_tiles                       # both directions
         work = {"k_desc_nn_tc": ("tensor", flop)}
+        _, _, tie0 = ops.desc_nn(tiles[0]["fs"], tiles[0]["ft"], tie_eps=1e-6)
         r = {"value": rows / (ms * 1e-3), "src_points_per_sec": n * n_tiles / (ms * 1e-3), "ms_per_step": ms,
+             "ties": {"desc_nn_rows_within_1e-6": int(tie0.sum()), "of_rows": int(tie0.numel())},
              "steps": a.config_steps, "dvf_points_per_step": rows, "src_points_per_step": n * n_tiles,
              "gpu_launches_per_step": launches, "kernels": dict(list(kern.items())[:6]),
              "mutual_fraction": float(sum((o["scores"] > 0).float().mean().item() for o in outs) / n_tiles),
@@ -1050,6 +1052,13 @@ def bench_c2f(a, dev, L, peaks, fusion):
                 P = tt["src_pts"][torch.as_tensor(spt_s[l["m"][q]])].cpu().numpy().astype(np.float64)
                 To = of["T"][q].astype(np.float64)
                 worst = max(worst, float(np.abs((P @ Tg[q][:3, :3].T + Tg[q][:3, 3]) - (P @ To[:3, :3].T + To[:3, 3])).max()))
+        from fusion4landslide_b200 import ops as _ops
+        di_ = c.data_interim
+        _, _, desc_tie = _ops.desc_nn(di_.tile_pts_sub_feat_src, di_.tile_pts_sub_feat_tgt, tie_eps=1e-6)
+        knn_tie = _ops.knn_ties(di_.src_pts_sub.contiguous(), c.data_input_3d.src_pts.contiguous(), 1)
+        res["ties"] = {"desc_nn_rows_within_1e-6": int(desc_tie.sum()), "of_rows": int(desc_tie.numel()),
+                       "voxel_to_point_nn_ties_rel_1e-6": int(knn_tie.sum()), "of_voxels": int(knn_tie.numel()),
+                       "note": "flags exported by f4l_desc_nn_ex / f4l_knn_grid_ties on one tile: the rows exempt from index comparison"}
         res["parity"] = {"checked_against": "oracle/paths.py on the CPU-sampled pairs of one tile, in this run",
                          "levels_with_identical_pair_lists": pair_lists_equal, "pairs_checked": checked, "K_mismatch": bad_K,
                          "status_mismatch": bad_status, "fitted_pairs": fitted, "icp_path_flips": flips,

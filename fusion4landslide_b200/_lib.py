@@ -70,6 +70,7 @@ SIGNATURES = {
     "f4l_f2s3_prune_tail": (c_int, [P, P, P, P, c_i32, c_f32, P, P, P, P, P, P]),
     "f4l_knn_grid_workspace_bytes": (c_size, [c_i32, c_i32]),
     "f4l_knn_grid": (c_int, [P, c_i32, P, c_i32, c_i32, c_f32, c_f32, P, P, P, c_size, P]),
+    "f4l_knn_grid_ties": (c_int, [P, c_i32, P, c_i32, c_i32, c_f32, c_f32, c_f32, P, P, c_size, P]),
     "f4l_select_kth_workspace_bytes": (c_size, [c_i32]),
     "f4l_select_kth": (c_int, [P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P, c_size, P]),
     "f4l_median_resolution_workspace_bytes": (c_size, [c_i32, c_i32]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "f4l_fine_fit_tiles": (c_int, [P, P, P, c_i32, c_i32, P, P]),
     "f4l_desc_nn_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_int]),
     "f4l_desc_nn": (c_int, [P, c_i32, P, c_i32, c_i32, P, P, c_f32, c_int, c_int, P, P, P, P, P, c_size, P]),
+    "f4l_desc_nn_ex": (c_int, [P, c_i32, P, c_i32, c_i32, P, P, c_f32, c_int, c_int, P, P, P, P, P, P, c_f64, P, c_size, P]),
     "f4l_scatter_global_matches_workspace_bytes": (c_size, [c_i32]),
     "f4l_scatter_global_matches": (c_int, [P, P, P, c_i32, P, P, c_f32, P, c_i32, P, c_size, P]),
     "f4l_vote_tgt_patch": (c_int, [P, P, P, c_i32, P, c_i32, P, c_i32, P, P, P, P]),

@@ -482,7 +482,7 @@ k_desc_rerank(const float* __restrict__ a, const float* __restrict__ b, int N, i
               const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
               const int32_t* __restrict__ cand_cnt, const float* __restrict__ cand_thr,
               int32_t* __restrict__ out_idx, float* __restrict__ out_d2, int32_t* __restrict__ ovf_list,
-              DescScalars* __restrict__ scal) {
+              DescScalars* __restrict__ scal, uint8_t* __restrict__ tie, double tie_eps) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= N) return;
@@ -496,7 +496,7 @@ k_desc_rerank(const float* __restrict__ a, const float* __restrict__ b, int N, i
     float av[D / 32];
 #pragma unroll
     for (int u = 0; u < D / 32; ++u) av[u] = __ldg(a + (size_t)i * D + u * 32 + lane);
-    double best = INFINITY;
+    double best = INFINITY, second = INFINITY;
     int bj = -1;
     for (int s = 0; s < DT_HALVES * DT_CAND; ++s) {
         const int h = s / DT_CAND;
@@ -510,11 +510,15 @@ k_desc_rerank(const float* __restrict__ a, const float* __restrict__ b, int N, i
             acc += d * d;
         }
         acc = warp_sum(acc);
-        if (acc < best || (acc == best && j < bj)) { best = acc; bj = j; }
+        if (acc < best || (acc == best && j < bj)) { second = best; best = acc; bj = j; }
+        else if (acc < second) second = acc;
     }
     if (lane == 0) {
         out_idx[i] = bj;
         out_d2[i] = (float)best;
+        // every row within tie_eps of the minimum is a candidate (the margin is >= 2e-3 in score units), so the runner-up
+        // among the candidates decides the flag
+        if (tie) tie[i] = (bj >= 0 && second - best <= tie_eps) ? 1 : 0;
     }
 }
 
@@ -530,11 +534,12 @@ __global__ void __launch_bounds__(EX_THREADS)
 k_desc_exact(const float* __restrict__ a, const float* __restrict__ b, int N, int M,
              const int32_t* __restrict__ rows, const int* __restrict__ n_rows_dev,
              const float* __restrict__ a_xyz, const float* __restrict__ b_xyz, double max_mag2,
-             int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+             int32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint8_t* __restrict__ tie, double tie_eps) {
     __shared__ float qa[EX_ROWS][D];
     __shared__ float qx[EX_ROWS][3];
     __shared__ int qrow[EX_ROWS];
     __shared__ double red_d[EX_THREADS / 32][EX_ROWS];
+    __shared__ double red_s[EX_THREADS / 32][EX_ROWS];
     __shared__ int red_j[EX_THREADS / 32][EX_ROWS];
     const int n_rows = rows ? *n_rows_dev : N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -553,10 +558,10 @@ k_desc_exact(const float* __restrict__ a, const float* __restrict__ b, int N, in
             qa[q][k] = qrow[q] >= 0 ? __ldg(a + (size_t)qrow[q] * D + k) : 0.f;
         }
         __syncthreads();
-        double best[EX_ROWS];
+        double best[EX_ROWS], sec[EX_ROWS];                 // sec: runner-up distance (tie flag)
         int bj[EX_ROWS];
 #pragma unroll
-        for (int q = 0; q < EX_ROWS; ++q) { best[q] = INFINITY; bj[q] = -1; }
+        for (int q = 0; q < EX_ROWS; ++q) { best[q] = INFINITY; sec[q] = INFINITY; bj[q] = -1; }
         for (int j = tid; j < M; j += EX_THREADS) {
             float bv[D];
             const float4* bp = reinterpret_cast<const float4*>(b + (size_t)j * D);
@@ -580,33 +585,38 @@ k_desc_exact(const float* __restrict__ a, const float* __restrict__ b, int N, in
                     const double d = (double)qa[q][k] - (double)bv[k];
                     acc = fma(d, d, acc);
                 }
-                if (acc < best[q]) { best[q] = acc; bj[q] = j; }
+                if (acc < best[q]) { sec[q] = best[q]; best[q] = acc; bj[q] = j; }
+                else if (acc < sec[q]) sec[q] = acc;
             }
         }
         // block argmin per query (lower index on equal distance; -1 = nothing passed the gate)
 #pragma unroll
         for (int q = 0; q < EX_ROWS; ++q) {
-            double d = best[q];
+            double d = best[q], sd = sec[q];
             int j = bj[q] < 0 ? 0x7fffffff : bj[q];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double od = __shfl_xor_sync(F4L_FULL, d, o);
+                const double os = __shfl_xor_sync(F4L_FULL, sd, o);
                 const int oj = __shfl_xor_sync(F4L_FULL, j, o);
+                sd = fmin(fmin(sd, os), fmax(d, od));       // runner-up of the union
                 if (od < d || (od == d && oj < j)) { d = od; j = oj; }
             }
-            if (lane == 0) { red_d[wid][q] = d; red_j[wid][q] = j; }
+            if (lane == 0) { red_d[wid][q] = d; red_s[wid][q] = sd; red_j[wid][q] = j; }
         }
         __syncthreads();
         if (tid < EX_ROWS && qrow[tid] >= 0) {
-            double d = red_d[0][tid];
+            double d = red_d[0][tid], sd = red_s[0][tid];
             int j = red_j[0][tid];
             for (int w = 1; w < EX_THREADS / 32; ++w) {
                 const double od = red_d[w][tid];
                 const int oj = red_j[w][tid];
+                sd = fmin(fmin(sd, red_s[w][tid]), fmax(d, od));
                 if (od < d || (od == d && oj < j)) { d = od; j = oj; }
             }
             out_idx[qrow[tid]] = j == 0x7fffffff ? -1 : j;
             out_d2[qrow[tid]] = (float)d;
+            if (tie) tie[qrow[tid]] = (j != 0x7fffffff && sd - d <= tie_eps) ? 1 : 0;
         }
     }
 }
@@ -693,7 +703,8 @@ extern "C" size_t f4l_desc_nn_workspace_bytes(int32_t N, int32_t M, int32_t D, i
 
 template <int D>
 static int desc_one_direction(const float* a, int N, const float* b, int M, const float* a_xyz, const float* b_xyz,
-                              float max_mag, int algo, int32_t* idx, float* d2, void* ws_base, cudaStream_t st) {
+                              float max_mag, int algo, int32_t* idx, float* d2, void* ws_base, cudaStream_t st,
+                              uint8_t* tie, double tie_eps) {
     const bool gate = a_xyz && b_xyz && max_mag > 0.f;
     const double mm2 = (double)max_mag * (double)max_mag;
     bool use_tc = algo == F4L_DESC_TENSOR;
@@ -706,7 +717,7 @@ static int desc_one_direction(const float* a, int N, const float* b, int M, cons
         const int grid = f4l_div_up(N, EX_ROWS) < 148 * 8 ? f4l_div_up(N, EX_ROWS) : 148 * 8;
         f4l_mark("k_desc_exact", st);
         k_desc_exact<D><<<grid, EX_THREADS, 0, st>>>(a, b, N, M, nullptr, nullptr, gate ? a_xyz : nullptr,
-                                                      gate ? b_xyz : nullptr, mm2, idx, d2);
+                                                      gate ? b_xyz : nullptr, mm2, idx, d2, tie, tie_eps);
         return F4L_OK;
     }
     DescWs w = desc_layout(ws_base, N, M, D);
@@ -753,15 +764,30 @@ static int desc_one_direction(const float* a, int N, const float* b, int M, cons
 #undef F4L_LAUNCH_TC
     f4l_mark("k_desc_rerank", st);
     k_desc_rerank<D><<<f4l_div_up(N, 8), 256, 0, st>>>(a, b, N, M, w.cand_idx, w.cand_val, w.cand_cnt, w.cand_thr, idx, d2,
-                                                      w.ovf_list, w.scal);
+                                                      w.ovf_list, w.scal, tie, tie_eps);
     f4l_mark("k_desc_exact", st);
-    k_desc_exact<D><<<148, EX_THREADS, 0, st>>>(a, b, N, M, w.ovf_list, &w.scal->n_overflow, nullptr, nullptr, -1.0, idx, d2);
+    k_desc_exact<D><<<148, EX_THREADS, 0, st>>>(a, b, N, M, w.ovf_list, &w.scal->n_overflow, nullptr, nullptr, -1.0, idx, d2,
+                                                tie, tie_eps);
     return F4L_OK;
 }
+
+extern "C" int f4l_desc_nn_ex(const float* a, int32_t N, const float* b, int32_t M, int32_t D, const float* a_xyz,
+                              const float* b_xyz, float max_mag, int both_dirs, int algo, int32_t* row_idx, float* row_d2,
+                              int32_t* col_idx, float* col_d2, uint8_t* row_tie, uint8_t* col_tie, double tie_eps,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 extern "C" int f4l_desc_nn(const float* a, int32_t N, const float* b, int32_t M, int32_t D, const float* a_xyz,
                            const float* b_xyz, float max_mag, int both_dirs, int algo, int32_t* row_idx, float* row_d2,
                            int32_t* col_idx, float* col_d2, void* workspace, size_t workspace_bytes, void* stream) {
+    return f4l_desc_nn_ex(a, N, b, M, D, a_xyz, b_xyz, max_mag, both_dirs, algo, row_idx, row_d2, col_idx, col_d2, nullptr,
+                          nullptr, 0.0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int f4l_desc_nn_ex(const float* a, int32_t N, const float* b, int32_t M, int32_t D, const float* a_xyz,
+                              const float* b_xyz, float max_mag, int both_dirs, int algo, int32_t* row_idx, float* row_d2,
+                              int32_t* col_idx, float* col_d2, uint8_t* row_tie, uint8_t* col_tie, double tie_eps,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    F4L_REQUIRE(tie_eps >= 0.0, "tie_eps < 0");
     F4L_REQUIRE(D == 32 || D == 64, "D must be 32 or 64");
     F4L_REQUIRE(N >= 0 && M >= 0, "negative size");
     F4L_REQUIRE(algo >= 0 && algo <= 2, "unknown algo");
@@ -781,18 +807,20 @@ extern "C" int f4l_desc_nn(const float* a, int32_t N, const float* b, int32_t M,
     if (M == 0) {
         cudaMemsetAsync(row_idx, 0xff, (size_t)N * 4, st);
         cudaMemsetAsync(row_d2, 0x7f, (size_t)N * 4, st);   // NaN pattern-free: 0x7f7f7f7f = 3.39e38
+        if (row_tie) cudaMemsetAsync(row_tie, 0, (size_t)N, st);
     } else if (N > 0) {
-        rc = D == 32 ? desc_one_direction<32>(a, N, b, M, a_xyz, b_xyz, max_mag, algo, row_idx, row_d2, ws, st)
-                     : desc_one_direction<64>(a, N, b, M, a_xyz, b_xyz, max_mag, algo, row_idx, row_d2, ws, st);
+        rc = D == 32 ? desc_one_direction<32>(a, N, b, M, a_xyz, b_xyz, max_mag, algo, row_idx, row_d2, ws, st, row_tie, tie_eps)
+                     : desc_one_direction<64>(a, N, b, M, a_xyz, b_xyz, max_mag, algo, row_idx, row_d2, ws, st, row_tie, tie_eps);
         if (rc != F4L_OK) return rc;
     }
     if (both_dirs && M > 0) {
         if (N == 0) {
             cudaMemsetAsync(col_idx, 0xff, (size_t)M * 4, st);
             cudaMemsetAsync(col_d2, 0x7f, (size_t)M * 4, st);
+            if (col_tie) cudaMemsetAsync(col_tie, 0, (size_t)M, st);
         } else {
-            rc = D == 32 ? desc_one_direction<32>(b, M, a, N, b_xyz, a_xyz, max_mag, algo, col_idx, col_d2, ws, st)
-                         : desc_one_direction<64>(b, M, a, N, b_xyz, a_xyz, max_mag, algo, col_idx, col_d2, ws, st);
+            rc = D == 32 ? desc_one_direction<32>(b, M, a, N, b_xyz, a_xyz, max_mag, algo, col_idx, col_d2, ws, st, col_tie, tie_eps)
+                         : desc_one_direction<64>(b, M, a, N, b_xyz, a_xyz, max_mag, algo, col_idx, col_d2, ws, st, col_tie, tie_eps);
             if (rc != F4L_OK) return rc;
         }
     }

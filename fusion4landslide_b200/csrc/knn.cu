@@ -150,6 +150,35 @@ k_grid_search(const float4* __restrict__ queries_sorted, int n, const float4* __
     for (int a = K; a < k; ++a) { out_idx[(size_t)qi * k + a] = -1; out_d2[(size_t)qi * k + a] = INFINITY; }
 }
 
+// Tie flags: tie[i] = 1 when two adjacent distances among the first k + 1 neighbours of query i
+// differ by no more than eps_rel * (the larger one) + 1e-12 -- the rows whose index order another exact search (the
+// reference's kd-trees) may legitimately report differently.  Same search with one more slot.
+template <int K1>
+__global__ void __launch_bounds__(128)
+k_grid_ties(const float4* __restrict__ queries_sorted, int n, const float4* __restrict__ sorted,
+            const int* __restrict__ cell_start, const GridParams* __restrict__ gp, int k, float max_r2, float eps_rel,
+            uint8_t* __restrict__ tie) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const GridParams g = *gp;
+    const float4 q = __ldg(queries_sorted + t);
+    const int qi = __float_as_int(q.w);
+    int cx, cy, cz;
+    cell_of(g, q.x, q.y, q.z, cx, cy, cz);
+    TopK<K1> tk;
+    tk.init();
+    grid_ring_search(sorted, cell_start, g, q.x, q.y, q.z, cx, cy, cz, k + 1 < K1 ? k + 1 : K1, INFINITY, tk);
+    bool flag = false;
+#pragma unroll
+    for (int a = 0; a + 1 < K1; ++a) {
+        if (a < k) {
+            const float d0 = tk.d(a), d1 = tk.d(a + 1);
+            if (d0 < max_r2 && d1 < INFINITY && d1 - d0 <= eps_rel * d1 + 1e-12f) flag = true;
+        }
+    }
+    tie[qi] = flag ? 1 : 0;
+}
+
 __global__ void k_fill_none(int n, int k, int* idx, float* d2) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n * k) { idx[t] = -1; d2[t] = INFINITY; }
@@ -214,7 +243,7 @@ static int bin_points(const float* p, int n, const KnnWs& w, int mc, float4* sor
 
 static int knn_grid_impl(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
                          float cell, int32_t* idx, float* d2, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+                         void* stream, uint8_t* tie = nullptr, float eps_rel = 0.f) {
     cudaStream_t st = (cudaStream_t)stream;
     KnnWs w = knn_layout(workspace, N, M);
     if (workspace_bytes < w.total) {
@@ -250,6 +279,13 @@ static int knn_grid_impl(const float* q, int32_t N, const float* r, int32_t M, i
     }
     const float max_r2 = max_radius > 0.f ? max_radius * max_radius : INFINITY;
     const int blocks = f4l_div_up(N, 128);
+    if (tie) {
+        f4l_mark("k_grid_ties", st);
+        if (k == 1) k_grid_ties<2><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, eps_rel, tie);
+        else if (k <= 3) k_grid_ties<4><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, eps_rel, tie);
+        else k_grid_ties<8><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, eps_rel, tie);
+        return f4l_finish("f4l_knn_grid_ties", stream);
+    }
     f4l_mark("k_grid_search", st);
 #define KNN_LAUNCH(KK) k_grid_search<KK><<<blocks, 128, 0, st>>>(qs, N, w.sorted_r, ref_start, w.gp, k, max_r2, idx, d2)
     if (k == 1) KNN_LAUNCH(1);
@@ -275,6 +311,22 @@ extern "C" int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M
     }
     F4L_REQUIRE(r && workspace, "null pointer");
     return knn_grid_impl(q, N, r, M, k, max_radius, cell, idx, d2, workspace, workspace_bytes, stream);
+}
+
+extern "C" int f4l_knn_grid_ties(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
+                                 float cell, float eps_rel, uint8_t* tie, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    F4L_REQUIRE(N >= 0 && M >= 0, "negative size");
+    F4L_REQUIRE(k >= 1 && k <= 7, "k must be in [1,7]");
+    F4L_REQUIRE(eps_rel >= 0.f, "eps_rel < 0");
+    if (N == 0) return F4L_OK;
+    F4L_REQUIRE(q && tie, "null pointer");
+    if (M == 0) {
+        cudaMemsetAsync(tie, 0, (size_t)N, (cudaStream_t)stream);
+        return F4L_OK;
+    }
+    F4L_REQUIRE(r && workspace, "null pointer");
+    return knn_grid_impl(q, N, r, M, k, max_radius, cell, nullptr, nullptr, workspace, workspace_bytes, stream, tie, eps_rel);
 }
 
 // ---- radix select (k-th smallest) -------------------------------------------------------------

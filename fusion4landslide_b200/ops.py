@@ -105,6 +105,17 @@ def knn_grid(q, r, k, max_radius=0.0, cell=0.0):
     return idx, d2
 
 
+def knn_ties(q, r, k, eps_rel=1e-6, max_radius=0.0, cell=0.0):
+    """Tie flags (N) u8 of knn_grid(q, r, k): rows whose neighbour order is decided by a distance difference below
+    eps_rel (relative) -- exempt from index comparison with another exact search (f4l_knn_grid_ties)."""
+    N, M = q.shape[0], r.shape[0]
+    tie = _empty((N,), torch.uint8, q)
+    ws = _workspace(lib().f4l_knn_grid_workspace_bytes(N, M), q.device)
+    check(lib().f4l_knn_grid_ties(ptr(q, F32), N, ptr(r, F32), M, int(k), float(max_radius), float(cell), float(eps_rel),
+                                  ptr(tie), ptr(ws), ws.numel(), stream_ptr(q.device)), "f4l_knn_grid_ties")
+    return tie
+
+
 def patch_icp(src, tgt, s_start, t_start, s_count=None, t_count=None, src_idx=None, tgt_idx=None,
               T0=None, max_corr_dist=0.1, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6, seg_skip=None,
               want_corr=False):
@@ -168,23 +179,29 @@ def select_kth(x, k, k2=-1, stride=1, offset=0):
 _DESC_ALGO = {"auto": 0, "tensor": 1, "exact": 2}
 
 
-def desc_nn(a, b, a_xyz=None, b_xyz=None, max_mag=0.0, both_dirs=False, algo="auto"):
+def desc_nn(a, b, a_xyz=None, b_xyz=None, max_mag=0.0, both_dirs=False, algo="auto", tie_eps=None):
     """K-b.  Exact descriptor-space nearest neighbour of every row of a (N,D) among b (M,D), D in {32,64}.
-    Returns row_idx (N) i32, row_d2 (N) f32 [, col_idx (M), col_d2 (M) when both_dirs]."""
+    Returns row_idx (N) i32, row_d2 (N) f32 [, col_idx (M), col_d2 (M) when both_dirs]
+    [, row_tie (N) u8 [, col_tie (M) u8] when tie_eps is given: another row within tie_eps of the minimum]."""
     N, D = a.shape
     M = b.shape[0]
     row_idx = _empty((N,), I32, a)
     row_d2 = _empty((N,), F32, a)
     col_idx = _empty((M,), I32, a) if both_dirs else None
     col_d2 = _empty((M,), F32, a) if both_dirs else None
+    ties = tie_eps is not None
+    row_tie = _empty((N,), torch.uint8, a) if ties else None
+    col_tie = _empty((M,), torch.uint8, a) if (ties and both_dirs) else None
     ws = _workspace(lib().f4l_desc_nn_workspace_bytes(N, M, D, int(both_dirs)), a.device)
-    check(lib().f4l_desc_nn(ptr(a, F32), N, ptr(b, F32), M, D, ptr(a_xyz, F32, True), ptr(b_xyz, F32, True),
-                            float(max_mag), int(both_dirs), _DESC_ALGO[algo], ptr(row_idx), ptr(row_d2),
-                            ptr(col_idx, I32, True), ptr(col_d2, F32, True), ptr(ws), ws.numel(),
-                            stream_ptr(a.device)), "f4l_desc_nn")
-    if both_dirs:
-        return row_idx, row_d2, col_idx, col_d2
-    return row_idx, row_d2
+    check(lib().f4l_desc_nn_ex(ptr(a, F32), N, ptr(b, F32), M, D, ptr(a_xyz, F32, True), ptr(b_xyz, F32, True),
+                               float(max_mag), int(both_dirs), _DESC_ALGO[algo], ptr(row_idx), ptr(row_d2),
+                               ptr(col_idx, I32, True), ptr(col_d2, F32, True), ptr(row_tie, torch.uint8, True),
+                               ptr(col_tie, torch.uint8, True), float(tie_eps or 0.0), ptr(ws), ws.numel(),
+                               stream_ptr(a.device)), "f4l_desc_nn")
+    out = (row_idx, row_d2) + ((col_idx, col_d2) if both_dirs else ())
+    if ties:
+        out = out + ((row_tie, col_tie) if both_dirs else (row_tie,))
+    return out
 
 
 def scatter_global_matches(labels, src_sub, tgt_sub, voxel2pts_src, voxel2pts_tgt, max_magnitude, n_raw):

@@ -125,6 +125,11 @@ F4L_API size_t f4l_knn_grid_workspace_bytes(int32_t N, int32_t M);
 F4L_API int f4l_knn_grid(const float* q, int32_t N, const float* r, int32_t M, int32_t k,
                  float max_radius, float cell, int32_t* idx, float* d2, void* workspace,
                  size_t workspace_bytes, void* stream);
+/* Tie flags of the same query ("indices identical except rows flagged as distance ties"): tie (N)
+ * uint8 = 1 when two adjacent squared distances among the first k + 1 neighbours differ by <= eps_rel * (the larger one)
+ * + 1e-12, i.e. where another exact search may order the indices differently.  k in [1,7]; same workspace size. */
+F4L_API int f4l_knn_grid_ties(const float* q, int32_t N, const float* r, int32_t M, int32_t k, float max_radius,
+                      float cell, float eps_rel, uint8_t* tie, void* workspace, size_t workspace_bytes, void* stream);
 
 /* k-th smallest (0-based) of x (n) f32, written to out[0] (device).  With k2 >= 0 also the k2-th
  * to out[1] (np.median of an even count averages the two middle elements: base.py:2732). */
@@ -279,6 +284,14 @@ F4L_API int f4l_desc_nn(const float* a, int32_t N, const float* b, int32_t M, in
                 const float* a_xyz, const float* b_xyz, float max_mag, int both_dirs, int algo,
                 int32_t* row_idx, float* row_d2, int32_t* col_idx, float* col_d2,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* The same search with tie flags (eps_desc = 1e-6 absolute on the squared distance): row_tie (N) /
+ * col_tie (M) uint8 or NULL = 1 when another reference row lies within tie_eps of the reported minimum, i.e. where
+ * torch.min / an approximate index may report a different index.  f4l_desc_nn == this with NULL flags. */
+F4L_API int f4l_desc_nn_ex(const float* a, int32_t N, const float* b, int32_t M, int32_t D,
+                   const float* a_xyz, const float* b_xyz, float max_mag, int both_dirs, int algo,
+                   int32_t* row_idx, float* row_d2, int32_t* col_idx, float* col_d2,
+                   uint8_t* row_tie, uint8_t* col_tie, double tie_eps,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* (b)+(c) scatter of global 3D matches: base.py:2872-2889.  labels (n_sub) int32 from f4l_desc_nn,
  * src_sub/tgt_sub (n_sub.,3) voxel points, voxel2pts_* int64 maps, corres (n_raw,2) int64 out:

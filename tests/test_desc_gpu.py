@@ -179,3 +179,27 @@ def test_scatter_global_matches(cuda):
     out = ops.scatter_global_matches(lab, T(src_sub), T(tgt_sub), T(v2p_s), T(v2p_t), 8.0, n_raw)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out.cpu().numpy(), C)
+
+
+def test_desc_nn_tie_flags(cuda):
+    """f4l_desc_nn_ex: rows with another reference row within eps of the minimum (duplicates, a zero query) are flagged on
+    both kernel paths; generic rows are not.  The BASELINE gate: labels equal the golden except flagged rows."""
+    from fusion4landslide_b200 import ops
+    rng = np.random.default_rng(8)
+    D, N, M = 32, 2500, 4000
+    b = _unit(rng, M, D)
+    b[3000] = b[11]                                  # duplicate reference rows
+    a = _unit(rng, N, D)
+    a[0] = b[11] + 1e-3 * rng.standard_normal(D).astype(np.float32)
+    a[1] = 0.0                                       # equidistant from every unit row up to rounding
+    for algo in ("tensor", "exact"):
+        idx, d2, tie = ops.desc_nn(torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda), algo=algo, tie_eps=1e-6)
+        torch.cuda.synchronize()
+        t = tie.cpu().numpy().astype(bool)
+        assert t[0] and idx[0].item() == 11          # the lower index of the duplicates, flagged
+        assert t[1]
+        oi, od, od2 = odesc.desc_nn(a, b, return_second=True)
+        o_tie = (od2 - od) <= 1e-6
+        assert (t | ~o_tie).all() and (t & ~o_tie).sum() <= 3
+        assert ((idx.cpu().numpy() == oi) | t).all()
+        assert t.mean() < 0.01

@@ -106,3 +106,28 @@ def test_select_kth_and_median_resolution(cuda, golden_dir):
     z = np.load(os.path.join(golden_dir, "knn_sklearn.npz"))
     med = ops.median_resolution(torch.from_numpy(z["a"]).to(cuda), torch.from_numpy(z["b"]).to(cuda)).item()
     assert abs(med - z["median_resolution"][0]) < 1e-6 * z["median_resolution"][0] + 1e-8
+
+
+def test_knn_tie_flags(cuda):
+    """f4l_knn_grid_ties: the rows another exact search may order differently.  Against the oracle's tie rule on the same
+    data: every oracle tie is flagged (the kernel's f32 gaps can flag a few more near the epsilon), exact duplicates and
+    lattice points are flagged, well separated points are not."""
+    from fusion4landslide_b200 import ops
+    from oracle import knn as oknn
+    rng = np.random.default_rng(5)
+    r = rng.uniform(0, 20, (6000, 3)).astype(np.float32)
+    r[100] = r[7]                                               # an exact duplicate: every query near it ties
+    lattice = (np.stack(np.meshgrid(np.arange(12), np.arange(12), [0.0]), -1).reshape(-1, 3) * 0.5 + 30).astype(np.float32)
+    r = np.vstack([r, lattice])
+    q = np.vstack([r[:3000], lattice[:50] + np.float32(0.25)])   # lattice cell centres: four equidistant neighbours
+    R, Qt = torch.from_numpy(r).to(cuda), torch.from_numpy(q).to(cuda)
+    for k in (1, 2):
+        tie = ops.knn_ties(Qt, R, k).cpu().numpy().astype(bool)
+        o = oknn.tie_rows(q, r, k)
+        assert (tie | ~o).all(), int((o & ~tie).sum())          # no oracle tie missed
+        assert tie[-50:].all() and tie[7] and tie[100]
+        assert (tie & ~o).sum() <= 5 and 0 < tie.mean() < 0.1
+        idx, _ = ops.knn_grid(Qt, R, k)
+        oi, _ = oknn.knn_exact(q, r, k)
+        same = (idx.cpu().numpy() == oi).all(1)
+        assert (same | tie).all()                               # the BASELINE gate: indices identical except flagged rows
