@@ -185,3 +185,34 @@ def f2s3_tile(src, tgt, feat_src, feat_tgt, svl_labels, weights, coeff=1.0, refi
     rows, mag, idx = rows[sel], mag[sel], idx[sel]
     return dict(labels=labels, back=back, rows=rows, mag=mag, idx=idx, R=np.asarray(R), t=np.asarray(T),
                 robust=np.asarray(robust, bool), lists=lists, seconds=sec)
+
+
+def rgb_local_rigid_refinement(corres_3d_refine, idx_valid_src_refine, segment_patches, icp_thres=0.1, icp_max_iter=30):
+    """`Image_DVFs.local_rigid_refinement` (src/rgb_guided.py:981-1062), patch by patch like the reference.
+    Returns (mask_valid_local rows, rows [src | T_icp src] stacked, per-patch dict lists)."""
+    from . import icp as oicp
+    corr_all = np.asarray(corres_3d_refine, np.float32)
+    ids = np.asarray(idx_valid_src_refine)
+    row_of = {int(v): k for k, v in enumerate(ids)}
+    keep_rows, out_rows, per = [], [], []
+    for patch in segment_patches:
+        idx = np.array([row_of[int(v)] for v in np.asarray(patch).reshape(-1) if int(v) in row_of], np.int64)    # :990-991
+        c = corr_all[idx]
+        if c.shape[0] == 0:
+            per.append(None)
+            continue
+        R, t = orig.weighted_procrustes(c[:, :3], c[:, 3:6], None, 0.0, eps=1e-6)        # rgb_guided.py:101-109
+        res = np.linalg.norm(c[:, :3].astype(np.float64) @ R.T + t - c[:, 3:6], axis=1)
+        mask = res < 2.5 * orig.lower_median(res)                                         # :115 torch.median
+        keep_rows.append(idx[mask])                                                       # :1001
+        T0 = np.eye(4)
+        T0[:3, :3], T0[:3, 3] = R, t
+        fit0 = oicp.icp_point_to_point(c[:, :3], c[:, 3:6], T0, icp_thres, 0)["fitness"]  # correspondences at the start
+        r = oicp.icp_point_to_point(c[:, :3], c[:, 3:6], T0, icp_thres, icp_max_iter)     # :1015-1019
+        T = r["transformation"].astype(np.float32)                                        # :1024
+        moved = (T[:3, :3] @ c[:, :3].T).T + T[:3, 3]                                     # :1027-1030 (f32)
+        out_rows.append(np.hstack([c[:, :3], moved]).astype(np.float32))
+        per.append(dict(T0=T0, T=T, iters=r["iters"], fitness=r["fitness"], fitness0=fit0, n=c.shape[0], kept=int(mask.sum())))
+    keep = np.concatenate(keep_rows) if keep_rows else np.zeros(0, np.int64)
+    rows = np.vstack(out_rows) if out_rows else np.zeros((0, 6), np.float32)
+    return keep, rows, per
