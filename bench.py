@@ -552,6 +552,17 @@ def run_b200(a):
                                 "smsp__inst_executed.sum"))
         if ctx:
             roofline["ncu_context"] = ctx          # from the committed capture, not measured in this run
+            inst = ctx.get("smsp__inst_executed.sum")
+            if inst and top.startswith("k_patch_fit_warp"):
+                # the roof this kernel actually sits under: warp-instruction issue slots (4 schedulers per SM, one
+                # instruction per cycle each).  Instructions per launch from the committed ncu capture of the same kernel
+                # on the same tile shape; duration measured in this run.
+                sm_hz = 1.965e9
+                peak = 148 * 4 * sm_hz
+                ach = inst * (q["pairs_all"] / q["pairs"] if top.endswith("_tiles") else 1.0) / (kernel_table[top]["ms_avg"] * 1e-3)
+                roofline["issue"] = {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s",
+                                     "frac": ach / peak, "warp_instructions_per_launch": inst,
+                                     "note": "148 SMs x 4 schedulers x 1.965 GHz; instruction count from " + ctx.get("source", "ncu")}
         # also report the two kernels the north star names (kNN search, Kabsch/ICP reduction)
         for name in ("k_a1_search", "k_a1_scatter", "k_a1_count", "k_a1_bbox", "k_patch_fit_warp", "k_patch_fit_warp_tiles", "k_patch_fit",
                      "k_apply_assign"):
