@@ -108,7 +108,7 @@ SIGNATURES = {
     "f4l_fine_matching": (c_int, [ctypes.POINTER(FineParams), ctypes.POINTER(FineBuffers), P, c_size, P]),
     "f4l_segment_scale_maxabs": (c_int, [P, c_i32, P, c_i32, c_i32, P, P]),
     "f4l_segment_norm2_relu": (c_int, [P, P, c_i32, c_i32, c_f32, P, P, P]),
-    "f4l_segment_attention_pool": (c_int, [P, P, P, P, c_i32, c_i32, c_f32, P, P]),
+    "f4l_segment_attention_pool": (c_int, [P, P, P, P, c_i32, c_i32, c_f32, c_i32, P, P]),
     "f4l_segment_mean": (c_int, [P, P, c_i32, c_i32, P, P]),
     "f4l_host_expand_sparse": (ctypes.c_longlong, [P, P, c_i32, P, c_i32]),
 }

@@ -528,12 +528,16 @@ def segment_norm2_relu(y, seg_ptr, eps=1e-3, residual=None):
     return out
 
 
-def segment_attention_pool(Qm, Km, Vm, seg_ptr, scale):
-    """(P,hidden): mean over the rows of each segment of softmax(Q K^T * scale) V."""
+def segment_attention_pool(Qm, Km, Vm, seg_ptr, scale, max_seg_rows=None):
+    """(P,hidden): mean over the rows of each segment of softmax(Q K^T * scale) V.  max_seg_rows: the longest segment
+    when the caller knows it (else read back here: one small device->host copy); 0 forces the CUDA-core kernel."""
     Pn = seg_ptr.numel() - 1
     out = _empty((Pn, Qm.shape[1]), F32, Qm)
+    if max_seg_rows is None:
+        max_seg_rows = int((seg_ptr[1:] - seg_ptr[:-1]).max().item()) if Pn > 0 else 0
     check(lib().f4l_segment_attention_pool(ptr(Qm, F32), ptr(Km, F32), ptr(Vm, F32), ptr(seg_ptr, I32), Pn, Qm.shape[1],
-                                           float(scale), ptr(out), stream_ptr(Qm.device)), "f4l_segment_attention_pool")
+                                           float(scale), int(max_seg_rows), ptr(out), stream_ptr(Qm.device)),
+          "f4l_segment_attention_pool")
     return out
 
 

@@ -453,8 +453,12 @@ F4L_API int f4l_segment_scale_maxabs(const void* x, int32_t x_is_f64, const int3
                              float* out, void* stream);
 F4L_API int f4l_segment_norm2_relu(const float* y, const int32_t* seg_ptr, int32_t Q, int32_t C, float eps,
                            const float* residual, float* out, void* stream);
+/* max_seg_rows: the longest segment (host value).  With it (and <= 2392 rows) the tensor-core kernel runs: mean_i sum_j
+ * a_ij V_j = sum_j (mean_i a_ij) V_j, so only the scores Q K^T are formed -- mma.sync TF32 with the 3xTF32 split (fp32-level
+ * accuracy), scores of 64 queries at a time in shared memory; <= 0 (unknown) or longer segments: the flash-style
+ * CUDA-core kernel (Q K^T and the product with V per query). */
 F4L_API int f4l_segment_attention_pool(const float* Qm, const float* Km, const float* Vm, const int32_t* seg_ptr,
-                               int32_t P, int32_t hidden, float scale, float* out, void* stream);
+                               int32_t P, int32_t hidden, float scale, int32_t max_seg_rows, float* out, void* stream);
 F4L_API int f4l_segment_mean(const float* x, const int32_t* seg_ptr, int32_t P, int32_t C, float* out, void* stream);
 
 #ifdef __cplusplus
