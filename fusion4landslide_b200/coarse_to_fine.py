@@ -176,18 +176,23 @@ def coarse_matching_3d(spt_coord_src, spt_feat_src, spt_coord_tgt, spt_feat_tgt,
 
 def coarse_matching_2d(corres_3d_from_2d_idx, sp_idx, sp_ptr, idx_pts2spt_tgt, idx_spt_tgt):
     """2D-vote coarse matching: for every source patch the target patch most of its 2D-lifted matches fall
-    into.  Returns (src patch positions, tgt patch positions in idx_spt_tgt, tie flags)."""
+    into.  Returns (src patch positions, tgt patch positions in idx_spt_tgt, tie flags).
+    idx_spt_tgt is ascending (prepare_pts2spt_dict): the winning label is located in it by binary search on the device,
+    so no label table has to be sized from a device-side maximum (one host synchronisation: the size of the result)."""
     dev = corres_3d_from_2d_idx.device
     lab_t = idx_pts2spt_tgt.to(dev, I32).contiguous()
-    spt_t = idx_spt_tgt.to(dev).long()
-    n_lab = int(max(int(spt_t.max().item()) if spt_t.numel() else -1, int(lab_t.max().item()) if lab_t.numel() else -1)) + 1
-    l2l = torch.full((max(n_lab, 1),), -1, dtype=I32, device=dev)
-    l2l[spt_t] = torch.arange(spt_t.numel(), device=dev, dtype=I32)
-    best, cnt, flag = ops.vote_tgt_patch(corres_3d_from_2d_idx.contiguous(), sp_idx, sp_ptr, lab_t, l2l)
+    spt_t = idx_spt_tgt.to(dev).long().contiguous()
+    best, cnt, flag = ops.vote_tgt_patch(corres_3d_from_2d_idx.contiguous(), sp_idx, sp_ptr, lab_t, None)   # raw labels
+    if spt_t.numel() == 0:
+        e = torch.zeros(0, dtype=torch.int64, device=dev)
+        return e, e, torch.zeros(0, dtype=torch.bool, device=dev)
+    lab = best.long()
+    pos = torch.searchsorted(spt_t, lab.clamp(min=0)).clamp(max=spt_t.numel() - 1)
+    local = torch.where((lab >= 0) & (spt_t[pos] == lab), pos, torch.full_like(pos, -1))        # base.py:3062-3064
+    m = torch.nonzero(local >= 0).reshape(-1)
     if bool((flag == 255).any().item()):
         raise RuntimeError("coarse_matching_2d: a source patch votes for more than 512 distinct target patches")
-    m = torch.nonzero(best >= 0).reshape(-1)
-    return m, best[m].long(), flag[m] == 1
+    return m, local[m], flag[m] == 1
 
 
 def fine_matching_with_different_types(src_pts, tgt_pts, label_src, label_tgt, corres_3d, corres_2d=None, pairs=None,
