@@ -128,3 +128,92 @@ def test_desc_nn_c2_tile_properties(cuda, D):
     got = col_idx.cpu().numpy()[cols]
     tie = (od_second - od) <= 1e-6
     assert ((got == oi) | tie).all(), int(((got != oi) & ~tie).sum())
+
+
+def test_piecewise_icp_c1_tile_vs_oracle(cuda):
+    """C1 at its full size: one 1 M-point tile pair (SURVEY 8(d) scene: independent epochs, known block motion) through
+    f4l_piecewise_icp against oracle/piecewise.py -- same cells, same stable set, identical rows."""
+    from fusion4landslide_b200 import ops, synth
+    from oracle import piecewise as opw
+    d = synth.make_scene(1_000_000, seed=21, device=cuda)
+    src64, tgt64 = d["src"].double().contiguous(), d["tgt"].double().contiguous()
+    dvfs, mag, counts, thr = ops.piecewise_icp(src64, tgt64, 5.0, 10)
+    c = counts.tolist()
+    o = opw.piecewise_icp(src64.cpu().numpy(), tgt64.cpu().numpy(), 5.0, 10)
+    assert c[0] == o["dvfs"].shape[0] and c[0] > 100_000
+    assert abs(thr.item() - o["thr"]) <= 1e-12 * max(1.0, abs(o["thr"]))
+    np.testing.assert_array_equal(dvfs[:c[0]].cpu().numpy(), o["dvfs"])
+    np.testing.assert_allclose(mag[:c[0]].cpu().numpy(), o["dvfms"][:, 3], rtol=4e-16, atol=0)     # fp64 norm: one ulp (fma)
+
+
+def test_coarse2fine_c3_tile_sampled_vs_oracle(cuda, golden_dir):
+    """C3 at its full tile size (625 k points per epoch, 3 superpoint levels) through the class entry point.  The
+    oracle's O(N^2) descriptor search cannot run at this size, so the check is staged: descriptor labels of a random
+    sample of voxels against the fp64 arg-min; voxel maps against the kd-tree except ties; and -- given the GPU's own
+    correspondences -- the pair lists of every level and the fine matching of a sample of pairs per level against
+    oracle/paths.c2f_tile; plus size-independent properties of the merged field."""
+    import os
+    from fusion4landslide_b200 import configs, nets, synth
+    from fusion4landslide_b200.entry_c2f import Coarse2Fine
+    from oracle import paths as opaths
+    z = np.load(os.path.join(golden_dir, "nets_shipped.npz"))
+    model = nets.ClusterFeatureNetWithAttention()
+    model.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("agg/")})
+    model = model.to(cuda).eval()
+    w = {k[4:]: z[k] for k in z.files if k.startswith("agg/")}
+    n = 625_000
+    d = synth.make_scene(n, seed=31, device=cuda, desc_dim=64)
+    ls = [d["labels_src"][k] for k in (1, 2, 3)]
+    lt = [d["labels_tgt"][k] for k in (1, 2, 3)]
+    tt = dict(src_pts=d["src"], tgt_pts=d["tgt"], partition_src=ls, partition_tgt=lt, feat_raw_src=d["src_feat"],
+              feat_raw_tgt=d["tgt_feat"])
+    c = Coarse2Fine(configs.fusion_config(tt, levels=[1, 2, 3], feat_aggregate_model=model))
+    c.implement_c2f_matching()
+    torch.cuda.synchronize()
+    di, do = c.data_interim, c.data_output
+    # descriptor labels: a sample of rows against the exact fp64 arg-min over ALL voxels of the other epoch
+    fs, ft = di.tile_pts_sub_feat_src.cpu().numpy(), di.tile_pts_sub_feat_tgt.cpu().numpy()
+    rng = np.random.default_rng(0)
+    pick = rng.choice(fs.shape[0], 512, replace=False)
+    oi, od, od2 = odesc.desc_nn(fs[pick], ft, return_second=True)
+    lab = di.labels_from_3d.cpu().numpy()[pick]
+    assert ((lab == oi) | ((od2 - od) <= 1e-6)).all()
+    # the rest of the path on the GPU's correspondences: pair lists and sampled fine matching per level
+    v2p = {k: di["idx_voxel2pts_" + k].cpu().numpy() for k in ("src", "tgt")}
+    o = opaths.c2f_tile(d["src"].cpu().numpy(), d["tgt"].cpu().numpy(), [x.cpu().numpy() for x in ls],
+                        [x.cpu().numpy() for x in lt], d["src_feat"].cpu().numpy(), d["tgt_feat"].cpu().numpy(), w,
+                        voxel_size=float(c.method.voxel_size), median_max_resolution=float(np.float32(c.para.median_max_resolution)),
+                        max_pairs_per_level=40, corr3d_given=di.corres_3d_voxel_from_3d_idx.cpu().numpy(), v2p_given=v2p)
+    for k, raw in (("src", d["src"].cpu().numpy()), ("tgt", d["tgt"].cpu().numpy())):
+        same = v2p[k] == o["idx_voxel2pts_kdtree_" + k]
+        assert same.mean() > 0.97
+        bad = np.nonzero(~same)[0][:2000]
+        assert oknn.tie_rows(o[k + "_pts_sub"][bad], raw, 1).all()
+    total_checked = 0
+    for lv in range(3):
+        ol = o["levels"][lv]
+        k = len(ol["m"])
+        _, spt_s = opaths.patch_lists(ls[lv].cpu().numpy(), 10)
+        assert [int(x[0]) for x in do.spt_corres_src_multiple[lv][:k]] == [int(spt_s[a][0]) for a in ol["m"]]
+        fr, of = c.fine_results_multiple[lv], ol["fine"]
+        np.testing.assert_array_equal(fr.K[:k].cpu().numpy(), of["K"])
+        np.testing.assert_array_equal(fr.status[:k].cpu().numpy(), of["status"])
+        it = fr.iters[:k].cpu().numpy()
+        ok = (of["status"] == 0) & (it == of["iters"])
+        assert ((of["status"] == 0) & (it != of["iters"])).sum() <= 1
+        Tg = fr.T[:k].cpu().numpy().astype(np.float64)
+        src_np = d["src"].cpu().numpy().astype(np.float64)
+        for q in np.nonzero(ok)[0]:
+            if round(of["fitness"][q] * of["K"][q]) < 3:
+                continue
+            P = src_np[spt_s[ol["m"][q]]]
+            To = of["T"][q].astype(np.float64)
+            assert np.abs((P @ Tg[q][:3, :3].T + Tg[q][:3, 3]) - (P @ To[:3, :3].T + To[:3, 3])).max() < 1e-5
+            total_checked += 1
+    assert total_checked > 30
+    merged = do.corres_3d_refine_apply_icp
+    assert merged.shape[0] > 0.3 * n
+    uniq = torch.unique(merged[:, :3], dim=0).shape[0]
+    assert uniq == merged.shape[0]                       # only_3d: every source point at most once after the level merge
+    n1 = do.corres_3d_refine_apply_icp_multiple[0].shape[0]
+    assert torch.equal(merged[:n1], do.corres_3d_refine_apply_icp_multiple[0])          # level 1 first and complete

@@ -7,6 +7,5 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 python -c "
 import json; s=open('gpurun_out/bench_ref.json').read(); d=json.loads(s[s.index('{\"'):]); print('reference arm: %.3f M pts/s, %.1f ms/step, cores %s' % (d['value']/1e6, d['ms_per_step'], d['cpu_baseline']['cores']))"
-/usr/bin/time -v -o gpurun_out/bench_time.txt timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-grep "Elapsed (wall" gpurun_out/bench_time.txt
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python tools/show_bench.py gpurun_out/bench.json
