@@ -123,6 +123,13 @@ __device__ __forceinline__ void seg_bounds(const int32_t* start, const int32_t* 
 // H^T H -- the basis a previous, similar H converged to.  The iteration then starts from a = H warm instead of
 // a = H, and one or two sweeps are enough (an ICP loop fits a slowly changing covariance up to 31 times).  The
 // converged basis is written back.  Any orthonormal start gives the same decomposition up to rounding.
+// Columns p, q count as orthogonal when cos^2 of their angle is below F4L_SVD_THR = 1e-30 (|cos| <= 1e-15).  A tighter
+// bound (round 1: 1.44e-32) sits inside the rounding noise of the dot product, so converged columns kept "rotating by
+// noise" for one or two extra sweeps -- ~180 dependent fp64 instructions each on chains that are pure latency (the
+// tail of k_kabsch_fused, every ICP iteration of the fit kernels).  The decomposition moves by ~1e-15 relative.
+#ifndef F4L_SVD_THR
+#define F4L_SVD_THR 1e-30
+#endif
 __device__ inline void svd3x3(const double H[9], double U[9], double S[3], double V[9], double* warm = nullptr) {
     double a[3][3];  // a[c][r]: column c
     double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // v[c][r]
@@ -155,7 +162,7 @@ __device__ inline void svd3x3(const double H[9], double U[9], double S[3], doubl
             double alpha = a[p][0] * a[p][0] + a[p][1] * a[p][1] + a[p][2] * a[p][2];
             double beta = a[q][0] * a[q][0] + a[q][1] * a[q][1] + a[q][2] * a[q][2];
             double gamma = a[p][0] * a[q][0] + a[p][1] * a[q][1] + a[p][2] * a[q][2];
-            if (gamma == 0.0 || gamma * gamma <= 1.44e-32 * (alpha * beta)) continue;
+            if (gamma == 0.0 || gamma * gamma <= F4L_SVD_THR * (alpha * beta)) continue;
             rotated = true;
             const double da = beta - alpha, db = 2.0 * gamma;
             const double inv_r = rsqrt(da * da + db * db);

@@ -1,150 +1,15 @@
 // K-d segmented weighted Kabsch / Procrustes, K-f transform apply, K-c rigidity check and
-// segmented median.  One warp per segment for the reductions: a segment's points are read from
-// HBM exactly once, moments are accumulated in fp64 about a per-segment pivot, the 3x3 SVD runs
-// in fp64 on lane 0.
+// segmented median.  A segment's points are read from HBM exactly once, moments are accumulated in fp64
+// about a per-segment pivot, the 3x3 SVD runs in fp64, one segment per lane of a fitting warp.
 #include "common.cuh"
 #include "rigid_device.cuh"
 
 // ------------------------------------------------------------------------------------------
-// K-d.  A warp owns a GROUP of 32 consecutive segments: the moments of each segment are accumulated
-// cooperatively (coalesced, every point read from HBM once) and reduce-scattered over the warp with 16
-// double shuffles; then every lane solves the 3x3 SVD of ITS segment, so the long fp64 dependency chain of
-// the Jacobi sweeps runs 32-wide instead of once per warp.
+// K-d segmented weighted Kabsch / Procrustes: k_kabsch_fused (moments + fit, below) and the optional residual pass.
 #define KAB_WARPS 4
-
-// butterfly reduce-scatter of the 16 moments: afterwards lane l holds the warp total of m[(l >> 1) & 15]
-__device__ __forceinline__ double moments_reduce_scatter(const Moments& M, int lane) {
-    double v8[8], v4[4], v2[2];
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const double send = b4 ? M.m[i] : M.m[i + 8];
-        const double keep = b4 ? M.m[i + 8] : M.m[i];
-        v8[i] = keep + __shfl_xor_sync(F4L_FULL, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double send = b3 ? v8[i] : v8[i + 4];
-        const double keep = b3 ? v8[i + 4] : v8[i];
-        v4[i] = keep + __shfl_xor_sync(F4L_FULL, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double send = b2 ? v4[i] : v4[i + 2];
-        const double keep = b2 ? v4[i + 2] : v4[i];
-        v2[i] = keep + __shfl_xor_sync(F4L_FULL, send, 4);
-    }
-    double v = (b1 ? v2[1] : v2[0]) + __shfl_xor_sync(F4L_FULL, b1 ? v2[0] : v2[1], 2);
-    v += __shfl_xor_sync(F4L_FULL, v, 1);
-    return v;
-}
-
-// pass 1: warp per segment, every point read from HBM exactly once, 16 raw moments to scratch.
-// The kernel is a pure stream with ~25 fp64 ops per 24 bytes, so what limits it is bytes in flight, and
-// with fp64 accumulators registers cap the occupancy: each warp therefore stages its segment through shared
-// memory with cp.async (LDGSTS, 4-byte granules so that unaligned / gathered segments work) -- a whole
-// 256-point chunk (6 KB) is in flight per warp without holding a single register.
-#define KAB_CHUNK 256
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                  : "memory");
-}
-
-__global__ void __launch_bounds__(KAB_WARPS * 32)
-k_kabsch_moments(const float* __restrict__ src, const float* __restrict__ tgt,
-                 const int32_t* __restrict__ src_idx, const int32_t* __restrict__ tgt_idx,
-                 const float* __restrict__ w, const int32_t* __restrict__ seg_start,
-                 const int32_t* __restrict__ seg_count, int Q, float weight_thresh, int variant,
-                 double* __restrict__ mom) {
-    __shared__ float stage[KAB_WARPS][2][KAB_CHUNK * 3];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int q = blockIdx.x * KAB_WARPS + wid;
-    if (q >= Q) return;
-    int s0, n;
-    seg_bounds(seg_start, seg_count, q, s0, n);
-    float* ss = stage[wid][0];
-    float* st = stage[wid][1];
-    Moments M;
-    moments_zero(M);
-    if (n > 0) {
-        double ps[3], pt[3];
-        load_pt(src, src_idx, s0, ps[0], ps[1], ps[2]);
-        load_pt(tgt, tgt_idx, s0, pt[0], pt[1], pt[2]);
-        for (int c0 = 0; c0 < n; c0 += KAB_CHUNK) {
-            const int cnt = min(KAB_CHUNK, n - c0);
-            if (!src_idx && !tgt_idx) {
-                // packed pairs: the chunk is one contiguous run of 3*cnt floats per array
-                const float* gs = src + (size_t)(s0 + c0) * 3;
-                const float* gt = tgt + (size_t)(s0 + c0) * 3;
-                for (int e = lane; e < 3 * cnt; e += 32) { cp_async4(ss + e, gs + e); cp_async4(st + e, gt + e); }
-            } else {
-                for (int j = lane; j < cnt; j += 32) {
-                    const size_t a = src_idx ? (size_t)src_idx[s0 + c0 + j] : (size_t)(s0 + c0 + j);
-                    const size_t b = tgt_idx ? (size_t)tgt_idx[s0 + c0 + j] : (size_t)(s0 + c0 + j);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { cp_async4(ss + 3 * j + k, src + a * 3 + k); cp_async4(st + 3 * j + k, tgt + b * 3 + k); }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            for (int j = lane; j < cnt; j += 32) {
-                double wi = 1.0;
-                if (w) {
-                    float wf = __ldg(w + s0 + c0 + j);
-                    if (variant == 0 && wf < weight_thresh) wf = 0.f;
-                    wi = (double)wf;
-                }
-                moments_add(M, wi, (double)ss[3 * j] - ps[0], (double)ss[3 * j + 1] - ps[1], (double)ss[3 * j + 2] - ps[2],
-                            (double)st[3 * j] - pt[0], (double)st[3 * j + 1] - pt[1], (double)st[3 * j + 2] - pt[2]);
-            }
-            __syncwarp();
-        }
-    }
-    const double v = moments_reduce_scatter(M, lane);
-    if (!(lane & 1)) mom[(size_t)q * 16 + (lane >> 1)] = v;
-}
-
-// pass 2: THREAD per segment: reference formulas + 3x3 SVD, 32 segments per warp in flight
-__global__ void __launch_bounds__(128)
-k_kabsch_fit(const float* __restrict__ src, const float* __restrict__ tgt, const int32_t* __restrict__ src_idx,
-             const int32_t* __restrict__ tgt_idx, const int32_t* __restrict__ seg_start,
-             const int32_t* __restrict__ seg_count, int Q, double eps, int variant, double* __restrict__ mom,
-             float* __restrict__ R, float* __restrict__ t, double* __restrict__ T64, uint8_t* __restrict__ flag) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    int s0, n;
-    seg_bounds(seg_start, seg_count, q, s0, n);
-    double Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tv[3] = {0, 0, 0};
-    bool bad = true;
-    if (n > 0) {
-        Moments M;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) M.m[i] = mom[(size_t)q * 16 + i];
-        double ps[3], pt[3];
-        load_pt(src, src_idx, s0, ps[0], ps[1], ps[2]);
-        load_pt(tgt, tgt_idx, s0, pt[0], pt[1], pt[2]);
-        bad = fit_from_moments(M, ps, pt, eps, variant, Rm, tv);
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[(size_t)q * 9 + i] = (float)Rm[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) t[(size_t)q * 3 + i] = (float)tv[i];
-    if (T64) {
-        double* T = T64 + (size_t)q * 16;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            T[i * 4 + 0] = Rm[i * 3 + 0]; T[i * 4 + 1] = Rm[i * 3 + 1]; T[i * 4 + 2] = Rm[i * 3 + 2];
-            T[i * 4 + 3] = tv[i];
-        }
-        T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
-    }
-    if (flag) flag[q] = bad ? 1 : 0;
-    // fp64 fit for the residual pass (overwrites this segment's moments)
-#pragma unroll
-    for (int i = 0; i < 9; ++i) mom[(size_t)q * 16 + i] = Rm[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) mom[(size_t)q * 16 + 9 + i] = tv[i];
 }
 
 // pass 3 (optional): residuals ||R s + t - tgt||, warp per segment
@@ -174,6 +39,298 @@ k_kabsch_residuals(const float* __restrict__ src, const float* __restrict__ tgt,
     }
 }
 
+// ---- fused form: moments + fit in ONE persistent launch ---------------------------------------------------------
+// CTAs are persistent (3 per SM) and walk over groups of 16 consecutive segments.  Warps 0-7 STREAM: warp w accumulates
+// the moments of segments w and w + 8 of the group through a two-stage pipeline -- the next 128-point chunk is in flight
+// while the current one is accumulated -- and leaves the 16 moments and the pivot of each segment in shared memory.
+// Warp 8 FITS: its 32 lanes run the reference formulas and the 3x3 SVD of the 2 x 16 segments of the two previous groups
+// while the streaming warps are already on the next ones (full / empty mbarriers over four moment tables), so the long
+// fp64 dependency chain of the Jacobi sweeps (~1 800 dependent instructions per fit) is off the streaming path and costs
+// one warp slot in nine; no second launch, no scratch round trip, no stream-ordered allocation.  16 segments per group
+// keep the scheduling quantum at ~100 KB per CTA.
+// Staging of packed pairs: ONE TMA bulk copy per array and chunk (cp.async.bulk global -> shared, completion on the
+// stage's mbarrier), issued by lane 0: the 16-byte lines that cover the run, the run itself starting `mis` floats into
+// the buffer (segments start at any multiple of 12 bytes).  A chunk costs ~30 instructions to stage instead of ~250 with
+// per-lane 4-byte cp.async: the kernel is issue- / latency-bound, not DRAM-bound (ncu: 83 M warp instructions at 16 M
+// pairs with per-lane staging, 51 M with bulk copies).
+#define KF_WARPS 8                      // streaming warps; warp KF_WARPS fits
+#ifndef KF_SEGS
+#define KF_SEGS 1                       // segments per streaming warp and group
+#endif
+#define KF_GROUP (KF_WARPS * KF_SEGS)
+#define KF_FIT_GROUPS (32 / KF_GROUP)   // groups the fitting warp takes at once (one segment per lane)
+#define KF_CHUNK 128
+#define KF_STAGE_FLOATS (KF_CHUNK * 3 + 8)
+#define KF_MOM 23                       // 16 moments + 2 pivots, odd stride (conflict-free thread-per-segment reads)
+#define KF_CTAS_PER_SM 3
+#define KF_SLOTS (2 * KF_FIT_GROUPS)     // moment tables in flight: half being fitted, half being streamed
+struct KfWarpStage {
+    float s[KF_STAGE_FLOATS];
+    float t[KF_STAGE_FLOATS];
+    float w[KF_CHUNK + 8];
+};
+struct KfSmem {
+    KfWarpStage st[KF_WARPS][2];
+    double mom[KF_SLOTS][KF_GROUP][KF_MOM];
+    unsigned long long bar[KF_WARPS][2];
+    unsigned long long full[KF_SLOTS], empty[KF_SLOTS];
+    int seg[KF_WARPS][KF_SEGS][2];      // (first item, count) of the warp's segments
+};
+static_assert(sizeof(KfWarpStage) % 16 == 0 && sizeof(KfWarpStage) >= 8 * 33 * 8, "stage: 16-byte multiples; hosts the reduction tile");
+static_assert(offsetof(KfWarpStage, t) % 16 == 0 && offsetof(KfWarpStage, w) % 16 == 0, "bulk-copy destinations are 16-byte aligned");
+
+__device__ __forceinline__ uint32_t kf_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kf_mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KF_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra KF_WAIT_%=;\n\t}" ::"r"(mbar), "r"(parity)
+        : "memory");
+}
+
+// One bulk copy stages the run of F floats at g: the 16-byte lines that cover it, [g - mis, round-up of the end), land at
+// `dst` (16-byte aligned) and the run starts at dst + mis floats (mis = g's offset inside its line).  Up to 12 bytes
+// before / after the run ride along; they lie in lines that hold valid bytes of the same array, so they are mapped.
+// Returns the bytes the stage's mbarrier has to expect.
+__device__ __forceinline__ uint32_t kf_bulk_bytes(const float* g, int F) {
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(g) >> 2) & 3u);
+    return ((mis + (uint32_t)F) * 4u + 15u) & ~15u;
+}
+__device__ __forceinline__ void kf_bulk(uint32_t dst, const float* g, uint32_t bytes, uint32_t mbar) {
+    const float* g_al = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g_al),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void moments_add_unit(Moments& M, double sx, double sy, double sz, double tx, double ty, double tz) {
+    // moments_add with w = 1 (bit-identical: the products with 1.0 are exact)
+    M.m[0] += 1.0;
+    M.m[1] += sx; M.m[2] += sy; M.m[3] += sz;
+    M.m[4] += tx; M.m[5] += ty; M.m[6] += tz;
+    M.m[7] += sx * tx; M.m[8] += sx * ty; M.m[9] += sx * tz;
+    M.m[10] += sy * tx; M.m[11] += sy * ty; M.m[12] += sy * tz;
+    M.m[13] += sz * tx; M.m[14] += sz * ty; M.m[15] += sz * tz;
+}
+
+// warp total of the 16 moments -> row[0..15], through an 8 x 33 tile of doubles (two rounds of eight moments): lane l
+// adds the eight partials of moment (l & 7) held by lanes 8 (l >> 3) .., two shuffles finish -- 64 instructions instead
+// of the 150 of the butterfly reduce-scatter.  Deterministic order.
+__device__ __forceinline__ void kf_reduce(const Moments& M, double* tile, double* row, int lane) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[i * 33 + lane] = M.m[8 * r + i];
+        __syncwarp();
+        const double* col = tile + (lane & 7) * 33 + (lane >> 3) * 8;
+        double v = col[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) v += col[k];
+        v += __shfl_xor_sync(F4L_FULL, v, 8);
+        v += __shfl_xor_sync(F4L_FULL, v, 16);
+        if (lane < 8) row[8 * r + lane] = v;
+        __syncwarp();
+    }
+}
+
+template <bool HAS_W>
+__global__ void __launch_bounds__((KF_WARPS + 1) * 32, KF_CTAS_PER_SM)
+k_kabsch_fused(const float* __restrict__ src, const float* __restrict__ tgt, const int32_t* __restrict__ src_idx,
+               const int32_t* __restrict__ tgt_idx, const float* __restrict__ w, const int32_t* __restrict__ seg_start,
+               const int32_t* __restrict__ seg_count, int Q, double eps, float weight_thresh, int variant,
+               float* __restrict__ R, float* __restrict__ t, double* __restrict__ T64, uint8_t* __restrict__ flag,
+               double* __restrict__ fit64) {
+    extern __shared__ __align__(16) unsigned char kf_raw[];
+    KfSmem& sm = *reinterpret_cast<KfSmem*>(kf_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n_groups = (Q + KF_GROUP - 1) / KF_GROUP;
+    const uint32_t sm_base = kf_u32(kf_raw);
+    const uint32_t full_base = sm_base + (uint32_t)offsetof(KfSmem, full), empty_base = sm_base + (uint32_t)offsetof(KfSmem, empty);
+    if (threadIdx.x < KF_SLOTS) {
+        // every thread that wrote (read) a moment table arrives itself: its own release (acquire) orders its accesses
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_base + threadIdx.x * 8u), "r"((uint32_t)KF_WARPS * 32u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_base + threadIdx.x * 8u), "r"((uint32_t)KF_GROUP) : "memory");
+    }
+    if (wid < KF_WARPS && lane < 2)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_base + (uint32_t)offsetof(KfSmem, bar) + (uint32_t)(wid * 2 + lane) * 8u),
+                     "r"(1u)
+                     : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    if (wid == KF_WARPS) {
+        // ---- fitting warp: the 32 lanes fit the segments of KF_FIT_GROUPS consecutive groups of this CTA at once
+        const int sub = lane / KF_GROUP, l = lane % KF_GROUP;
+        for (int it = 0, g = blockIdx.x; g < n_groups; g += KF_FIT_GROUPS * gridDim.x, it += KF_FIT_GROUPS) {
+#pragma unroll
+            for (int u = 0; u < KF_FIT_GROUPS; ++u)
+                if (g + u * (int)gridDim.x < n_groups)
+                    kf_mbar_wait(full_base + (uint32_t)((it + u) & (KF_SLOTS - 1)) * 8u, (uint32_t)((it + u) / KF_SLOTS) & 1u);
+            const int slot = (it + sub) & (KF_SLOTS - 1);
+            const int gs = g + sub * (int)gridDim.x;
+            const int q = gs * KF_GROUP + l;
+            if (gs < n_groups && q < Q) {
+                int s0, n;
+                seg_bounds(seg_start, seg_count, q, s0, n);
+                double Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tv[3] = {0, 0, 0};
+                bool bad = true;
+                if (n > 0) {
+                    const double* row = sm.mom[slot][l];
+                    Moments Mq;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) Mq.m[i] = row[i];
+                    double qs[3] = {row[16], row[17], row[18]}, qt[3] = {row[19], row[20], row[21]};
+                    bad = fit_from_moments(Mq, qs, qt, eps, variant, Rm, tv);
+                }
+#pragma unroll
+                for (int i = 0; i < 9; ++i) R[(size_t)q * 9 + i] = (float)Rm[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) t[(size_t)q * 3 + i] = (float)tv[i];
+                if (T64) {
+                    double* T = T64 + (size_t)q * 16;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        T[i * 4 + 0] = Rm[i * 3 + 0]; T[i * 4 + 1] = Rm[i * 3 + 1]; T[i * 4 + 2] = Rm[i * 3 + 2];
+                        T[i * 4 + 3] = tv[i];
+                    }
+                    T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+                }
+                if (flag) flag[q] = bad ? 1 : 0;
+                if (fit64) {                  // fp64 fit for the residual pass
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) fit64[(size_t)q * 16 + i] = Rm[i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) fit64[(size_t)q * 16 + 9 + i] = tv[i];
+                }
+            }
+            if (gs < n_groups)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_base + (uint32_t)slot * 8u) : "memory");
+        }
+        return;
+    }
+
+    // ---- streaming warps ------------------------------------------------------------------------------------------
+    const bool packed = !src_idx && !tgt_idx;
+    const int (*seg)[2] = sm.seg[wid];
+    const uint32_t bar_base = sm_base + (uint32_t)offsetof(KfSmem, bar) + (uint32_t)wid * 16u;
+    const uint32_t stage_base = sm_base + (uint32_t)wid * 2u * (uint32_t)sizeof(KfWarpStage);
+    // put the chunk (segment first item s0, chunk offset c0, n items) in flight into stage b
+    auto issue = [&](int s0, int c0, int n, int b) {
+        const int cnt = min(KF_CHUNK, n - c0);
+        const uint32_t mbar = bar_base + (uint32_t)b * 8u;
+        if (packed) {
+            if (lane == 0) {
+                const uint32_t dst = stage_base + (uint32_t)b * (uint32_t)sizeof(KfWarpStage);
+                const float* gs = src + (size_t)(s0 + c0) * 3;
+                const float* gt = tgt + (size_t)(s0 + c0) * 3;
+                const uint32_t bs = kf_bulk_bytes(gs, 3 * cnt), bt = kf_bulk_bytes(gt, 3 * cnt);
+                const uint32_t bw = HAS_W ? kf_bulk_bytes(w + s0 + c0, cnt) : 0u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bs + bt + bw) : "memory");
+                kf_bulk(dst, gs, bs, mbar);
+                kf_bulk(dst + (uint32_t)offsetof(KfWarpStage, t), gt, bt, mbar);
+                if (HAS_W) kf_bulk(dst + (uint32_t)offsetof(KfWarpStage, w), w + s0 + c0, bw, mbar);
+            }
+        } else {
+            KfWarpStage& S = sm.st[wid][b];
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+            for (int j = lane; j < cnt; j += 32) {
+                const size_t a = src_idx ? (size_t)src_idx[s0 + c0 + j] : (size_t)(s0 + c0 + j);
+                const size_t bb = tgt_idx ? (size_t)tgt_idx[s0 + c0 + j] : (size_t)(s0 + c0 + j);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { cp_async4(S.s + 3 * j + k, src + a * 3 + k); cp_async4(S.t + 3 * j + k, tgt + bb * 3 + k); }
+                if (HAS_W) cp_async4(S.w + j, w + s0 + c0 + j);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+    // offsets (in floats) of the arrays inside their 16-byte lines: the run of item k starts at (off + stride k) & 3
+    const int off_s = packed ? (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u) : 0;
+    const int off_t = packed ? (int)((reinterpret_cast<uintptr_t>(tgt) >> 2) & 3u) : 0;
+    const int off_w = (packed && HAS_W) ? (int)((reinterpret_cast<uintptr_t>(w) >> 2) & 3u) : 0;
+    auto advance = [&](int& s, int& c) {      // the item after (s, c); s == KF_SEGS: none
+        c += KF_CHUNK;
+        if (c >= seg[s][1]) {
+            c = 0;
+            do { ++s; } while (s < KF_SEGS && seg[s][1] == 0);
+        }
+    };
+    int buf = 0;
+    unsigned phase = 0;                       // bit b: parity the next wait on stage b expects
+    int it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        const int mb = it & (KF_SLOTS - 1);
+        const int q0 = g * KF_GROUP;
+        if (lane < KF_SEGS) {
+            const int q = q0 + wid + KF_WARPS * lane;
+            int s0 = 0, n = 0;
+            if (q < Q) seg_bounds(seg_start, seg_count, q, s0, n);
+            sm.seg[wid][lane][0] = s0;
+            sm.seg[wid][lane][1] = max(n, 0);
+        }
+        __syncwarp();
+        int cs = 0, cc = 0;                   // item being computed
+        if (seg[0][1] == 0) { cc = -KF_CHUNK; advance(cs, cc); }
+        if (cs < KF_SEGS) issue(seg[cs][0], cc, seg[cs][1], buf);
+        // this moment table is free once the fitting warp is done with the group that used it KF_SLOTS groups ago
+        if (it >= KF_SLOTS) kf_mbar_wait(empty_base + (uint32_t)mb * 8u, (uint32_t)(it / KF_SLOTS - 1) & 1u);
+        Moments M;
+        moments_zero(M);
+        double ps[3] = {0, 0, 0}, pt[3] = {0, 0, 0};
+        while (cs < KF_SEGS) {
+            const int n = seg[cs][1];
+            const int k0 = packed ? seg[cs][0] + cc : 0;
+            int is = cs, ic = cc;
+            advance(is, ic);
+            if (is < KF_SEGS) {
+                issue(seg[is][0], ic, seg[is][1], buf ^ 1);
+                if (!packed) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else if (!packed) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            kf_mbar_wait(bar_base + (uint32_t)buf * 8u, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            __syncwarp();
+            const KfWarpStage& S = sm.st[wid][buf];
+            const float* ss = S.s + ((off_s + 3 * k0) & 3);
+            const float* st = S.t + ((off_t + 3 * k0) & 3);
+            const float* sw = S.w + ((off_w + k0) & 3);
+            if (cc == 0) {                    // pivot = the segment's first pair
+                ps[0] = ss[0]; ps[1] = ss[1]; ps[2] = ss[2];
+                pt[0] = st[0]; pt[1] = st[1]; pt[2] = st[2];
+            }
+            const int cnt = min(KF_CHUNK, n - cc);
+#pragma unroll 2
+            for (int j = lane; j < cnt; j += 32) {
+                const double sx = (double)ss[3 * j] - ps[0], sy = (double)ss[3 * j + 1] - ps[1], sz = (double)ss[3 * j + 2] - ps[2];
+                const double tx = (double)st[3 * j] - pt[0], ty = (double)st[3 * j + 1] - pt[1], tz = (double)st[3 * j + 2] - pt[2];
+                if (HAS_W) {
+                    float wf = sw[j];
+                    if (variant == 0 && wf < weight_thresh) wf = 0.f;
+                    moments_add(M, (double)wf, sx, sy, sz, tx, ty, tz);
+                } else {
+                    moments_add_unit(M, sx, sy, sz, tx, ty, tz);
+                }
+            }
+            __syncwarp();
+            if (cc + KF_CHUNK >= n) {         // segment complete: the stage just consumed hosts the reduction tile
+                double* row = sm.mom[mb][wid + KF_WARPS * cs];
+                kf_reduce(M, reinterpret_cast<double*>(&sm.st[wid][buf]), row, lane);
+                if (lane == 0) {
+                    row[16] = ps[0]; row[17] = ps[1]; row[18] = ps[2];
+                    row[19] = pt[0]; row[20] = pt[1]; row[21] = pt[2];
+                }
+                moments_zero(M);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile's generic writes before a later bulk copy lands here
+                __syncwarp();
+            }
+            cs = is; cc = ic;
+            buf ^= 1;
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_base + (uint32_t)mb * 8u) : "memory");
+    }
+}
+
 extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const int32_t* src_idx,
                                     const int32_t* tgt_idx, const float* w, const int32_t* seg_start,
                                     const int32_t* seg_count, int32_t Q, float eps, float weight_thresh,
@@ -184,10 +341,10 @@ extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const in
     F4L_REQUIRE(src && tgt && seg_start && R && t, "null pointer");
     F4L_REQUIRE(variant == F4L_KABSCH_PROCRUSTES || variant == F4L_KABSCH_F2S3, "unknown variant");
     cudaStream_t st = (cudaStream_t)stream;
-    // 128 B of scratch per segment (raw moments, then the fp64 fit), stream-ordered pool allocation
-    double* mom = nullptr;
-    static F4lPerDevice pool_ready;
-    if (!pool_ready.done()) {
+    static F4lPerDevice optin;
+    if (!optin.done()) {
+        if (!f4l_optin_smem(k_kabsch_fused<false>, sizeof(KfSmem), "k_kabsch_fused") ||
+            !f4l_optin_smem(k_kabsch_fused<true>, sizeof(KfSmem), "k_kabsch_fused")) return F4L_E_CUDA;
         // keep freed blocks in the default pool instead of returning them to the OS at every synchronisation
         int dev = 0;
         cudaMemPool_t pool;
@@ -195,25 +352,29 @@ extern "C" int f4l_segmented_kabsch(const float* src, const float* tgt, const in
             unsigned long long keep = 1ull << 30;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        pool_ready.mark();
+        optin.mark();
     }
-    if (cudaMallocAsync((void**)&mom, (size_t)Q * 16 * sizeof(double), st) != cudaSuccess) {
+    // 128 B of scratch per segment (the fp64 fit, for the residual pass), stream-ordered pool allocation
+    double* mom = nullptr;
+    if (res && cudaMallocAsync((void**)&mom, (size_t)Q * 16 * sizeof(double), st) != cudaSuccess) {
         f4l_set_error("f4l_segmented_kabsch: cudaMallocAsync of %zu bytes failed", (size_t)Q * 128);
         cudaGetLastError();
         return F4L_E_CUDA;
     }
-    f4l_mark("k_kabsch_moments", st);
-    k_kabsch_moments<<<f4l_div_up(Q, KAB_WARPS), KAB_WARPS * 32, 0, st>>>(src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q,
-                                                                         weight_thresh, variant, mom);
-    f4l_mark("k_kabsch_fit", st);
-    k_kabsch_fit<<<f4l_div_up(Q, 128), 128, 0, st>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count, Q, (double)eps, variant,
-                                                    mom, R, t, T64, flag);
+    const int kf_grid = f4l_div_up(Q, KF_GROUP) < 148 * KF_CTAS_PER_SM ? f4l_div_up(Q, KF_GROUP) : 148 * KF_CTAS_PER_SM;
+    f4l_mark("k_kabsch_fused", st);
+    if (w)
+        k_kabsch_fused<true><<<kf_grid, (KF_WARPS + 1) * 32, sizeof(KfSmem), st>>>(
+            src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q, (double)eps, weight_thresh, variant, R, t, T64, flag, mom);
+    else
+        k_kabsch_fused<false><<<kf_grid, (KF_WARPS + 1) * 32, sizeof(KfSmem), st>>>(
+            src, tgt, src_idx, tgt_idx, w, seg_start, seg_count, Q, (double)eps, weight_thresh, variant, R, t, T64, flag, mom);
     if (res) {
         f4l_mark("k_kabsch_residuals", st);
         k_kabsch_residuals<<<f4l_div_up(Q, KAB_WARPS), KAB_WARPS * 32, 0, st>>>(src, tgt, src_idx, tgt_idx, seg_start, seg_count,
                                                                                Q, mom, res);
     }
-    cudaFreeAsync(mom, st);
+    if (mom) cudaFreeAsync(mom, st);
     return f4l_finish("f4l_segmented_kabsch", stream);
 }
 

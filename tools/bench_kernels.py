@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--n", type=int, default=4_000_000)
     ap.add_argument("--patch", type=int, default=256)
     ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--only", default="", help="'rigid': K-d / K-f / K-c only (skip the kNN / voxel part)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
@@ -81,7 +82,7 @@ def main():
     ms = timed(lambda: ops.rigidity_check(src, tgt, ptr, 0.5), a.reps, flush)
     rec("k_rigidity (K^2/2 pairs per patch)", ms, 24 * K + 8 * Q, {"pair_evals_per_s": Q * a.patch * (a.patch - 1) / 2 / ms * 1e3})
     # K-a on a synthetic TLS tile pair
-    for n in (1_000_000, a.n):
+    for n in (() if a.only == "rigid" else (1_000_000, a.n)):
         d = synth.make_tile(n, seed=1, device=dev, patch_pts=a.patch)
         s, tg = d["src"], d["tgt"]
         ms = timed(lambda: ops.knn_grid(s, s, 2), a.reps, flush)
