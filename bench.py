@@ -260,10 +260,13 @@ def run_b200(a):
     else:
         arenas = [torch.empty((cap_rows, 6), dtype=torch.float32, device=dev)]
     dense_arena = arenas[0]
-    T_arena = torch.empty((cap_pairs, 4, 4), dtype=torch.float32, device=dev)
+    # per parity ONE small arena [transforms | row counts]: a single all-gather per step ships both, and the step that
+    # overwrites it is two steps later (the gather of step k runs on the exchange stream under step k + 1)
     n_tiles_max = (a.tiles + world - 1) // world
-    counts_arena = torch.zeros((n_tiles_max, 4), dtype=torch.int32, device=dev)
-    counts_arenas = [counts_arena] + [torch.zeros_like(counts_arena) for _ in arenas[1:]]
+    meta_arenas = [torch.zeros((cap_pairs * 16 + n_tiles_max * 4,), dtype=torch.float32, device=dev) for _ in arenas]
+    T_arenas = [m[:cap_pairs * 16].view(cap_pairs, 4, 4) for m in meta_arenas]
+    counts_arenas = [m[cap_pairs * 16:].view(torch.int32).view(n_tiles_max, 4) for m in meta_arenas]
+    T_arena, counts_arena = T_arenas[0], counts_arenas[0]
     meds = torch.empty((max(len(tiles), 1),), dtype=torch.float32, device=dev)
     from fusion4landslide_b200 import ops as ops_mod
     from fusion4landslide_b200.ops import FineResult
@@ -292,8 +295,9 @@ def run_b200(a):
             else:                                           # parity 1 differs only in the dense arena
                 for k in FineResult.__slots__:
                     setattr(r, k, getattr(outs_par[0][i], k, None))
-            if par > 0:                                     # the copy kernels of step k read the counts while step k+1 runs
+            if par > 0:                                     # the copy kernels / the gather of step k run while step k+1 computes
                 r.counts = counts_arenas[par][i]
+                r.T = T_arenas[par][po:po + Q]
             r.dense = arena[ro:ro + t.n_src_items]
             outs.append(r)
             peers.append(ex.peer_ptrs(par, ro) if fused else None)
@@ -304,8 +308,8 @@ def run_b200(a):
     outs = outs_par[0]
     if world > 1:
         gathered_dense = None if fused else torch.empty((world * cap_rows, 6), dtype=torch.float32, device=dev)
-        gathered_T = torch.empty((world * cap_pairs, 4, 4), dtype=torch.float32, device=dev)
-        gathered_counts = torch.empty((world * n_tiles_max * 4,), dtype=torch.int32, device=dev)
+        gathered_meta = torch.empty((world, meta_arenas[0].numel()), dtype=torch.float32, device=dev)
+        gathered_counts = gathered_meta[:, cap_pairs * 16:]            # (world, n_tiles_max * 4) int32 bit patterns
 
     streams = pipeline.make_streams(a.streams, dev) if a.streams > 1 else None
     sides = pipeline.make_streams(a.streams, dev) if (a.streams > 1 and a.a1_overlap) else None
@@ -358,10 +362,9 @@ def run_b200(a):
     def exchange(par=0):
         # fused: the dense rows are already in every rank's field; this small all-gather is also the barrier
         # that orders all ranks' pushed rows before anyone reads the field
-        dist.all_gather_into_tensor(gathered_T, T_arena)
         if not fused:
             dist.all_gather_into_tensor(gathered_dense, dense_arena)
-        dist.all_gather_into_tensor(gathered_counts, counts_arenas[par % len(counts_arenas)].reshape(-1))
+        dist.all_gather_into_tensor(gathered_meta.view(-1), meta_arenas[par % len(meta_arenas)])
 
     push_done = [None]
 
@@ -378,6 +381,9 @@ def run_b200(a):
             xstream.wait_event(ev)
             for i in range(len(tiles)):
                 ops_mod.peer_push(outs_par[par][i].dense, outs_par[par][i].counts, peers_par[par][i])
+            # the small all-gather (transforms + counts) follows the copies ON THE EXCHANGE STREAM: when it completes
+            # every rank has issued its copies of this step, and the main stream never waits for a collective
+            exchange(par)
             done = torch.cuda.Event()
             done.record(xstream)
         push_done[0] = done
@@ -393,9 +399,10 @@ def run_b200(a):
         compute(par)
         if world > 1 and not a.no_gather:
             if pushing:
-                drain_pushes()             # the previous step's rows have left: its field is complete on every rank
-                launch_pushes(par)         # ... once the small all-gather below has passed on all of them
-            exchange(par)
+                drain_pushes()             # the previous step's rows have left and its gather has passed on every rank
+                launch_pushes(par)
+            else:
+                exchange(par)
 
     def barrier():
         torch.cuda.synchronize()           # own copy kernels first: a peer may read its field right after the barrier
@@ -454,7 +461,8 @@ def run_b200(a):
         if pushing:
             launch_pushes(par_b)
             drain_pushes()                 # un-pipelined here: the copies' own duration shows up in exchange_ms
-        exchange(par_b)
+        else:
+            exchange(par_b)
         ec.record()
         barrier()
         bd = torch.tensor([ea.elapsed_time(eb), eb.elapsed_time(ec)], device=dev, dtype=torch.float64)
@@ -467,7 +475,7 @@ def run_b200(a):
             ref = torch.empty((world * cap_rows, 6), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(ref, arenas[last])
             ref = ref.view(world, cap_rows, 6)
-            cnt = gathered_counts.view(world, n_tiles_max, 4)[:, :, 0].sum(1).tolist()
+            cnt = gathered_counts.contiguous().view(torch.int32).view(world, n_tiles_max, 4)[:, :, 0].sum(1).tolist()
             ok = all(torch.equal(ex.field(last)[r, :cnt[r]], ref[r, :cnt[r]]) for r in range(world))
             okt = torch.tensor([1 if ok else 0], device=dev)
             dist.all_reduce(okt, op=dist.ReduceOp.MIN)
