@@ -291,6 +291,7 @@ def run_b200(a):
                 r.sparse = torch.empty((2 * t.n_src_items, 6), dtype=torch.float32, device=dev)
                 r.tgt2src = None
                 r.sparse_pair_rows = None
+                r.icp_fragile = torch.zeros((Q,), dtype=torch.uint8, device=dev)
                 r.counts = counts_arena[i]
             else:                                           # parity 1 differs only in the dense arena
                 for k in FineResult.__slots__:
@@ -639,7 +640,11 @@ def c5_parity(r, spt_src, tile, out):
         To = r["T"][q].astype(np.float64)
         worst = max(worst, float(np.abs((P @ Tg[q][:3, :3].T + Tg[q][:3, 3]) - (P @ To[:3, :3].T + To[:3, 3])).max()))
     rejected = int((r["status"] == 1).sum())
+    frag = getattr(out, "icp_fragile", None)
+    frag = frag[:k].cpu().numpy() if frag is not None else np.zeros(k, np.uint8)
+    flip = ok & (Ig != r["iters"])
     return {"checked_against": "oracle/cpu_path.py on the CPU-sampled pairs of tile 0, in this run", "pairs_checked": int(k),
+            "icp_fragile_pairs": int((ok & (frag != 0)).sum()), "icp_path_flips_unflagged": int((flip & (frag == 0)).sum()),
             "K_mismatch": int((Kg != r["K"]).sum()), "status_mismatch": int((Sg != r["status"]).sum()),
             "rigidity_rejected_pairs": rejected, "rigidity_flips": int(((Sg == 1) != (r["status"] == 1)).sum()),
             "fitted_pairs": int(ok.sum()), "icp_path_flips": int((ok & (Ig != r["iters"])).sum()),

@@ -48,6 +48,7 @@ class FineBuffers(ctypes.Structure):
         ("dense", c_void_p), ("sparse", c_void_p), ("tgt2src", c_void_p), ("counts", c_void_p),
         ("n_peers", c_i32), ("peer_dense", c_void_p * MAX_PEERS),
         ("sparse_pair_rows", c_void_p), ("median_ready_event", c_void_p), ("phases", c_i32),
+        ("icp_fragile", c_void_p),
     ]
 
 
@@ -78,6 +79,8 @@ SIGNATURES = {
     "f4l_segmented_nn": (c_int, [P, P, P, P, P, P, P, P, c_i32, P, P, P, P, P]),
     "f4l_patch_icp": (c_int, [P, P, P, P, P, P, P, P, P, c_i32, P, c_f64, c_i32, c_f64, c_f64,
                               P, P, P, P, P, P]),
+    "f4l_patch_icp_ex": (c_int, [P, P, P, P, P, P, P, P, P, c_i32, P, c_f64, c_i32, c_f64, c_f64,
+                                 P, P, P, P, P, P, c_f64, P]),
     "f4l_peer_push": (c_int, [P, P, c_i32, ctypes.c_int64, P, c_i32, c_i32, P]),
     "f4l_fine_fit_tiles": (c_int, [P, P, P, c_i32, c_i32, P, P]),
     "f4l_desc_nn_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_int]),

@@ -81,7 +81,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
             const int32_t* __restrict__ kstart, const int32_t* __restrict__ K, int Q, f4l_fine_params prm,
             float* __restrict__ T32, double* __restrict__ T64, int8_t* __restrict__ status,
             double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
-            float* __restrict__ ratio_inlier, float* __restrict__ dist_mean) {
+            float* __restrict__ ratio_inlier, float* __restrict__ dist_mean, uint8_t* __restrict__ fragile) {
     extern __shared__ float dyn[];
     __shared__ FitShared sh;
     const int tid = threadIdx.x;
@@ -117,7 +117,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
                 T64q[tid] = v;
                 T32[(size_t)q * 16 + tid] = (float)v;
             }
-            if (tid == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
+            if (tid == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; if (fragile) fragile[q] = 0; }
             continue;
         }
         // D2: Procrustes on the matched pairs (weights None, eps 1e-6: weighted_svd.py:134-142)
@@ -135,7 +135,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
         }
         __syncthreads();
         IcpResult r;
-        r.fitness = 0; r.rmse = 0; r.iters = 0;
+        r.fitness = 0; r.rmse = 0; r.iters = 0; r.fragile = 0;
         if (prm.icp_refine) {
             // E1: ICP between the MATCHED points (base.py:3353-3358), init = T_svd
             r = block_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, sh.Tsvd, prm.icp_threshold, prm.icp_max_iter,
@@ -145,7 +145,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
         }
         __syncthreads();
         if (tid < 16) T32[(size_t)q * 16 + tid] = (float)T64q[tid];                                   // base.py:3366
-        if (tid == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+        if (tid == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; if (fragile) fragile[q] = (uint8_t)r.fragile; }
     }
 }
 
@@ -165,6 +165,7 @@ struct FitTile {
     const int32_t* cs; const int32_t* ct; const int32_t* kstart; const int32_t* K;
     float* T32; double* T64; int8_t* status; double* fitness; double* rmse; int32_t* iters;
     float* ratio_inlier; float* dist_mean;
+    uint8_t* fragile;
     int32_t Q;
 };
 
@@ -184,6 +185,7 @@ __device__ __forceinline__ void fit_pair_warp(const FitTile& tl, int q, const f4
     int32_t* __restrict__ iters = tl.iters;
     float* __restrict__ ratio_inlier = tl.ratio_inlier;
     float* __restrict__ dist_mean = tl.dist_mean;
+    uint8_t* __restrict__ fragile = tl.fragile;
     const int k0 = kstart[q], k = K[q];
     if (k > WICP_CAP) return;             // fitted by the CTA kernel
     __syncwarp();
@@ -218,7 +220,7 @@ __device__ __forceinline__ void fit_pair_warp(const FitTile& tl, int q, const f4
             T64q[lane] = v;
             T32[(size_t)q * 16 + lane] = (float)v;
         }
-        if (lane == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
+        if (lane == 0) { status[q] = (int8_t)st; fitness[q] = 0; rmse[q] = 0; iters[q] = 0; if (fragile) fragile[q] = 0; }
         return;
     }
     // D2: Procrustes (weights None, eps 1e-6)
@@ -237,7 +239,7 @@ __device__ __forceinline__ void fit_pair_warp(const FitTile& tl, int q, const f4
     Tsvd[12] = 0; Tsvd[13] = 0; Tsvd[14] = 0; Tsvd[15] = 1;
     DBG_T(9)
     IcpResult r;
-    r.fitness = 0; r.rmse = 0; r.iters = 0;
+    r.fitness = 0; r.rmse = 0; r.iters = 0; r.fragile = 0;
     if (prm.icp_refine) {
         r = warp_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, Tsvd, prm.icp_threshold, prm.icp_max_iter, 1e-6, 1e-6,
                      T64q, nullptr, sm, lane);
@@ -248,7 +250,7 @@ __device__ __forceinline__ void fit_pair_warp(const FitTile& tl, int q, const f4
     }
     __syncwarp();
     if (lane < 16) T32[(size_t)q * 16 + lane] = (float)T64q[lane];                                // base.py:3366
-    if (lane == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+    if (lane == 0) { status[q] = 0; fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; if (fragile) fragile[q] = (uint8_t)r.fragile; }
 #ifdef F4L_DEBUG_SCANS
     if (lane == 0) atomicAdd(&g_dbg[16], (unsigned long long)(clock64() - dbg_start));
 #endif
@@ -754,6 +756,7 @@ static FitTile fit_tile_of(const f4l_fine_buffers* bf, const FineWs& w) {
     t.cs = w.cs; t.ct = w.ct; t.kstart = w.kstart; t.K = bf->K;
     t.T32 = bf->T; t.T64 = bf->T64; t.status = bf->status; t.fitness = bf->fitness; t.rmse = bf->rmse; t.iters = bf->iters;
     t.ratio_inlier = bf->ratio_inlier; t.dist_mean = bf->dist_mean;
+    t.fragile = bf->icp_fragile;
     t.Q = bf->Q;
     return t;
 }
@@ -847,7 +850,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
         f4l_mark("k_patch_fit", st);
         k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
                                                             *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
-                                                            bf->iters, bf->ratio_inlier, bf->dist_mean);
+                                                            bf->iters, bf->ratio_inlier, bf->dist_mean, bf->icp_fragile);
     }
     if (phases & F4L_FINE_FINISH) {
         f4l_mark("k_row_offsets", st);

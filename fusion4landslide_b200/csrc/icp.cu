@@ -9,7 +9,7 @@ k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
             const uint8_t* __restrict__ seg_skip, int Q, const double* __restrict__ T0, double max_dist,
             int max_iter, double rel_fit, double rel_rmse, double* __restrict__ T,
             double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
-            int32_t* __restrict__ corr) {
+            int32_t* __restrict__ corr, uint8_t* __restrict__ fragile, double tie_eps) {
     extern __shared__ float pts[];
     __shared__ IcpShared sh;
     for (int q = blockIdx.x; q < Q; q += gridDim.x) {
@@ -25,13 +25,13 @@ k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
                 if (T0q) v = T0q[threadIdx.x];
                 T[(size_t)q * 16 + threadIdx.x] = v;
             }
-            if (threadIdx.x == 0) { fitness[q] = 0; rmse[q] = 0; iters[q] = 0; }
+            if (threadIdx.x == 0) { fitness[q] = 0; rmse[q] = 0; iters[q] = 0; if (fragile) fragile[q] = 0; }
             for (int i = threadIdx.x; corr && i < ns; i += ICP_THREADS) corr[s0 + i] = -1;
             continue;
         }
         IcpResult r = block_icp(src, src_idx, s0, ns, tgt, tgt_idx, t0, nt, T0q, max_dist, max_iter, rel_fit,
-                                rel_rmse, T + (size_t)q * 16, corr, pts, sh);
-        if (threadIdx.x == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+                                rel_rmse, T + (size_t)q * 16, corr, pts, sh, tie_eps);
+        if (threadIdx.x == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; if (fragile) fragile[q] = (uint8_t)r.fragile; }
         __syncthreads();
     }
 }
@@ -46,7 +46,7 @@ k_patch_icp_warp(const float* __restrict__ src, const int32_t* __restrict__ src_
                  const uint8_t* __restrict__ seg_skip, int Q, const double* __restrict__ T0, double max_dist,
                  int max_iter, double rel_fit, double rel_rmse, double* __restrict__ T,
                  double* __restrict__ fitness, double* __restrict__ rmse, int32_t* __restrict__ iters,
-                 int32_t* __restrict__ corr) {
+                 int32_t* __restrict__ corr, uint8_t* __restrict__ fragile, double tie_eps) {
     extern __shared__ __align__(16) unsigned char icpw_raw[];
     WarpIcpSmem* smem = reinterpret_cast<WarpIcpSmem*>(icpw_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -61,18 +61,19 @@ k_patch_icp_warp(const float* __restrict__ src, const int32_t* __restrict__ src_
         if (lane < 9) smem[wid].Vw[lane] = (lane % 4 == 0) ? 1.0 : 0.0;     // svd warm-start slot: cold for a new pair
         __syncwarp();
         IcpResult r = warp_icp(src, src_idx, s0, ns, tgt, tgt_idx, t0, nt, T0 ? T0 + (size_t)q * 16 : nullptr, max_dist,
-                               max_iter, rel_fit, rel_rmse, T + (size_t)q * 16, corr, smem[wid], lane);
-        if (lane == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; }
+                               max_iter, rel_fit, rel_rmse, T + (size_t)q * 16, corr, smem[wid], lane, tie_eps);
+        if (lane == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; if (fragile) fragile[q] = (uint8_t)r.fragile; }
     }
 }
 
-extern "C" int f4l_patch_icp(const float* src, const int32_t* src_idx, const int32_t* s_start,
-                             const int32_t* s_count, const float* tgt, const int32_t* tgt_idx,
-                             const int32_t* t_start, const int32_t* t_count, const uint8_t* seg_skip, int32_t Q,
-                             const double* T0, double max_corr_dist, int32_t max_iter, double rel_fitness,
-                             double rel_rmse, double* T, double* fitness, double* rmse, int32_t* iters,
-                             int32_t* corr, void* stream) {
+extern "C" int f4l_patch_icp_ex(const float* src, const int32_t* src_idx, const int32_t* s_start,
+                                const int32_t* s_count, const float* tgt, const int32_t* tgt_idx,
+                                const int32_t* t_start, const int32_t* t_count, const uint8_t* seg_skip, int32_t Q,
+                                const double* T0, double max_corr_dist, int32_t max_iter, double rel_fitness,
+                                double rel_rmse, double* T, double* fitness, double* rmse, int32_t* iters,
+                                int32_t* corr, uint8_t* fragile, double tie_eps, void* stream) {
     F4L_REQUIRE(Q >= 0, "Q < 0");
+    if (!(tie_eps > 0.0)) tie_eps = F4L_ICP_TIE_EPS;
     if (Q == 0) return F4L_OK;
     F4L_REQUIRE(src && tgt && s_start && t_start && T && fitness && rmse && iters, "null pointer");
     F4L_REQUIRE(max_corr_dist > 0.0, "max_correspondence_distance must be > 0 (Open3D raises too)");
@@ -89,13 +90,23 @@ extern "C" int f4l_patch_icp(const float* src, const int32_t* src_idx, const int
     f4l_mark("k_patch_icp_warp", (cudaStream_t)stream);
     k_patch_icp_warp<<<grid_w, ICPW_WARPS * 32, ICPW_WARPS * sizeof(WarpIcpSmem), (cudaStream_t)stream>>>(
         src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
-        rel_fitness, rel_rmse, T, fitness, rmse, iters, corr);
+        rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, fragile, tie_eps);
     const int grid = Q < 148 * 16 ? Q : 148 * 16;
     f4l_mark("k_patch_icp", (cudaStream_t)stream);
     k_patch_icp<<<grid, ICP_THREADS, smem, (cudaStream_t)stream>>>(
         src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
-        rel_fitness, rel_rmse, T, fitness, rmse, iters, corr);
+        rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, fragile, tie_eps);
     return f4l_finish("f4l_patch_icp", stream);
+}
+
+extern "C" int f4l_patch_icp(const float* src, const int32_t* src_idx, const int32_t* s_start,
+                             const int32_t* s_count, const float* tgt, const int32_t* tgt_idx,
+                             const int32_t* t_start, const int32_t* t_count, const uint8_t* seg_skip, int32_t Q,
+                             const double* T0, double max_corr_dist, int32_t max_iter, double rel_fitness,
+                             double rel_rmse, double* T, double* fitness, double* rmse, int32_t* iters,
+                             int32_t* corr, void* stream) {
+    return f4l_patch_icp_ex(src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist,
+                            max_iter, rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, nullptr, 0.0, stream);
 }
 
 // ------------------------------------------------------------------------------------------

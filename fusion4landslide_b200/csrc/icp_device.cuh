@@ -22,7 +22,20 @@ struct IcpShared {
 struct IcpResult {
     double fitness, rmse;
     int iters;
+    int fragile;   // OR of F4L_ICP_FRAGILE_*: a decision of the loop was within tie_eps of flipping
 };
+// Fragility of an ICP run (the tie[Q] of the boundary schema): the loop's result is a chain of discrete decisions; when one
+// of them is within a relative tie_eps of going the other way, an implementation with a different fp64 operation order
+// (Open3D's KD-tree + Eigen, the oracle) may take the other branch and end on a different, equally valid path.
+// F4L_ICP_FRAGILE_NN / _INLIER / _STOP: include/f4l_b200.h
+#define F4L_ICP_TIE_EPS 1e-9
+
+__device__ __forceinline__ int icp_stop_fragile(double prev_fit, double fit, double prev_rmse, double rmse, double rel_fit,
+                                                double rel_rmse, double tie_eps) {
+    const bool f = fabs(fabs(prev_fit - fit) - rel_fit) <= tie_eps;
+    const bool r = fabs(fabs(prev_rmse - rmse) - rel_rmse) <= tie_eps * fmax(fmax(prev_rmse, rmse), rel_rmse);
+    return (f || r) ? F4L_ICP_FRAGILE_STOP : 0;
+}
 
 // src/tgt: base arrays; sidx/tidx: optional gathers; items [s0,s0+ns) and [t0,t0+nt).
 // T0: 16 doubles row-major (or nullptr = identity).  Tout: 16 doubles.  corr (ns ints at s0) or
@@ -32,7 +45,7 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
                                       const int32_t* __restrict__ tidx, int t0, int nt,
                                       const double* T0, double max_dist, int max_iter, double rel_fit,
                                       double rel_rmse, double* Tout, int32_t* __restrict__ corr,
-                                      float* pts, IcpShared& sh) {
+                                      float* pts, IcpShared& sh, double tie_eps = F4L_ICP_TIE_EPS) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
     const bool staged = (ns + nt) <= ICP_SMEM_PTS;
@@ -59,7 +72,8 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
     __syncthreads();
 
     IcpResult out;
-    out.fitness = 0.0; out.rmse = 0.0; out.iters = 0;
+    out.fitness = 0.0; out.rmse = 0.0; out.iters = 0; out.fragile = 0;
+    int frag = 0;
     if (ns <= 0 || nt <= 0) {
         if (tid < 16) Tout[tid] = tid < 12 ? sh.T[tid] : (tid == 15 ? 1.0 : 0.0);
         for (int i = tid; corr && i < ns; i += ICP_THREADS) corr[s0 + i] = -1;
@@ -91,7 +105,7 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
             const double px = T[0] * fx + T[1] * fy + T[2] * fz + T[3];
             const double py = T[4] * fx + T[5] * fy + T[6] * fz + T[7];
             const double pz = T[8] * fx + T[9] * fy + T[10] * fz + T[11];
-            double best = INFINITY;
+            double best = INFINITY, second = INFINITY;     // second: nearest target with other coordinates than the winner
             int bj = -1;
             double bx = 0, by = 0, bz = 0;
             for (int j = 0; j < nt; ++j) {
@@ -100,10 +114,13 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
                 else load_ptf(tgt, tidx, t0 + j, gx, gy, gz);
                 const double dx = px - (double)gx, dy = py - (double)gy, dz = pz - (double)gz;
                 const double d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 < best) { best = d2; bj = j; bx = gx; by = gy; bz = gz; }
+                if (d2 < best) { second = best; best = d2; bj = j; bx = gx; by = gy; bz = gz; }
+                else if (d2 < second && !(d2 == best && (double)gx == bx && (double)gy == by && (double)gz == bz)) second = d2;
             }
             const bool ok = best < max_d2;     // strict, as the hybrid search of Open3D
             if (corr) corr[s0 + i] = ok ? bj : -1;
+            if (fabs(best - max_d2) <= tie_eps * max_d2) frag |= F4L_ICP_FRAGILE_INLIER;
+            if (ok && second - best <= tie_eps * best) frag |= F4L_ICP_FRAGILE_NN;
             if (ok) {
                 err2 += best;
                 cnt += 1.0;
@@ -137,6 +154,7 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
             sh.rmse = rmse;
             bool stop = false;
             if (it > 0 && fabs(prev_fit - fit) < rel_fit && fabs(prev_rmse - rmse) < rel_rmse) stop = true;
+            if (it > 0 && it < max_iter) frag |= icp_stop_fragile(prev_fit, fit, prev_rmse, rmse, rel_fit, rel_rmse, tie_eps);
             if (it >= max_iter) stop = true;
             if (!stop) {
                 // U = umeyama(P[corr], tgt[corr]);  T <- U T
@@ -165,6 +183,8 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
     }
     out.fitness = sh.fitness;
     out.rmse = sh.rmse;
+    // __syncthreads_or is a logical OR of predicates: one round per flag bit
+    out.fragile = (__syncthreads_or(frag & 1) ? 1 : 0) | (__syncthreads_or(frag & 2) ? 2 : 0) | (__syncthreads_or(frag & 4) ? 4 : 0);
     if (tid < 16) Tout[tid] = tid < 12 ? sh.T[tid] : (tid == 15 ? 1.0 : 0.0);
     return out;
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ void warp_top2_f64(double& d1, int& j1, double& d2) {
 // and a lower bound of the distance to the second nearest distinct target.  Only queries whose f32 scan could
 // not separate its two best candidates come here.
 __device__ inline void warp_scan_point(const WarpIcpSmem& sm, int nt, const double pg[3], int lane, int& jbest,
-                                       float& d2lb) {
+                                       float& d2lb, double& d2_best, double& d2_second) {
 #ifdef F4L_DEBUG_SCANS
     if (lane == 0) atomicAdd(&g_dbg[1], 1ull);
 #endif
@@ -134,6 +134,8 @@ __device__ inline void warp_scan_point(const WarpIcpSmem& sm, int nt, const doub
         warp_argmin_f64(e2, k2);
     }
     jbest = k1;
+    d2_best = e1;
+    d2_second = e2;          // nearest target with other coordinates than the winner
     d2lb = (e2 == INFINITY) ? INFINITY : fmaxf((float)(sqrt(e2) * (1.0 - 1e-7)) - 1e-7f, 0.f);
 }
 
@@ -142,7 +144,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
                                      int ns, const float* __restrict__ tgt, const int32_t* __restrict__ tidx,
                                      int t0, int nt, const double* T0, double max_dist, int max_iter,
                                      double rel_fit, double rel_rmse, double* Tout, int32_t* __restrict__ corr,
-                                     WarpIcpSmem& sm, int lane) {
+                                     WarpIcpSmem& sm, int lane, double tie_eps = F4L_ICP_TIE_EPS) {
     DBG_T0
     // ---- stage ------------------------------------------------------------------------------
     double cB[3];
@@ -223,7 +225,8 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
     DBG_T(10)
     const double max_d2 = max_dist * max_dist;
     IcpResult out;
-    out.fitness = 0; out.rmse = 0; out.iters = 0;
+    out.fitness = 0; out.rmse = 0; out.iters = 0; out.fragile = 0;
+    int frag = 0;            // lane-local until the end
     double prev_fit = 0.0, prev_rmse = 0.0;
     for (int it = 0;; ++it) {
         // ---- phase 1: which points need a scan -------------------------------------------
@@ -324,7 +327,11 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
             pg[2] = T[8] * fx + T[9] * fy + T[10] * fz + T[11];
             int jb;
             float lb;
-            warp_scan_point(sm, nt, pg, lane, jb, lb);
+            double e1, e2;
+            warp_scan_point(sm, nt, pg, lane, jb, lb, e1, e2);
+            // points whose f32 scan separated the two best candidates (factor 1.004) or that kept their neighbour by the
+            // triangle inequality (margin 1e-5) are far from a tie: only the exact path can see one
+            if (e1 < max_d2 && e2 - e1 <= tie_eps * e1) frag |= F4L_ICP_FRAGILE_NN;
             if (lane == 0) {
                 sm.jstar[i] = (unsigned short)jb;
                 sm.d2lb[i] = lb;
@@ -348,6 +355,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
             const double d2 = dx * dx + dy * dy + dz * dz;
             const bool ok = d2 < max_d2;
             if (corr) corr[s0 + i] = ok ? j : -1;
+            if (fabs(d2 - max_d2) <= tie_eps * max_d2) frag |= F4L_ICP_FRAGILE_INLIER;
             if (ok) {
                 err2 += d2;
                 cnt += 1.0;
@@ -363,6 +371,7 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
         out.rmse = rmse;
         bool stop = false;
         if (it > 0 && fabs(prev_fit - fit) < rel_fit && fabs(prev_rmse - rmse) < rel_rmse) stop = true;
+        if (it > 0 && it < max_iter) frag |= icp_stop_fragile(prev_fit, fit, prev_rmse, rmse, rel_fit, rel_rmse, tie_eps);
         if (it >= max_iter) stop = true;
         DBG_T(14)
         if (stop) {
@@ -388,6 +397,9 @@ __device__ inline IcpResult warp_icp(const float* __restrict__ src, const int32_
     for (int a = 0; a < 12; ++a)
         if (lane == a) Tout[a] = T[a];
     if (lane >= 12 && lane < 16) Tout[lane] = lane == 15 ? 1.0 : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) frag |= __shfl_xor_sync(F4L_FULL, frag, o);
+    out.fragile = frag;
     return out;
 }
 

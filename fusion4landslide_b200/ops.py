@@ -118,8 +118,10 @@ def knn_ties(q, r, k, eps_rel=1e-6, max_radius=0.0, cell=0.0):
 
 def patch_icp(src, tgt, s_start, t_start, s_count=None, t_count=None, src_idx=None, tgt_idx=None,
               T0=None, max_corr_dist=0.1, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6, seg_skip=None,
-              want_corr=False):
-    """K-e.  Returns T (Q,4,4) f64, fitness (Q) f64, rmse (Q) f64, iters (Q) i32, [corr (items) i32]."""
+              want_corr=False, want_fragile=False, tie_eps=None):
+    """K-e.  Returns T (Q,4,4) f64, fitness (Q) f64, rmse (Q) f64, iters (Q) i32, [corr (items) i32],
+    [fragile (Q) u8: OR of FRAGILE_NN / FRAGILE_INLIER / FRAGILE_STOP -- a decision of the loop was within tie_eps
+    (default 1e-9, relative) of flipping, include/f4l_b200.h f4l_patch_icp_ex]."""
     Q = s_start.numel() if s_count is not None else s_start.numel() - 1
     T = _empty((Q, 4, 4), F64, src)
     fit = _empty((Q,), F64, src)
@@ -129,14 +131,23 @@ def patch_icp(src, tgt, s_start, t_start, s_count=None, t_count=None, src_idx=No
     corr = _empty((n_items,), I32, src) if want_corr else None
     if T0 is not None:
         T0 = T0.reshape(Q, 16)
-    check(lib().f4l_patch_icp(
+    fragile = _empty((Q,), torch.uint8, src) if want_fragile else None
+    check(lib().f4l_patch_icp_ex(
         ptr(src, F32), ptr(src_idx, I32, True), ptr(s_start, I32), ptr(s_count, I32, True),
         ptr(tgt, F32), ptr(tgt_idx, I32, True), ptr(t_start, I32), ptr(t_count, I32, True),
         ptr(seg_skip, torch.uint8, True), Q, ptr(T0, F64, True), float(max_corr_dist), int(max_iter),
         float(rel_fitness), float(rel_rmse), ptr(T), ptr(fit), ptr(rmse), ptr(iters),
-        ptr(corr, I32, True), stream_ptr(src.device)), "f4l_patch_icp")
+        ptr(corr, I32, True), ptr(fragile, torch.uint8, True), float(tie_eps or 0.0), stream_ptr(src.device)),
+        "f4l_patch_icp_ex")
     out = (T, fit, rmse, iters)
-    return out + (corr,) if want_corr else out
+    if want_corr:
+        out = out + (corr,)
+    if want_fragile:
+        out = out + (fragile,)
+    return out
+
+
+FRAGILE_NN, FRAGILE_INLIER, FRAGILE_STOP = 1, 2, 4
 
 
 def segmented_nn(qpts, rpts, q_start, r_start, q_count=None, r_count=None, qidx=None, ridx=None,
@@ -298,7 +309,7 @@ def piecewise_icp(src64, tgt64, smax, number_points_min, internal_min_points=250
 class FineResult:
     """Outputs of the fused fine-matching stage (device tensors; row counts in `counts`)."""
     __slots__ = ("T", "T64", "status", "K", "fitness", "rmse", "iters", "ratio_inlier", "dist_mean",
-                 "dense", "sparse", "tgt2src", "counts", "sparse_pair_rows")
+                 "dense", "sparse", "tgt2src", "counts", "sparse_pair_rows", "icp_fragile")
 
     def rows(self):
         """Host sync: slice the row buffers to their true lengths (dense, sparse, tgt2src)."""
@@ -360,6 +371,7 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
         r.tgt2src = torch.empty((n_tgt_items, 6), dtype=F32, device=dev) if output_tgt2src else None
         r.counts = torch.empty((4,), dtype=I32, device=dev)
         r.sparse_pair_rows = torch.empty((Q,), dtype=I32, device=dev) if assign_type == "assign_then_nn_once" else None
+        r.icp_fragile = torch.empty((Q,), dtype=torch.uint8, device=dev)
     prm = _lib.FineParams(_MODES[mode], int(remove_low_quality_patch_matches), int(num_min_matches_for_quality_check),
                           float(thres_dist_diff), float(thres_inlier_ratio), int(num_min_fine_match), int(icp_refine),
                           _ASSIGN[assign_type], int(output_tgt2src), float(icp_threshold),
@@ -379,6 +391,9 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
     spr = getattr(r, "sparse_pair_rows", None)
     if spr is not None:
         bf.sparse_pair_rows = ptr(spr, I32)
+    frag = getattr(r, "icp_fragile", None)
+    if frag is not None:
+        bf.icp_fragile = ptr(frag, torch.uint8)
     if peer_dense:
         if len(peer_dense) > _lib.MAX_PEERS:
             raise _lib.F4LError("at most %d peers" % _lib.MAX_PEERS)

@@ -170,6 +170,23 @@ F4L_API int f4l_patch_icp(const float* src, const int32_t* src_idx, const int32_
                   double rel_fitness, double rel_rmse, double* T, double* fitness, double* rmse,
                   int32_t* iters, int32_t* corr, void* stream);
 
+/* The same with the tie[Q] flag of the boundary schema: fragile (Q) u8 or NULL = OR of
+ *   F4L_ICP_FRAGILE_NN     a matched source point had a DISTINCT target within tie_eps (relative, squared distance) of
+ *                          its nearest one in some iteration (Open3D's KD-tree may return either);
+ *   F4L_ICP_FRAGILE_INLIER a nearest distance within tie_eps of max_corr_dist^2 (strict `<`, o3d hybrid search);
+ *   F4L_ICP_FRAGILE_STOP   |delta fitness| or |delta rmse| within tie_eps of the convergence thresholds.
+ * An implementation with another fp64 operation order can leave the path of this one only at such a decision: parity
+ * tests assert "same iteration count and transform except for flagged pairs".  tie_eps <= 0: 1e-9. */
+#define F4L_ICP_FRAGILE_NN 1
+#define F4L_ICP_FRAGILE_INLIER 2
+#define F4L_ICP_FRAGILE_STOP 4
+F4L_API int f4l_patch_icp_ex(const float* src, const int32_t* src_idx, const int32_t* s_start,
+                     const int32_t* s_count, const float* tgt, const int32_t* tgt_idx,
+                     const int32_t* t_start, const int32_t* t_count, const uint8_t* seg_skip,
+                     int32_t Q, const double* T0, double max_corr_dist, int32_t max_iter,
+                     double rel_fitness, double rel_rmse, double* T, double* fitness, double* rmse,
+                     int32_t* iters, int32_t* corr, uint8_t* fragile, double tie_eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * The fused fine-matching stage for one tile (all patch pairs in one launch sequence).
  * Replaces base.py:3236-3457 fine_matching_with_different_types:
@@ -232,6 +249,8 @@ typedef struct f4l_fine_buffers {
     int32_t phases;              /* 0 = the whole stage; else an OR of F4L_FINE_*: a caller that fits the small pairs of
                                     many tiles in one launch (f4l_fine_fit_tiles) runs SELECT, then that, then
                                     FIT_LARGE | FINISH on the same buffers and workspace */
+    uint8_t* icp_fragile;        /* (Q) or NULL: OR of F4L_ICP_FRAGILE_* per fitted pair (0 for the others), tie_eps 1e-9 --
+                                    the tie[Q] flag of f4l_patch_icp_ex for the fused stage */
 } f4l_fine_buffers;
 
 #define F4L_FINE_SELECT 1      /* F2: correspondence selection                       (k_select_corr) */

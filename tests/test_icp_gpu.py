@@ -107,6 +107,80 @@ def test_patch_icp_skip_and_limits(cuda):
         ops.patch_icp(src, tgt, ptr, ptr, max_corr_dist=0.0)
 
 
+def _crafted_fragile_cases():
+    """(source, target, max_dist, expected flag bit) -- exact in f32, so the decisions really sit ON the boundary."""
+    rng = np.random.default_rng(11)
+    base = (rng.integers(0, 64, size=(40, 3)) * 0.25).astype(np.float32)          # a rigid, well separated cloud
+    cases = []
+    # (a) one source point exactly midway between two DISTINCT targets (identity start, exact match elsewhere)
+    a = np.concatenate([base, [[100.0, 0.0, 0.0]]]).astype(np.float32)
+    b = np.concatenate([base, [[99.5, 0.0, 0.0], [100.5, 0.0, 0.0]]]).astype(np.float32)
+    cases.append((a, b, 1.0, 1))
+    # (b) a nearest distance exactly equal to max_correspondence_distance (strict `<`: rejected, by a hair)
+    a = np.concatenate([base, [[100.0, 0.0, 0.0]]]).astype(np.float32)
+    b = np.concatenate([base, [[100.5, 0.0, 0.0]]]).astype(np.float32)
+    cases.append((a, b, 0.5, 2))
+    # (c) duplicates of the winner are NOT a tie (same coordinates: the transform cannot depend on which one is taken)
+    a = base.copy()
+    b = np.concatenate([base, base[:7]]).astype(np.float32)
+    cases.append((a, b, 1.0, 0))
+    return cases
+
+
+@pytest.mark.parametrize("pad", [0, 300])     # 300 extra far-away targets push the pair onto the CTA kernel (> 224 points)
+def test_patch_icp_fragile_flags_crafted(cuda, pad):
+    from fusion4landslide_b200 import ops
+    A_list, B_list, want = [], [], []
+    far = (np.arange(pad, dtype=np.float32)[:, None] * np.array([[0.0, 3.0, 0.0]], np.float32) + np.array([[0, 1000, 0]], np.float32))
+    for a, b, md, bit in _crafted_fragile_cases():
+        A_list.append(a)
+        B_list.append(np.concatenate([b, far]).astype(np.float32) if pad else b)
+        want.append((md, bit))
+    for (md, bit), a, b in zip(want, A_list, B_list):
+        src, tgt = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+        sp = torch.tensor([0, len(a)], dtype=torch.int32, device=cuda)
+        tp = torch.tensor([0, len(b)], dtype=torch.int32, device=cuda)
+        out = ops.patch_icp(src, tgt, sp, tp, max_corr_dist=md, want_fragile=True)
+        flag = int(out[-1].item())
+        if bit:
+            assert flag & bit, (md, bit, flag)
+        else:
+            assert flag & 3 == 0, (md, bit, flag)
+
+
+def test_patch_icp_path_flips_only_on_fragile_pairs(cuda):
+    """The tie[Q] contract: a pair whose ICP path differs from the fp64 restatement must carry the flag (the converse does
+    not hold -- most fragile decisions still go the same way)."""
+    from fusion4landslide_b200 import ops
+    d, (ptr_s, idx_s), (ptr_t, idx_t), m, j = _tile_patches(n_pts=80_000, seed=5)
+    A_list, B_list = [], []
+    for a, b in zip(m.tolist()[:250], j.tolist()[:250]):
+        ps = idx_s[ptr_s[a]:ptr_s[a + 1]].numpy()
+        pt = idx_t[ptr_t[b]:ptr_t[b + 1]].numpy()
+        A, B = _matched(d, ps, pt)
+        if A.shape[0] >= 10:
+            A_list.append(A)
+            B_list.append(B)
+    Q = len(A_list)
+    sptr = np.zeros(Q + 1, np.int32)
+    sptr[1:] = np.cumsum([len(a) for a in A_list])
+    src = torch.from_numpy(np.concatenate(A_list)).to(cuda)
+    tgt = torch.from_numpy(np.concatenate(B_list)).to(cuda)
+    dptr = torch.from_numpy(sptr).to(cuda)
+    T, fit, rmse, iters, fragile = ops.patch_icp(src, tgt, dptr, dptr, max_corr_dist=0.1, want_fragile=True)
+    iters, fit, fragile = iters.cpu().numpy(), fit.cpu().numpy(), fragile.cpu().numpy()
+    n_flip = 0
+    for q in range(Q):
+        o = oicp.icp_point_to_point(A_list[q], B_list[q], None, 0.1)
+        if 0 < o["min_ncorr"] < 4 or (o["min_ncorr"] > 0 and o["min_sv_ratio"] < 1e-6):
+            continue
+        if not (iters[q] == o["iters"] and abs(fit[q] - o["fitness"]) < 1e-12):
+            n_flip += 1
+            assert fragile[q] != 0, "pair %d left the oracle's path without a fragility flag" % q
+    print("icp fragility: %d pairs, %d flagged, %d path flips" % (Q, int((fragile != 0).sum()), n_flip))
+    assert (fragile != 0).mean() < 0.2
+
+
 def test_segmented_nn_vs_oracle(cuda):
     from fusion4landslide_b200 import ops
     d, (ptr_s, idx_s), (ptr_t, idx_t), m, j = _tile_patches(n_pts=40_000, seed=22)
