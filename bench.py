@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--c2f-threads", type=int, default=2, help="C3 / C4: host threads (one CUDA stream each) the tiles are spread over")
     ap.add_argument("--streams", type=int, default=4, help="side streams for tile-level concurrency (1 = serial)")
     ap.add_argument("--workload", default="c5", choices=["c5", "dips"],
                     help="c5: the headline hot path (default).  dips: the DIPs patch front-end of SURVEY 8(f) rank 1 "
@@ -979,14 +980,43 @@ def bench_c2f(a, dev, L, peaks, fusion):
         c.implement_c2f_matching()
         return c
 
+    # Tiles are independent: `--c2f-threads` host threads take them round-robin, each on its own CUDA stream, so the host side
+    # of one tile (list / mask bookkeeping of the class path, a few row-count syncs) overlaps the kernels of another
+    n_thr = max(1, min(int(a.c2f_threads), n_tiles))
+    wstreams = [torch.cuda.Stream(device=dev) for _ in range(n_thr)] if n_thr > 1 else []
+    pool = None
+    if n_thr > 1:
+        import concurrent.futures
+        pool = concurrent.futures.ThreadPoolExecutor(max_workers=n_thr)
+
+    def worker(w, cur):
+        torch.cuda.set_device(dev)
+        rows, c = 0, None
+        with torch.cuda.stream(wstreams[w]):
+            wstreams[w].wait_stream(cur)
+            for tt in tiles[w::n_thr]:
+                c = run_tile(tt)
+                rows += int(c.data_output.corres_3d_refine_apply_icp.shape[0])
+        return rows, c
+
     def step():
         rows = 0
+        if n_thr > 1:
+            cur = torch.cuda.current_stream(dev)
+            res_w = [f.result() for f in [pool.submit(worker, w, cur) for w in range(n_thr)]]
+            for s_ in wstreams:
+                cur.wait_stream(s_)
+            rows = sum(r_[0] for r_ in res_w)
+            last["c"] = res_w[(n_tiles - 1) % n_thr][1]        # the worker that ran tiles[-1]
+            return rows
         for tt in tiles:
             c = run_tile(tt)
             rows += int(c.data_output.corres_3d_refine_apply_icp.shape[0])
             last["c"] = c
         return rows
     ms, rows = _timed(step, 1, a.config_steps, dev)
+    if pool is not None:
+        pool.shutdown()
     kern, launches = _profiled(lambda: run_tile(tiles[0]), L, dev)
     c = last["c"]
     n_sub = int(c.data_interim.src_pts_sub.shape[0]), int(c.data_interim.tgt_pts_sub.shape[0])
@@ -1000,6 +1030,7 @@ def bench_c2f(a, dev, L, peaks, fusion):
                         " + 2D vote (B4)" if fusion else ""),
            "metric": METRIC, "unit": UNIT, "value": rows / (ms * 1e-3), "src_points_per_sec": n * n_tiles / (ms * 1e-3),
            "ms_per_step": ms, "steps": a.config_steps, "dvf_points_per_step": rows, "src_points_per_step": n * n_tiles,
+           "host_threads": n_thr,
            "dtype": "fp16 tensor-core candidates + f64 re-rank (descriptor NN), f32 i/o + f64 accumulation (fits)",
            "gpu_launches_per_tile": launches, "voxels_per_tile": list(n_sub),
            "pairs_per_level_last_tile": [len(x) for x in c.data_output.spt_corres_src_multiple],

@@ -105,6 +105,35 @@ def test_fused_push_to_other_device_one_process(cuda):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_kernels_on_second_device_after_first_one_process(cuda):
+    """The opt-ins to > 48 KB of dynamic shared memory (fit, apply + assign, ICP, K-d, DIPs kernels) are per device: a
+    process that has computed on cuda:0 must get the same results on cuda:1 (round-1 advisor finding: a process-wide
+    flag skipped the opt-in on the second device and the launch failed with `invalid argument`)."""
+    from fusion4landslide_b200 import ops, pipeline
+    tile0 = _tile(cuda)
+    r0, med0 = pipeline.displacement_field(tile0)
+    g = torch.Generator().manual_seed(3)
+    src = torch.rand((5000, 3), generator=g) * 10
+    tgt = src + 0.01 * torch.randn((5000, 3), generator=g)
+    ptr = torch.arange(0, 5001, 250, dtype=torch.int32)
+    R0, t0, _ = ops.segmented_kabsch(src.to(cuda), tgt.to(cuda), ptr.to(cuda))
+    T0, f0, _, i0 = ops.patch_icp(src.to(cuda), tgt.to(cuda), ptr.to(cuda), ptr.to(cuda), max_corr_dist=0.1)
+    torch.cuda.synchronize(0)
+    dev1 = torch.device("cuda:1")
+    with torch.cuda.device(1):
+        tile1 = _tile(dev1)
+        r1, med1 = pipeline.displacement_field(tile1)
+        R1, t1, _ = ops.segmented_kabsch(src.to(dev1), tgt.to(dev1), ptr.to(dev1))
+        T1, f1, _, i1 = ops.patch_icp(src.to(dev1), tgt.to(dev1), ptr.to(dev1), ptr.to(dev1), max_corr_dist=0.1)
+        torch.cuda.synchronize(1)
+    n = int(r0.counts[0])
+    assert n > 1000 and int(r1.counts[0]) == n
+    assert torch.equal(r1.dense[:n].cpu(), r0.dense[:n].cpu()) and float(med0) == float(med1)
+    assert torch.equal(R1.cpu(), R0.cpu()) and torch.equal(t1.cpu(), t0.cpu())
+    assert torch.equal(T1.cpu(), T0.cpu()) and torch.equal(i1.cpu(), i0.cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_peer_exchange_two_processes():
     """torchrun x2: every rank's field must hold both ranks' dense rows (tools/check_exchange.py)."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
