@@ -75,6 +75,7 @@ struct FitShared {
     int decision;
 };
 
+template <bool FRAG>
 __global__ void __launch_bounds__(ICP_THREADS)
 k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts,
             const int32_t* __restrict__ cs, const int32_t* __restrict__ ct,
@@ -138,7 +139,7 @@ k_patch_fit(const float* __restrict__ src_pts, const float* __restrict__ tgt_pts
         r.fitness = 0; r.rmse = 0; r.iters = 0; r.fragile = 0;
         if (prm.icp_refine) {
             // E1: ICP between the MATCHED points (base.py:3353-3358), init = T_svd
-            r = block_icp(src_pts, cs, k0, k, tgt_pts, ct, k0, k, sh.Tsvd, prm.icp_threshold, prm.icp_max_iter,
+            r = block_icp<FRAG>(src_pts, cs, k0, k, tgt_pts, ct, k0, k, sh.Tsvd, prm.icp_threshold, prm.icp_max_iter,
                           1e-6, 1e-6, T64q, nullptr, dyn, sh.icp);
         } else if (tid < 16) {
             T64q[tid] = sh.Tsvd[tid];
@@ -741,7 +742,8 @@ extern "C" size_t f4l_fine_matching_workspace_bytes(int32_t n_src_items, int32_t
 static bool fine_optin() {
     static F4lPerDevice once;
     if (once.done()) return true;
-    if (!f4l_optin_smem(k_patch_fit, (size_t)ICP_SMEM_PTS * 3 * sizeof(float), "k_patch_fit") ||
+    if (!f4l_optin_smem(k_patch_fit<false>, (size_t)ICP_SMEM_PTS * 3 * sizeof(float), "k_patch_fit") ||
+        !f4l_optin_smem(k_patch_fit<true>, (size_t)ICP_SMEM_PTS * 3 * sizeof(float), "k_patch_fit") ||
         !f4l_optin_smem(k_apply_assign, (size_t)AA_SMEM_PTS * sizeof(float4), "k_apply_assign") ||
         !f4l_optin_smem(k_patch_fit_warp, FITW_WARPS * sizeof(WarpIcpSmem), "k_patch_fit_warp") ||
         !f4l_optin_smem(k_patch_fit_warp_tiles, FITW_WARPS * sizeof(WarpIcpSmem), "k_patch_fit_warp_tiles"))
@@ -848,9 +850,14 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
     if (phases & F4L_FINE_FIT_LARGE) {
         const int grid_fit = Q < 148 * 16 ? Q : 148 * 16;
         f4l_mark("k_patch_fit", st);
-        k_patch_fit<<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
-                                                            *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
-                                                            bf->iters, bf->ratio_inlier, bf->dist_mean, bf->icp_fragile);
+        if (bf->icp_fragile)
+            k_patch_fit<true><<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
+                                                                      *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
+                                                                      bf->iters, bf->ratio_inlier, bf->dist_mean, bf->icp_fragile);
+        else
+            k_patch_fit<false><<<grid_fit, ICP_THREADS, smem_fit, st>>>(bf->src_pts, bf->tgt_pts, w.cs, w.ct, w.kstart, bf->K, Q,
+                                                                       *prm, bf->T, bf->T64, bf->status, bf->fitness, bf->rmse,
+                                                                       bf->iters, bf->ratio_inlier, bf->dist_mean, nullptr);
     }
     if (phases & F4L_FINE_FINISH) {
         f4l_mark("k_row_offsets", st);

@@ -1,6 +1,7 @@
 // K-e per-patch ICP (standalone entry point) and the segmented 1-NN used by assign_then_nn.
 #include "icp_warp.cuh"
 
+template <bool FRAG>
 __global__ void __launch_bounds__(ICP_THREADS)
 k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
             const int32_t* __restrict__ s_start, const int32_t* __restrict__ s_count,
@@ -29,7 +30,7 @@ k_patch_icp(const float* __restrict__ src, const int32_t* __restrict__ src_idx,
             for (int i = threadIdx.x; corr && i < ns; i += ICP_THREADS) corr[s0 + i] = -1;
             continue;
         }
-        IcpResult r = block_icp(src, src_idx, s0, ns, tgt, tgt_idx, t0, nt, T0q, max_dist, max_iter, rel_fit,
+        IcpResult r = block_icp<FRAG>(src, src_idx, s0, ns, tgt, tgt_idx, t0, nt, T0q, max_dist, max_iter, rel_fit,
                                 rel_rmse, T + (size_t)q * 16, corr, pts, sh, tie_eps);
         if (threadIdx.x == 0) { fitness[q] = r.fitness; rmse[q] = r.rmse; iters[q] = r.iters; if (fragile) fragile[q] = (uint8_t)r.fragile; }
         __syncthreads();
@@ -82,7 +83,7 @@ extern "C" int f4l_patch_icp_ex(const float* src, const int32_t* src_idx, const 
     static F4lPerDevice once;
     if (!once.done()) {
         if (!f4l_optin_smem(k_patch_icp_warp, ICPW_WARPS * sizeof(WarpIcpSmem), "k_patch_icp_warp") ||
-            !f4l_optin_smem(k_patch_icp, smem, "k_patch_icp"))
+            !f4l_optin_smem(k_patch_icp<false>, smem, "k_patch_icp") || !f4l_optin_smem(k_patch_icp<true>, smem, "k_patch_icp"))
             return F4L_E_CUDA;
         once.mark();
     }
@@ -93,9 +94,14 @@ extern "C" int f4l_patch_icp_ex(const float* src, const int32_t* src_idx, const 
         rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, fragile, tie_eps);
     const int grid = Q < 148 * 16 ? Q : 148 * 16;
     f4l_mark("k_patch_icp", (cudaStream_t)stream);
-    k_patch_icp<<<grid, ICP_THREADS, smem, (cudaStream_t)stream>>>(
-        src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
-        rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, fragile, tie_eps);
+    if (fragile)
+        k_patch_icp<true><<<grid, ICP_THREADS, smem, (cudaStream_t)stream>>>(
+            src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
+            rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, fragile, tie_eps);
+    else
+        k_patch_icp<false><<<grid, ICP_THREADS, smem, (cudaStream_t)stream>>>(
+            src, src_idx, s_start, s_count, tgt, tgt_idx, t_start, t_count, seg_skip, Q, T0, max_corr_dist, max_iter,
+            rel_fitness, rel_rmse, T, fitness, rmse, iters, corr, fragile, tie_eps);
     return f4l_finish("f4l_patch_icp", stream);
 }
 

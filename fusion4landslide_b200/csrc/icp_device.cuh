@@ -40,6 +40,9 @@ __device__ __forceinline__ int icp_stop_fragile(double prev_fit, double fit, dou
 // src/tgt: base arrays; sidx/tidx: optional gathers; items [s0,s0+ns) and [t0,t0+nt).
 // T0: 16 doubles row-major (or nullptr = identity).  Tout: 16 doubles.  corr (ns ints at s0) or
 // nullptr.  pts: dynamic shared memory of 3*ICP_SMEM_PTS floats.
+// FRAG: also track the nearest target with other coordinates than the winner and set IcpResult::fragile (one more
+// compare per candidate in the exhaustive loop: +45 % on this kernel, so only callers that asked for the flag pay it).
+template <bool FRAG>
 __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32_t* __restrict__ sidx,
                                       int s0, int ns, const float* __restrict__ tgt,
                                       const int32_t* __restrict__ tidx, int t0, int nt,
@@ -114,13 +117,13 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
                 else load_ptf(tgt, tidx, t0 + j, gx, gy, gz);
                 const double dx = px - (double)gx, dy = py - (double)gy, dz = pz - (double)gz;
                 const double d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 < best) { second = best; best = d2; bj = j; bx = gx; by = gy; bz = gz; }
-                else if (d2 < second && !(d2 == best && (double)gx == bx && (double)gy == by && (double)gz == bz)) second = d2;
+                if (d2 < best) { if (FRAG) second = best; best = d2; bj = j; bx = gx; by = gy; bz = gz; }
+                else if (FRAG && d2 < second && !(d2 == best && (double)gx == bx && (double)gy == by && (double)gz == bz)) second = d2;
             }
             const bool ok = best < max_d2;     // strict, as the hybrid search of Open3D
             if (corr) corr[s0 + i] = ok ? bj : -1;
-            if (fabs(best - max_d2) <= tie_eps * max_d2) frag |= F4L_ICP_FRAGILE_INLIER;
-            if (ok && second - best <= tie_eps * best) frag |= F4L_ICP_FRAGILE_NN;
+            if (FRAG && fabs(best - max_d2) <= tie_eps * max_d2) frag |= F4L_ICP_FRAGILE_INLIER;
+            if (FRAG && ok && second - best <= tie_eps * best) frag |= F4L_ICP_FRAGILE_NN;
             if (ok) {
                 err2 += best;
                 cnt += 1.0;
@@ -154,7 +157,7 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
             sh.rmse = rmse;
             bool stop = false;
             if (it > 0 && fabs(prev_fit - fit) < rel_fit && fabs(prev_rmse - rmse) < rel_rmse) stop = true;
-            if (it > 0 && it < max_iter) frag |= icp_stop_fragile(prev_fit, fit, prev_rmse, rmse, rel_fit, rel_rmse, tie_eps);
+            if (FRAG && it > 0 && it < max_iter) frag |= icp_stop_fragile(prev_fit, fit, prev_rmse, rmse, rel_fit, rel_rmse, tie_eps);
             if (it >= max_iter) stop = true;
             if (!stop) {
                 // U = umeyama(P[corr], tgt[corr]);  T <- U T
@@ -184,7 +187,8 @@ __device__ inline IcpResult block_icp(const float* __restrict__ src, const int32
     out.fitness = sh.fitness;
     out.rmse = sh.rmse;
     // __syncthreads_or is a logical OR of predicates: one round per flag bit
-    out.fragile = (__syncthreads_or(frag & 1) ? 1 : 0) | (__syncthreads_or(frag & 2) ? 2 : 0) | (__syncthreads_or(frag & 4) ? 4 : 0);
+    if (FRAG)
+        out.fragile = (__syncthreads_or(frag & 1) ? 1 : 0) | (__syncthreads_or(frag & 2) ? 2 : 0) | (__syncthreads_or(frag & 4) ? 4 : 0);
     if (tid < 16) Tout[tid] = tid < 12 ? sh.T[tid] : (tid == 15 ? 1.0 : 0.0);
     return out;
 }

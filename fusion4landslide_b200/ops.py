@@ -344,7 +344,7 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
                  num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
                  output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
                  d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None,
-                 peer_dense=None, median_event=None, own_workspace=False):
+                 peer_dense=None, median_event=None, own_workspace=False, want_fragile=False):
     """Builds the FineCall of one tile (see fine_matching for the arguments).  own_workspace: allocate a workspace that
     belongs to this call (needed when the phases of several tiles interleave: fine_fit_tiles); default: the per-stream
     cached one."""
@@ -371,7 +371,7 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
         r.tgt2src = torch.empty((n_tgt_items, 6), dtype=F32, device=dev) if output_tgt2src else None
         r.counts = torch.empty((4,), dtype=I32, device=dev)
         r.sparse_pair_rows = torch.empty((Q,), dtype=I32, device=dev) if assign_type == "assign_then_nn_once" else None
-        r.icp_fragile = torch.empty((Q,), dtype=torch.uint8, device=dev)
+        r.icp_fragile = torch.empty((Q,), dtype=torch.uint8, device=dev) if want_fragile else None
     prm = _lib.FineParams(_MODES[mode], int(remove_low_quality_patch_matches), int(num_min_matches_for_quality_check),
                           float(thres_dist_diff), float(thres_inlier_ratio), int(num_min_fine_match), int(icp_refine),
                           _ASSIGN[assign_type], int(output_tgt2src), float(icp_threshold),

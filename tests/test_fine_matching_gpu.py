@@ -123,10 +123,16 @@ def test_fine_matching_fusion_mode_and_device_median(cuda):
     o = ofm.fine_matching(d["src"].numpy(), d["tgt"].numpy(), d["corr3d"].numpy(), c2, spt_src, spt_tgt, prm)
     r = ops.fine_matching(g["src"], g["tgt"], g["sp_idx"], g["sp_ptr"], g["tp_idx"], g["tp_ptr"], g["tpo"],
                           g["pair_tgt"], corr3d=g["corr3d"], corr2d=torch.from_numpy(c2).to(cuda), mode="fusion",
-                          d_median_resolution=med_dev)
+                          d_median_resolution=med_dev, want_fragile=True)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(r.K.cpu().numpy(), o["K"])
     np.testing.assert_array_equal(r.status.cpu().numpy(), o["status"])
+    # the fused stage's ICP fragility flags (f4l_fine_buffers.icp_fragile): 0 for pairs that were not fitted, a 3-bit OR else;
+    # a pair whose iteration count differs from the oracle's must carry one
+    frag = r.icp_fragile.cpu().numpy()
+    assert frag.shape == o["status"].shape and (frag[o["status"] != 0] == 0).all() and (frag < 8).all()
+    flip = (o["status"] == 0) & (r.iters.cpu().numpy() != o["iters"])
+    assert (frag[flip] != 0).all()
     dense, _, _ = r.rows()
     assert dense.shape[0] == ofm.stack(o["dense"]).shape[0]
 
