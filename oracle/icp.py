@@ -23,6 +23,11 @@ GetRegistrationResultAndCorrespondences) and Eigen::umeyama (with_scaling = fals
   fitness = #corr / #source ; inlier_rmse = sqrt(sum d2 / #corr)  (both 0 when no corr)
 
 All arithmetic is fp64, as in Open3D (the reference promotes its f32 tensors, o3d_tools.py:180-257).
+
+Partial pin: the rigid-update step (umeyama_noscale) agrees to 3e-14 with OpenCV's independent implementation of the
+same algorithm, cv2.estimateAffine3D(force_rotation=True), on 200 random cases including mirrored and coplanar inputs
+(tests/test_oracle_golden.py::test_icp_umeyama_step_matches_opencv).  The loop around it (match, strict d2 < max^2,
+both-delta convergence test) stays a restatement without a third-party check.
 """
 import numpy as np
 from scipy.spatial import cKDTree

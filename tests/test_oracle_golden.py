@@ -193,3 +193,39 @@ def test_merge_matches_reference_function(golden_dir):
     assert 0 < (~masks[2]).sum() < masks[2].size
     merged0, _ = desc_nn.merge_by_priority([levels[0][:0], levels[1], levels[2]])
     np.testing.assert_array_equal(merged0, z["merged_empty0"])
+
+
+def test_icp_umeyama_step_matches_opencv():
+    """Partial pin of the (otherwise unpinned) ICP oracle: its rigid-update step, Eigen::umeyama without scaling as restated
+    in oracle/icp.py, against an independent compiled implementation of the same published algorithm -- OpenCV's
+    cv2.estimateAffine3D(src, dst, force_rotation=True) (calib3d, Umeyama 1991).  The rotation does not depend on the
+    scale estimate, so the rotations must agree to rounding, including improper optimal maps (a mirrored target: the
+    last singular vector is flipped) and rank-deficient covariances (coplanar points)."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "estimateAffine3D"):
+        pytest.skip("this OpenCV build has no estimateAffine3D")
+    from scipy.spatial.transform import Rotation
+    from oracle import icp as oicp
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for case in range(200):
+        n = int(rng.integers(3, 200))
+        src = rng.random((n, 3)) * rng.uniform(0.5, 20) + rng.uniform(-100, 100, 3)
+        R = Rotation.from_rotvec(rng.normal(size=3) * rng.uniform(0, 1.5)).as_matrix()
+        t = rng.normal(size=3)
+        dst = src @ R.T + t + rng.uniform(0, 0.05) * rng.standard_normal((n, 3))
+        if case % 4 == 1:
+            dst = dst * np.array([1.0, 1.0, -1.0])
+        if case % 4 == 2:
+            src[:, 2] = src[0, 2]
+            dst = src @ R.T + t
+        T = oicp.umeyama_noscale(src, dst)
+        try:
+            Rt, _ = cv2.estimateAffine3D(src, dst, force_rotation=True)
+        except TypeError:
+            pytest.skip("cv2.estimateAffine3D without the Umeyama overload")
+        assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-9
+        worst = max(worst, float(np.abs(T[:3, :3] - Rt[:, :3]).max()))
+        # the translation of the no-scale variant follows from the rotation and the means
+        np.testing.assert_allclose(T[:3, 3], dst.mean(0) - T[:3, :3] @ src.mean(0), atol=1e-9)
+    assert worst < 1e-9, worst
