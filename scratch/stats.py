@@ -2,7 +2,7 @@ import torch, numpy as np, sys
 sys.path.insert(0, '.')
 from fusion4landslide_b200 import pipeline, synth
 dev = torch.device('cuda:0')
-d = synth.make_tile(781250, seed=0, device=dev, patch_pts=256)
+d = synth.make_scene(781250, seed=0, device=dev) if "--v1" not in sys.argv else synth.make_tile(781250, seed=0, device=dev, patch_pts=256)
 t = pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"])
 r, med = pipeline.displacement_field(t)
 torch.cuda.synchronize()
