@@ -607,7 +607,7 @@ def run_b200(a):
                        "parallelism": ("tile-sharded x%d; dense DVF rows copied into every GPU's field over NVLink by TMA copy kernels (one "
                                        "per tile, peer memory) on an exchange stream, pipelined with the next step's fits (fields "
                                        "double-buffered by step parity; the last step's copies end inside the timed region); "
-                                       "transforms + row counts all-gathered over NCCL" % world) if pushing
+                                       "transforms + row counts: one NCCL all-gather per step on the same exchange stream" % world) if pushing
                        else ("tile-sharded x%d; dense DVF rows stored into every GPU's field by the producing kernel over "
                              "NVLink (peer memory), transforms + row counts all-gathered over NCCL" % world) if fused
                        else "tile-sharded x%d, NCCL all-gather of transforms + dense DVF" % world,
