@@ -70,6 +70,8 @@ F4L_API void f4l_profile_reset(void);
  *   R (Q,9), t (Q,3) f32; T64 (Q,16) f64 row-major 4x4 or NULL; res (K) residual
  *   ||R s + t - tgt|| or NULL; flag (Q) uint8 or NULL: 1 = degenerate (K<1 or non-finite) ->
  *   identity, mirroring functions.py:62-71.
+ *   Packed inputs are staged with 16-byte-granular bulk copies: up to 12 bytes before the first and after the last
+ *   element of src / tgt / w are read (never used) -- always inside a 16-byte line that holds valid bytes of the array.
  */
 #define F4L_KABSCH_PROCRUSTES 0
 #define F4L_KABSCH_F2S3 1
