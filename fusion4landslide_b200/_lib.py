@@ -48,7 +48,7 @@ class FineBuffers(ctypes.Structure):
         ("dense", c_void_p), ("sparse", c_void_p), ("tgt2src", c_void_p), ("counts", c_void_p),
         ("n_peers", c_i32), ("peer_dense", c_void_p * MAX_PEERS),
         ("sparse_pair_rows", c_void_p), ("median_ready_event", c_void_p), ("phases", c_i32),
-        ("icp_fragile", c_void_p),
+        ("icp_fragile", c_void_p), ("corr3d_tgt", c_void_p), ("corr2d_tgt", c_void_p),
     ]
 
 
@@ -114,6 +114,7 @@ SIGNATURES = {
     "f4l_segment_attention_pool": (c_int, [P, P, P, P, c_i32, c_i32, c_f32, c_i32, P, P]),
     "f4l_segment_mean": (c_int, [P, P, c_i32, c_i32, P, P]),
     "f4l_host_expand_sparse": (ctypes.c_longlong, [P, P, c_i32, P, c_i32]),
+    "f4l_host_pack_corr_targets": (None, [P, ctypes.c_int64, P, c_i32]),
 }
 
 

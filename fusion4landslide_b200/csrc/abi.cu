@@ -110,6 +110,27 @@ extern "C" void f4l_profile_reset(void) {
 #include <thread>
 #include <vector>
 
+extern "C" void f4l_host_pack_corr_targets(const int64_t* h_corr, int64_t n, int32_t* h_out, int32_t n_threads) {
+    if (!h_corr || !h_out || n <= 0) return;
+    int nt = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+    if (n < 65536) nt = 1;
+    auto work = [&](int t) {
+        const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t v = h_corr[2 * i + 1];
+            h_out[i] = (v >= 0 && v <= 0x7fffffffLL) ? (int32_t)v : -1;
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+}
+
 extern "C" long long f4l_host_expand_sparse(const float* h_once, const int32_t* h_pair_rows, int32_t Q, float* h_out,
                                             int32_t n_threads) {
     if (!h_once || !h_pair_rows || !h_out || Q <= 0) return 0;

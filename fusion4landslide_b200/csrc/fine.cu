@@ -17,7 +17,9 @@
 #define FINE_MODE_FUSION 2
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int warp_compact_rows(const int64_t* __restrict__ corr, const int32_t* __restrict__ sp_idx,
+// corr: the reference's (n_src,2) int64 table, or NULL with corr32 = its column 1 as int32
+__device__ __forceinline__ int warp_compact_rows(const int64_t* __restrict__ corr, const int32_t* __restrict__ corr32,
+                                                 const int32_t* __restrict__ sp_idx,
                                                  int s0, int ns, const int32_t* __restrict__ tgt_patch_of_point,
                                                  int want_patch, int n_tgt, int lane, int32_t* __restrict__ cs,
                                                  int32_t* __restrict__ ct, int base) {
@@ -31,7 +33,7 @@ __device__ __forceinline__ int warp_compact_rows(const int64_t* __restrict__ cor
         bool ok = false;
         if (i < ns) {
             p = sp_idx[s0 + i];
-            t = corr[2 * (size_t)p + 1];
+            t = corr ? corr[2 * (size_t)p + 1] : (long long)corr32[p];
             ok = t >= 0 && t < n_tgt && tgt_patch_of_point[t] == want_patch;
         }
         const unsigned m = __ballot_sync(F4L_FULL, ok);
@@ -50,7 +52,8 @@ k_select_corr(const int64_t* __restrict__ corr3d, const int64_t* __restrict__ co
               const int32_t* __restrict__ sp_idx, const int32_t* __restrict__ sp_ptr,
               const int32_t* __restrict__ tgt_patch_of_point, const int32_t* __restrict__ pair_tgt_patch,
               int n_tgt, int Q, int mode, int32_t* __restrict__ cs, int32_t* __restrict__ ct,
-              int32_t* __restrict__ kstart, int32_t* __restrict__ K) {
+              int32_t* __restrict__ kstart, int32_t* __restrict__ K, const int32_t* __restrict__ corr3d_tgt,
+              const int32_t* __restrict__ corr2d_tgt) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
@@ -58,8 +61,8 @@ k_select_corr(const int64_t* __restrict__ corr3d, const int64_t* __restrict__ co
     const int slot = (mode == FINE_MODE_FUSION ? 2 : 1) * s0;
     const int want = pair_tgt_patch[q];
     int w = slot;
-    if (mode != FINE_MODE_2D) w = warp_compact_rows(corr3d, sp_idx, s0, ns, tgt_patch_of_point, want, n_tgt, lane, cs, ct, w);
-    if (mode != FINE_MODE_3D) w = warp_compact_rows(corr2d, sp_idx, s0, ns, tgt_patch_of_point, want, n_tgt, lane, cs, ct, w);
+    if (mode != FINE_MODE_2D) w = warp_compact_rows(corr3d, corr3d_tgt, sp_idx, s0, ns, tgt_patch_of_point, want, n_tgt, lane, cs, ct, w);
+    if (mode != FINE_MODE_3D) w = warp_compact_rows(corr2d, corr2d_tgt, sp_idx, s0, ns, tgt_patch_of_point, want, n_tgt, lane, cs, ct, w);
     if (lane == 0) {
         kstart[q] = slot;
         K[q] = w - slot;
@@ -814,8 +817,8 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
     }
     F4L_REQUIRE(bf->src_pts && bf->tgt_pts && bf->sp_idx && bf->sp_ptr && bf->tp_idx && bf->tp_ptr &&
                     bf->tgt_patch_of_point && bf->pair_tgt_patch, "null input");
-    F4L_REQUIRE(prm->mode == FINE_MODE_2D || bf->corr3d, "corr3d is null");
-    F4L_REQUIRE(prm->mode == FINE_MODE_3D || bf->corr2d, "corr2d is null");
+    F4L_REQUIRE(prm->mode == FINE_MODE_2D || bf->corr3d || bf->corr3d_tgt, "corr3d and corr3d_tgt are null");
+    F4L_REQUIRE(prm->mode == FINE_MODE_3D || bf->corr2d || bf->corr2d_tgt, "corr2d and corr2d_tgt are null");
     F4L_REQUIRE(bf->T && bf->T64 && bf->status && bf->K && bf->fitness && bf->rmse && bf->iters &&
                     bf->ratio_inlier && bf->dist_mean && bf->dense && bf->sparse, "null output");
     F4L_REQUIRE(!prm->output_tgt2src || bf->tgt2src, "tgt2src is null");
@@ -840,7 +843,7 @@ extern "C" int f4l_fine_matching(const f4l_fine_params* prm, const f4l_fine_buff
         f4l_mark("k_select_corr", st);
         k_select_corr<<<f4l_div_up(Q, 4), 128, 0, st>>>(bf->corr3d, bf->corr2d, bf->sp_idx, bf->sp_ptr,
                                                        bf->tgt_patch_of_point, bf->pair_tgt_patch, bf->n_tgt, Q,
-                                                       prm->mode, w.cs, w.ct, w.kstart, bf->K);
+                                                       prm->mode, w.cs, w.ct, w.kstart, bf->K, bf->corr3d_tgt, bf->corr2d_tgt);
     }
     if (phases & F4L_FINE_FIT_SMALL) {
         const int grid_w = f4l_div_up(Q, FITW_WARPS) < 148 * 32 / FITW_WARPS ? f4l_div_up(Q, FITW_WARPS) : 148 * 32 / FITW_WARPS;

@@ -344,7 +344,8 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
                  num_min_fine_match=10, icp_refine=True, assign_type="assign_then_nn",
                  output_tgt2src=False, icp_threshold=0.1, median_max_resolution=0.1,
                  d_median_resolution=None, icp_max_iter=30, n_src_items=None, n_tgt_items=None, out=None,
-                 peer_dense=None, median_event=None, own_workspace=False, want_fragile=False):
+                 peer_dense=None, median_event=None, own_workspace=False, want_fragile=False,
+                 corr3d_tgt=None, corr2d_tgt=None):
     """Builds the FineCall of one tile (see fine_matching for the arguments).  own_workspace: allocate a workspace that
     belongs to this call (needed when the phases of several tiles interleave: fine_fit_tiles); default: the per-stream
     cached one."""
@@ -394,6 +395,11 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
     frag = getattr(r, "icp_fragile", None)
     if frag is not None:
         bf.icp_fragile = ptr(frag, torch.uint8)
+    # column 1 of the correspondence tables as int32 (n_src): used when the int64 (n_src,2) table is not handed in
+    if corr3d is None and corr3d_tgt is not None:
+        bf.corr3d_tgt = ptr(corr3d_tgt, I32)
+    if corr2d is None and corr2d_tgt is not None:
+        bf.corr2d_tgt = ptr(corr2d_tgt, I32)
     if peer_dense:
         if len(peer_dense) > _lib.MAX_PEERS:
             raise _lib.F4LError("at most %d peers" % _lib.MAX_PEERS)
@@ -405,7 +411,7 @@ def fine_prepare(src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_
     c.result, c.prm, c.bf, c.device = r, prm, bf, dev
     c.ws = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev) if own_workspace else _workspace(nbytes, dev)
     c._keep = (src_pts, tgt_pts, sp_idx, sp_ptr, tp_idx, tp_ptr, tgt_patch_of_point, pair_tgt_patch, corr3d, corr2d,
-               d_median_resolution, median_event)
+               d_median_resolution, median_event, corr3d_tgt, corr2d_tgt)
     return c
 
 
@@ -490,6 +496,22 @@ def dips_patches(index, query64, num_points=256, ranks=None, seed=0, want_lrf=Fa
     if want_lrf:
         return patches, count, lrf
     return patches, count
+
+
+def host_pack_corr_targets(corr, out=None, n_threads=2):
+    """HOST tensors: column 1 of an (n,2) int64 correspondence table as int32 (n) -- what the fused stage reads of it
+    (`corr3d_tgt` / `corr2d_tgt`); 4 instead of 16 bytes per source point cross PCIe.  `out`: a pinned (n) int32 buffer."""
+    if corr.is_cuda or (out is not None and out.is_cuda):
+        raise F4LError("host_pack_corr_targets works on host tensors")
+    if corr.dtype != torch.int64 or corr.dim() != 2 or corr.shape[1] != 2 or not corr.is_contiguous():
+        raise F4LError("corr must be a contiguous (n,2) int64 tensor")
+    n = int(corr.shape[0])
+    if out is None:
+        out = torch.empty((n,), dtype=I32)
+    if out.dtype != I32 or out.numel() < n or not out.is_contiguous():
+        raise F4LError("out must be a contiguous int32 tensor of at least n elements")
+    lib().f4l_host_pack_corr_targets(corr.data_ptr(), n, out.data_ptr(), int(n_threads))
+    return out[:n]
 
 
 def host_expand_sparse(once, pair_rows, out, n_threads=4):

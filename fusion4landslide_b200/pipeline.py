@@ -300,12 +300,24 @@ class HostPipeline:
     back per tile (a stream-local synchronisation) so that only the rows that exist cross PCIe."""
 
     def __init__(self, host_tiles, cfg=None, device="cuda:0", n_streams=4, want_sparse=True, sparse_once=False,
-                 expand_threads=8):
+                 expand_threads=8, compact_corr=False, pack_threads=4):
         """sparse_once: the reference appends every pair's sparse rows twice (base.py:3430,3436); with this option
         the kernels emit them once and host threads restore the doubled layout while later tiles are in flight
         (same bytes in the returned tensors, a third less device->host traffic).  OFF by default: measured on the
         B200 box the DMA engines move the second copy at 56 GB/s while host threads rebuild it at ~14 GB/s
         (tools/exp_e2e.py: 25.2 ms vs 22.6 ms per 16 tiles) -- it only pays on hosts with a slow PCIe link."""
+        # compact_corr: the fused stage reads only column 1 of the (n,2) int64 correspondence tables; host threads repack
+        # it to int32 (n) into pinned buffers while earlier tiles are in flight, and 4 instead of 16 bytes per source
+        # point cross PCIe (the conversion is part of run(), i.e. inside whatever the caller times)
+        self.compact_corr = bool(compact_corr)
+        self.pack_pool = None
+        self.corr32 = []
+        if self.compact_corr:
+            import concurrent.futures
+            self.pack_pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, int(pack_threads)))
+            for ht in host_tiles:
+                self.corr32.append({k: torch.empty((ht.t[k].shape[0],), dtype=torch.int32).pin_memory()
+                                    for k in ("corr3d", "corr2d") if ht.t.get(k) is not None})
         self.host_tiles = host_tiles
         self.cfg = cfg or FineConfig()
         self.sparse_once = bool(sparse_once and want_sparse and self.cfg.fine_kwargs().get("assign_type") == "assign_then_nn")
@@ -343,20 +355,34 @@ class HostPipeline:
         kw = dict(self.cfg.fine_kwargs())
         if self.sparse_once:
             kw["assign_type"] = "assign_then_nn_once"
+        packs = []
+        if self.compact_corr:                              # all repacks are queued now; tile i waits for its own only
+            for i, ht in enumerate(self.host_tiles):
+                packs.append({k: self.pack_pool.submit(ops.host_pack_corr_targets, ht.t[k], buf, 1)
+                              for k, buf in self.corr32[i].items()})
         for i, ht in enumerate(self.host_tiles):
             st = self.streams[i % len(self.streams)]
             with torch.cuda.stream(st):
                 t = TileInputs()
                 for k in TileInputs.__slots__:
                     setattr(t, k, None)
+                c32 = {}
                 for k, v in ht.t.items():
-                    setattr(t, k, v.to(self.dev, non_blocking=True))
+                    if self.compact_corr and k in self.corr32[i]:
+                        packs[i][k].result()
+                        v = self.corr32[i][k]
+                        c32[k] = v.to(self.dev, non_blocking=True)
+                    else:
+                        setattr(t, k, v.to(self.dev, non_blocking=True))
                     h2d += v.numel() * v.element_size()
                 t.n_src_items, t.n_tgt_items, t.n_pairs = ht.meta
                 med = ops.median_resolution(t.src, t.tgt)
                 r = ops.fine_matching(t.src, t.tgt, t.sp_idx, t.sp_ptr, t.tp_idx, t.tp_ptr, t.tgt_patch_of_point,
                                       t.pair_tgt_patch, corr3d=t.corr3d, corr2d=t.corr2d, d_median_resolution=med,
-                                      n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items, **kw)
+                                      n_src_items=t.n_src_items, n_tgt_items=t.n_tgt_items,
+                                      corr3d_tgt=c32.get("corr3d"), corr2d_tgt=c32.get("corr2d"), **kw)
+                t.corr3d, t.corr2d = (c32.get("corr3d") if t.corr3d is None else t.corr3d,
+                                      c32.get("corr2d") if t.corr2d is None else t.corr2d)   # kept alive with the tile
                 o = self.out[i]
                 o["counts"].copy_(r.counts, non_blocking=True)
                 if self.sparse_once:

@@ -253,6 +253,10 @@ typedef struct f4l_fine_buffers {
                                     FIT_LARGE | FINISH on the same buffers and workspace */
     uint8_t* icp_fragile;        /* (Q) or NULL: OR of F4L_ICP_FRAGILE_* per fitted pair (0 for the others), tie_eps 1e-9 --
                                     the tie[Q] flag of f4l_patch_icp_ex for the fused stage */
+    const int32_t* corr3d_tgt;   /* (n_src) or NULL: column 1 of corr3d as int32 (target index of source point p, -1 = none),
+                                    read when corr3d is NULL.  The stage only ever reads that column; a host caller ships 4
+                                    instead of 16 bytes per source point over PCIe (f4l_host_pack_corr_targets) */
+    const int32_t* corr2d_tgt;   /* the same for corr2d */
 } f4l_fine_buffers;
 
 #define F4L_FINE_SELECT 1      /* F2: correspondence selection                       (k_select_corr) */
@@ -281,6 +285,10 @@ F4L_API int f4l_fine_fit_tiles(const f4l_fine_params* h_params, const f4l_fine_b
  * assign_type 2 -- every kept row once, h_pair_rows[q] rows for pair q, pairs back to back -- and restores the
  * reference layout on the host: out = [rows of pair 0][rows of pair 0][rows of pair 1][rows of pair 1]...
  * h_out holds 2 * sum(h_pair_rows) rows of 6 floats.  Uses up to n_threads host threads.  Returns the rows written. */
+/* HOST function: h_out[i] = column 1 of the (n,2) int64 correspondence table h_corr as int32; entries outside
+ * [0, 2^31) become -1 (the stage treats every negative target as "no correspondence").  Up to n_threads host threads. */
+F4L_API void f4l_host_pack_corr_targets(const int64_t* h_corr, int64_t n, int32_t* h_out, int32_t n_threads);
+
 F4L_API long long f4l_host_expand_sparse(const float* h_once, const int32_t* h_pair_rows, int32_t Q, float* h_out,
                                  int32_t n_threads);
 

@@ -277,6 +277,27 @@ def test_host_pipeline_sparse_once_equals_doubled(cuda):
             assert torch.equal(x[k], y[k]), k
 
 
+def test_host_pipeline_compact_corr_equals_int64_tables(cuda):
+    """HostPipeline(compact_corr=True): column 1 of the int64 correspondence tables repacked to int32 on the host
+    (f4l_host_pack_corr_targets) and read through f4l_fine_buffers.corr3d_tgt -- same results, fewer bytes uploaded."""
+    from fusion4landslide_b200 import ops, pipeline, synth
+    tiles = []
+    for s in range(3):
+        d = synth.make_tile(30_000 + 5000 * s, seed=50 + s, device=cuda, patch_pts=200)
+        tiles.append(pipeline.prepare_tile(d["src"], d["tgt"], d["label_src"], d["label_tgt"], d["corr3d"]))
+    hts = [pipeline.HostTile(t) for t in tiles]
+    a, ua, _ = pipeline.HostPipeline(hts, None, cuda, n_streams=2).run()
+    b, ub, _ = pipeline.HostPipeline(hts, None, cuda, n_streams=2, compact_corr=True, pack_threads=2).run()
+    assert ub < ua
+    for x, y in zip(a, b):
+        assert x["dense"].shape[0] > 0
+        for k in ("dense", "sparse", "T", "status", "median_resolution"):
+            assert torch.equal(x[k], y[k]), k
+    # the host helper: out-of-range targets become -1
+    c = torch.tensor([[0, 5], [1, -1], [2, 2 ** 40], [3, 2 ** 31 - 1], [4, -7]], dtype=torch.int64)
+    assert ops.host_pack_corr_targets(c).tolist() == [5, -1, -1, 2 ** 31 - 1, -1]
+
+
 def test_map_corr_2d_to_3d_golden(cuda, golden_dir):
     """2D match -> 3D point lifting (base.py:387-472) against the reference's own output.  Index / mask differences
     are allowed only where a hop is a documented tie: two candidates within 1e-6 (relative, squared pixel distance)
